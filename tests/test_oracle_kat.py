@@ -1,0 +1,274 @@
+"""Pins the CPU oracle (oracle/vpm_oracle.c) with known-answer tests and a scipy twin.
+
+The reference holds no golden vectors for the hot path, so these KATs are what
+stands behind the oracle: partition of unity, Galerkin stencils, clamped/Dirichlet basis shape,
+an analytic Poisson mode, Maxwellian projection, the restated reference test
+(test/projections_tests.jl) and conservation identities of the LB operators.
+"""
+import numpy as np
+import pytest
+from scipy.interpolate import BSpline
+
+
+def periodic_design_row(lo, hi, K, nh, x):
+    """scipy twin of basis(x): dense row of the nh periodic basis functions at x."""
+    h = (hi - lo) / nh
+    L = hi - lo
+    xr = lo + np.mod(x - lo, L)
+    row = np.zeros(nh)
+    # extended uniform knot vector covering [lo - K h, hi + K h]
+    t = lo + h * np.arange(-K, nh + K + 1)
+    for i in range(-K, nh):  # function with support [t_i, t_{i+K}]
+        kn = lo + h * np.arange(i, i + K + 1)
+        b = BSpline.basis_element(kn, extrapolate=False)
+        val = b(xr)
+        if np.isfinite(val):
+            row[i % nh] += val
+    return row
+
+
+@pytest.mark.parametrize("K", [2, 3, 4, 5, 6])
+def test_kat1_partition_of_unity_and_scipy_twin(oracle, K):
+    rng = np.random.default_rng(1)
+    lo, hi, nh = -0.7, 2.4, 11
+    xs = oracle.XSpace(lo, hi, K, nh)
+    for x in rng.uniform(lo - 7.0, hi + 7.0, 40):
+        c, b = xs.basis(x)
+        assert abs(b.sum() - 1.0) < 1e-14
+        assert (b >= -1e-16).all()
+        row = np.zeros(nh)
+        for j in range(K):
+            row[(c - K + 1 + j) % nh] += b[j]
+        np.testing.assert_allclose(row, periodic_design_row(lo, hi, K, nh, x), atol=2e-13)
+    x = rng.uniform(lo - 5, hi + 5, 5000)
+    w = rng.uniform(0.5, 1.5, 5000)
+    rhs = xs.deposit(x, w)
+    assert abs(rhs.sum() - w.sum()) < 1e-14 * np.sqrt(x.size) * w.sum()
+
+
+def test_kat2_galerkin_stencils(oracle):
+    # order 3, 4, 5 uniform periodic stencils (exact rationals for 3 and 4)
+    h = 0.37
+    nh = 16
+    cases = {
+        3: (np.array([66, 26, 1]) / 120.0, np.array([1.0, -1 / 3, -1 / 6])),
+        4: (np.array([2416, 1191, 120, 1]) / 5040.0, np.array([2 / 3, -1 / 8, -1 / 5, -1 / 120])),
+        5: (np.array([0.430417769, 0.243149250, 0.0402557319, 0.00138337743, 2.75573192e-6]),
+            np.array([0.486111111, -0.0305555556, -0.188888889, -0.0234126984, -0.000198412698])),
+    }
+    for K, (m, s) in cases.items():
+        xs = oracle.XSpace(0.0, nh * h, K, nh)
+        M, S = xs.matrices()
+        tol = 1e-13 if K < 5 else 2e-9
+        for d in range(K):
+            np.testing.assert_allclose(M[3, (3 + d) % nh] / h, m[d], rtol=0, atol=tol)
+            np.testing.assert_allclose(S[3, (3 + d) % nh] * h, s[d], rtol=0, atol=tol)
+        np.testing.assert_allclose(M, M.T, atol=1e-15)
+        np.testing.assert_allclose(S.sum(axis=1), 0.0, atol=1e-12)
+        np.testing.assert_allclose(M.sum(axis=1), h, atol=1e-14)
+
+
+def test_kat3_clamped_dirichlet_basis(oracle):
+    vs = oracle.VSpace(-10.0, 10.0, 41, 4, dirichlet=True)
+    assert vs.nv == 41
+    M = vs.mass()
+    band = max(abs(i - j) for i in range(41) for j in range(41) if abs(M[i, j]) > 1e-15)
+    assert band == 3
+    assert abs(np.linalg.cond(M) - 20.5) < 0.5
+    # scipy twin for the clamped basis (full, 43 functions)
+    K, nk = 4, 41
+    br = np.linspace(-10, 10, nk)
+    T = np.r_[[br[0]] * (K - 1), br, [br[-1]] * (K - 1)]
+    full = oracle.VSpace(-10.0, 10.0, 41, 4, dirichlet=False)
+    assert full.nv == 43
+    rng = np.random.default_rng(2)
+    for v in np.r_[rng.uniform(-10, 10, 60), -10.0, 10.0, -9.99, 9.99, 0.0, 0.5]:
+        dm = BSpline.design_matrix(np.array([v]), T, K - 1).toarray()[0]
+        c, b = full.basis(v)
+        row = np.zeros(43)
+        row[c:c + K] = b
+        np.testing.assert_allclose(row, dm, atol=1e-14)
+        # derivative twin
+        c, db = full.basis(v, deriv=1)
+        drow = np.zeros(43)
+        drow[c:c + K] = db
+        ref = np.array([BSpline(T, np.eye(43)[i], K - 1)(v, 1) for i in range(43)])
+        if abs(v) < 10.0:
+            np.testing.assert_allclose(drow, ref, atol=1e-12)
+    # scipy mass matrix by Gauss quadrature
+    xq, wq = np.polynomial.legendre.leggauss(K)
+    Mref = np.zeros((43, 43))
+    for a, b_ in zip(br[:-1], br[1:]):
+        xx = 0.5 * (a + b_) + 0.5 * (b_ - a) * xq
+        D = BSpline.design_matrix(xx, T, K - 1).toarray()
+        Mref += D.T @ (D * (0.5 * (b_ - a) * wq)[:, None])
+    np.testing.assert_allclose(full.mass(), Mref, atol=1e-14)
+    np.testing.assert_allclose(M, Mref[1:-1, 1:-1], atol=1e-14)
+
+
+@pytest.mark.parametrize("K,nh", [(3, 32), (4, 32), (5, 64)])
+def test_kat4_poisson_mode(oracle, K, nh):
+    # rho = 1 + eps cos(kappa x); -phi'' = rho - <rho>  => phi = eps cos(kappa x)/kappa^2
+    kappa, eps = 0.5, 0.01
+    L = 2 * np.pi / kappa
+    xs = oracle.XSpace(0.0, L, K, nh)
+    h = L / nh
+    # rhs_i = \int rho B_i dx by fine Gauss quadrature on each cell
+    xq, wq = np.polynomial.legendre.leggauss(12)
+    rhs = np.zeros(nh)
+    for c in range(nh):
+        xx = (c + 0.5) * h + 0.5 * h * xq
+        rho = 1 + eps * np.cos(kappa * xx)
+        for x_, r_, w_ in zip(xx, rho, 0.5 * h * wq):
+            cc, b = xs.basis(x_)
+            for j in range(K):
+                rhs[(cc - K + 1 + j) % nh] += w_ * r_ * b[j]
+    phi = xs.poisson_solve(rhs)
+    assert abs(phi.sum()) < 1e-12
+    xt = np.linspace(0, L, 200, endpoint=False) + 0.013
+    err_phi = np.abs(xs.eval(phi, xt) - eps * np.cos(kappa * xt) / kappa**2).max()
+    err_dphi = np.abs(xs.eval(phi, xt, 1) + eps * np.sin(kappa * xt) / kappa).max()
+    assert err_phi < 5 * eps / kappa**2 * (kappa * h) ** K
+    assert err_dphi < 5 * eps / kappa * (kappa * h) ** (K - 1)
+    # sign: kick acceleration -phi' = +eps sin(kappa x)/kappa  (repulsive, vlasov_poisson.jl:65)
+    v = xs.push_kick(phi, xt, np.zeros_like(xt), 1.0)
+    np.testing.assert_allclose(v, eps * np.sin(kappa * xt) / kappa, atol=5 * eps / kappa * (kappa * h) ** (K - 1))
+    # field energy = 1/2 int phi'^2 = eps^2 L /(4 kappa^2)
+    assert abs(xs.field_energy(phi) - eps**2 * L / (4 * kappa**2)) < 1e-3 * eps**2 * L / (4 * kappa**2)
+
+
+def test_kat5_restated_reference_projection_test(oracle):
+    """test/projections_tests.jl:6-34 restated: order 5, 32 knots, 1e6 samples, atol 5e-2."""
+    npart, nknot, order = 1_000_000, 32, 5
+    sigma = 2.0
+    f = lambda x: np.exp(-0.5 * (4 * np.pi * x - 2 * np.pi) ** 2 / sigma**2) * np.sqrt(np.pi * sigma**2) / np.sqrt(2)
+    rng = np.random.default_rng(1234)
+    # rejection sampling of f on (0,1)
+    out = []
+    fmax = f(0.5)
+    while sum(len(o) for o in out) < npart:
+        x = rng.uniform(0, 1, 2 * npart)
+        keep = rng.uniform(0, fmax, x.size) < f(x)
+        out.append(x[keep])
+    x = np.concatenate(out)[:npart]
+    w = np.ones(npart) / npart
+    xs = oracle.XSpace(0.0, 1.0, order, nknot)
+    oracle.set_threads(min(8, oracle.max_threads()))
+    rhs = xs.deposit(x, w)
+    oracle.set_threads(1)
+    rho = xs.mass_solve(rhs)
+    xt = np.arange(0.0, 1.0001, 0.1)
+    # the reference compares the *unnormalised* f against the *normalised* particle density; they
+    # agree within atol because \int f dx = 0.99993 (sigma chosen so); we compare both ways.
+    from scipy.integrate import quad
+    Z = quad(f, 0, 1)[0]
+    got = xs.eval(rho, xt)
+    np.testing.assert_allclose(got[2:-2], f(xt)[2:-2], atol=5e-2)
+    np.testing.assert_allclose(got[2:-2], f(xt)[2:-2] / Z, atol=2e-2)
+
+
+def test_kat7_lb_identities(oracle):
+    rng = np.random.default_rng(5)
+    N = 20000
+    vs = oracle.VSpace(-10.0, 10.0, 41, 4)
+    v = rng.standard_normal(N)
+    w = np.ones(N) / N
+    coef = vs.project(v, w)
+    # projected spline approximates the unit Maxwellian
+    vt = np.linspace(-4, 4, 33)
+    assert np.abs(vs.eval(coef, vt) - np.exp(-vt**2 / 2) / np.sqrt(2 * np.pi)).max() < 3e-2
+    # scipy twin of projection: M c = rhs
+    K, nk = 4, 41
+    br = np.linspace(-10, 10, nk)
+    T = np.r_[[br[0]] * (K - 1), br, [br[-1]] * (K - 1)]
+    D = BSpline.design_matrix(v, T, K - 1).toarray()[:, 1:-1]
+    rhs = D.T @ w
+    np.testing.assert_allclose(vs.deposit(v, w), rhs, atol=1e-15)
+    np.testing.assert_allclose(coef, np.linalg.solve(vs.mass(), rhs), rtol=0, atol=1e-13)
+    # spline + derivative evaluation twin
+    spl = BSpline(T, np.r_[0.0, coef, 0.0], K - 1)
+    np.testing.assert_allclose(vs.eval(coef, vt), spl(vt), atol=1e-14)
+    np.testing.assert_allclose(vs.eval(coef, vt, 1), spl(vt, 1), atol=1e-13)
+    # moments twin (unweighted sums, density.jl:45,48)
+    m5 = vs.moments(coef, v)
+    f, df = spl(v), spl(v, 1)
+    np.testing.assert_allclose(m5, [f.sum(), (v * f).sum(), (v * v * f).sum(), df.sum(), (v * df).sum()], rtol=1e-11, atol=1e-9)
+    # KAT-8 linearity: sum_p m(v_p) f(v_p) = c . r^m
+    np.testing.assert_allclose(m5[1], coef @ (D.T @ v), rtol=1e-11, atol=1e-10)
+    # CLB: with A from compute_coefficients, sum vdot = 0 and sum v vdot = 0 exactly (algebraically)
+    vdot, _, A = vs.lb_rhs(v, w, nu=1.3, conservative=True)
+    np.testing.assert_allclose(A, oracle.clb_coefficients(m5), rtol=1e-12)
+    assert abs(vdot.sum()) < 1e-9 * np.abs(vdot).sum()
+    assert abs((v * vdot).sum()) < 1e-9 * np.abs(v * vdot).sum()
+    # plain LB does not conserve energy identically
+    vdot_lb, _, _ = vs.lb_rhs(v, w, nu=1.3, conservative=False)
+    np.testing.assert_allclose(vdot_lb, -1.3 * (df + v * f), rtol=1e-11, atol=1e-12)
+    # RK438 conservation over a few steps (scripts/lenard_bernstein_conservative.jl:49-50)
+    v2, d = vs.rk438(v, w, 1.0, 1e-2, 5, conservative=True)
+    assert abs(d[-1, 0] - d[0, 0]) < 1e-9 * N
+    assert abs(d[-1, 1] - d[0, 1]) / d[0, 1] < 1e-8
+
+
+def test_rk438_order_and_tableau(oracle):
+    """RK438 restatement has order 4: halve dt => error / 16 (against a dt/8 run)."""
+    rng = np.random.default_rng(11)
+    N = 4000
+    vs = oracle.VSpace(-10.0, 10.0, 41, 4)
+    v0 = np.r_[rng.standard_normal(N // 2) + 2, rng.standard_normal(N // 2) - 2]
+    w = np.ones(N) / N
+    T = 0.2
+    ref, _ = vs.rk438(v0, w, 1.0, T / 32, 32, diag=False)
+    e1 = np.abs(vs.rk438(v0, w, 1.0, T / 2, 2, diag=False)[0] - ref).max()
+    e2 = np.abs(vs.rk438(v0, w, 1.0, T / 4, 4, diag=False)[0] - ref).max()
+    assert 8 < e1 / e2 < 40
+
+
+def test_strang_paths_consistency(oracle):
+    rng = np.random.default_rng(3)
+    N, K, nh = 3000, 4, 16
+    L = 2 * np.pi / 0.3
+    xs = oracle.XSpace(0.0, L, K, nh)
+    x, v, w = oracle.sample_bump_on_tail(N)
+    # self-consistent: one step == manual composition of operator calls
+    x1, v1, d, phi = xs.strang_selfconsistent(x, v, w, 0.1, 1)
+    xa = oracle.push_drift(x, v, 0.05)
+    ph = xs.poisson_solve(xs.deposit(xa, w))
+    va = xs.push_kick(ph, xa, v, 0.1)
+    xb = oracle.push_drift(xa, va, 0.05)
+    np.testing.assert_array_equal(x1, xb)
+    np.testing.assert_array_equal(v1, va)
+    np.testing.assert_array_equal(phi, ph)
+    assert d.shape == (2, 3) and d[0, 1] > 0
+    # Galerkin spline PIC is not momentum-conserving; the drift over one step is only noise-small
+    assert abs(d[1, 2] - d[0, 2]) < 1e-3 * abs(d[0, 2])
+    # frozen: field never changes
+    xf, vf, phf = xs.strang_frozen(x, v, x, w, 0.1, 3)
+    np.testing.assert_array_equal(phf, xs.poisson_solve(xs.deposit(x, w)))
+    # chi scaling (ScaledField, electric_field.jl:26-29; dt_eff = dt*chi, vlasov_poisson.jl:80)
+    x2, v2, d2, _ = xs.strang_selfconsistent(x, v, w, 0.1, 1, chi=2.0)
+    va2 = xs.push_kick(xs.poisson_solve(xs.deposit(oracle.push_drift(x, v, 0.1), w)), oracle.push_drift(x, v, 0.1), v, 0.2, 0.25)
+    np.testing.assert_array_equal(v2, va2)
+
+
+def test_samplers(oracle):
+    from scipy.stats import norm, kstest
+    u = np.array([oracle.uniform(7, i, 0) for i in range(20000)])
+    assert kstest(u, "uniform").pvalue > 1e-3
+    for p in [1e-300, 1e-20, 1e-5, 0.01, 0.3, 0.5, 0.77, 0.999, 1 - 1e-12]:
+        assert abs(oracle.norminv(p) - norm.ppf(p)) <= 2e-15 * max(1.0, abs(norm.ppf(p)))
+    N = 200000
+    x, v, w = oracle.sample_bump_on_tail(N)
+    L = 2 * np.pi / 0.3
+    assert x.min() >= 0 and x.max() < L
+    np.testing.assert_allclose(w.sum(), L, rtol=1e-12)
+    # x-marginal 1 - eps cos(kappa x): first Fourier mode amplitude = -eps/2
+    assert abs(np.mean(np.cos(0.3 * x)) + 0.015) < 5e-3
+    # v: mixture mean = alpha*v0, var = (1-a) + a(sigma^2+v0^2) - (a v0)^2
+    assert abs(v.mean() - 0.45) < 2e-2
+    # slabs reproduce the global stream (multi-GPU sharding contract)
+    xa, va, wa = oracle.sample_bump_on_tail(1000, offset=5000, Ntotal=N)
+    np.testing.assert_array_equal(xa, x[5000:6000])
+    np.testing.assert_array_equal(va, v[5000:6000])
+    x, v, w = oracle.sample_maxwellian(N, shift=2.0, doubled=True, xlo=-10, xhi=10)
+    assert abs(v[: N // 2].mean() - 2) < 2e-2 and abs(v[N // 2:].mean() + 2) < 2e-2
+    np.testing.assert_allclose(w, 1.0 / N)
