@@ -1,0 +1,84 @@
+"""CPU-side checks: the C-ABI library loads, exports every symbol include/vpm_b200.h declares, the ctypes
+table matches the header, compute entry points fail loudly without a GPU, and the oracle reproduces the
+committed golden fixtures (regression pin of the checker)."""
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "vpm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vpm_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    import vpm_b200
+    return vpm_b200
+
+
+def test_library_exports_every_declared_symbol(built):
+    import ctypes
+    lib = ctypes.CDLL(built.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 50
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/vpm_b200.h but not exported"
+    assert sorted(built._cabi.SIGNATURES) == syms, "ctypes table and header disagree"
+    assert lib.vpm_version() == 100
+
+
+def test_no_cpu_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(built.VpmError) as e:
+        built.Context(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "vlasovparticlemethods.jl_b200")
+    for path in glob.glob(os.path.join(pkg, "**", "*"), recursive=True):
+        if os.path.isfile(path) and path.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+            txt = open(path, errors="ignore").read()
+            assert "oracle" not in txt.lower(), f"{path} references the oracle"
+
+
+def test_sm100a_only(built):
+    out = os.popen(f"cuobjdump -lelf {built.LIB_PATH} 2>/dev/null").read()
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.parametrize("name", ["vp_k4_n16", "vp_k3_n16_cfg1", "vp_k5_n11_chi"])
+def test_oracle_matches_golden_vp(oracle, name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    xs = oracle.XSpace(0.0, float(g["L"]), int(g["K"]), int(g["nh"]))
+    rhs = xs.deposit(g["x"], g["w"])
+    np.testing.assert_allclose(rhs, g["rhs"], rtol=0, atol=1e-15 * np.abs(g["rhs"]).max() * 10)
+    np.testing.assert_allclose(xs.poisson_solve(rhs), g["phi"], rtol=0, atol=1e-13 * np.abs(g["phi"]).max())
+    x1, v1, diag, _ = xs.strang_selfconsistent(g["x"], g["v"], g["w"], float(g["dt"]), int(g["nsteps"]), chi=float(g["chi"]))
+    np.testing.assert_allclose(x1, g["x1"], rtol=1e-13)
+    np.testing.assert_allclose(v1, g["v1"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(diag, g["diag"], rtol=1e-11)
+
+
+@pytest.mark.parametrize("name", ["lb_k4_n41", "lb_k5_n12"])
+def test_oracle_matches_golden_lb(oracle, name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    vs = oracle.VSpace(-10.0, 10.0, int(g["nknots"]), int(g["K"]))
+    np.testing.assert_allclose(vs.mass(), g["mass"], atol=1e-15)
+    coef = vs.project(g["v"], g["w"])
+    np.testing.assert_allclose(coef, g["coef"], atol=1e-14)
+    np.testing.assert_allclose(vs.lb_rhs(g["v"], g["w"], 0.7, True)[0], g["vdot_clb"], atol=1e-13)
+    v2, d = vs.rk438(g["v"], g["w"], 0.7, float(g["dt"]), int(g["nsteps"]), conservative=True)
+    np.testing.assert_allclose(v2, g["v_clb"], atol=1e-12)

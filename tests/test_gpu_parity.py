@@ -1,0 +1,292 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the host mirror) against the CPU oracle on the
+same seeded inputs and against the committed golden fixtures.
+
+Tolerance: the north star asks for 1e-12 relative, normwise, fp64 (scatter order differs).  `nrm` is that
+normwise relative error.  Everything here needs a B200: `pytest -m gpu`.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-12
+
+
+def nrm(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    d = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (d if d > 0 else 1.0)
+
+
+@pytest.fixture(scope="module")
+def vpm():
+    import vpm_b200
+    vpm_b200.default_context()
+    return vpm_b200
+
+
+def make_particles(vpm, x, v, w):
+    return vpm.ParticleDistribution(1, 1, len(x)).set(x, v, w)
+
+
+# ------------------------------------------------------------------------------------- x-space operators
+@pytest.mark.parametrize("K", [2, 3, 4, 5, 6])
+@pytest.mark.parametrize("nh", [16, 11, 100])
+def test_deposit_solve_gather(vpm, oracle, K, nh):
+    rng = np.random.default_rng(100 * K + nh)
+    n = 50001
+    lo, hi = -1.3, 4.9
+    x = rng.uniform(lo - 40.0, hi + 40.0, n)   # never wrapped in storage (vlasov_poisson.jl:55)
+    v = rng.standard_normal(n)
+    w = rng.uniform(0.2, 1.8, n) / n
+    d = make_particles(vpm, x, v, w)
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((lo, hi), K, nh))
+    xs = oracle.XSpace(lo, hi, K, nh)
+    vpm.projection_(pot, d)
+    rhs_o = xs.deposit(x, w)
+    assert nrm(pot.rhs, rhs_o) < TOL
+    assert abs(pot.rhs.sum() - w.sum()) < 1e-13          # KAT-1 partition of unity
+    vpm.update_(pot)
+    phi_o = xs.poisson_solve(rhs_o)
+    assert nrm(pot.coefficients, phi_o) < 1e-11
+    assert abs(pot.coefficients.sum()) < 1e-12 * np.abs(phi_o).sum() + 1e-18
+    # solve from a given rhs, gathers, energy, mass solve
+    assert nrm(pot.solve(rhs_o), phi_o) < 1e-11
+    xt = rng.uniform(lo - 10, hi + 10, 4097)
+    assert nrm(pot.evaluate(xt, 1, phi_o), xs.eval(phi_o, xt, 1)) < 1e-11
+    assert nrm(pot.evaluate(xt, 0, phi_o), xs.eval(phi_o, xt, 0)) < 1e-11
+    assert abs(pot.energy(phi_o) - xs.field_energy(phi_o)) < 1e-11 * abs(xs.field_energy(phi_o))
+    assert nrm(pot.mass_solve(rhs_o), xs.mass_solve(rhs_o)) < 1e-11
+    M, S = xs.matrices()
+    ms, ss = pot.stencils()
+    for dd in range(-(K - 1), K):
+        if nh > 2 * K:
+            assert abs(ms[dd + K - 1] - M[5, (5 + dd) % nh]) < 1e-14 * xs.h
+            assert abs(ss[dd + K - 1] - S[5, (5 + dd) % nh]) < 1e-13 / xs.h
+
+
+def test_deposit_edge_cases(vpm, oracle):
+    K, nh, lo, hi = 4, 16, 0.0, 2.0
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((lo, hi), K, nh))
+    xs = oracle.XSpace(lo, hi, K, nh)
+    h = (hi - lo) / nh
+    cases = {
+        "empty": np.zeros(0),
+        "single": np.array([0.3]),
+        "odd": np.linspace(-5, 5, 7),
+        "on_knots": lo + h * np.arange(-20, 40, dtype=float),
+        "one_cell": np.full(4099, 0.3) + 1e-3 * np.arange(4099) / 4099,
+        "domain_ends": np.array([lo, hi, np.nextafter(hi, lo), np.nextafter(lo, lo - 1), lo - hi, 2 * hi]),
+    }
+    for name, x in cases.items():
+        w = np.linspace(0.5, 1.5, x.size) if x.size else np.zeros(0)
+        d = make_particles(vpm, x, np.zeros(x.size), w)
+        vpm.projection_(pot, d)
+        ref = xs.deposit(x, w)
+        err = np.abs(pot.rhs - ref).max()
+        assert err <= 1e-13 * max(1.0, np.abs(ref).max()), (name, err)
+
+
+def test_push_operators(vpm, oracle):
+    rng = np.random.default_rng(7)
+    n, K, nh, L = 30000, 4, 16, 2 * np.pi / 0.3
+    x, v, w = oracle.sample_bump_on_tail(n)
+    d = make_particles(vpm, x, v, w)
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), K, nh))
+    xs = oracle.XSpace(0.0, L, K, nh)
+    vpm.s_advection_(d, pot, 0.37)
+    xo = oracle.push_drift(x, v, 0.37)
+    assert nrm(d.get("x"), xo) < TOL
+    vpm.s_acceleration_(d, pot, 0.21)              # update_potential! + kick
+    phi = xs.poisson_solve(xs.deposit(xo, w))
+    vo = xs.push_kick(phi, xo, v, 0.21)
+    assert nrm(d.get("v"), vo) < TOL
+    assert nrm(pot.coefficients, phi) < 1e-11
+    # AoS round trip (Julia 3 x N and 2 x N matrices)
+    z3 = np.vstack([x, v, w])
+    d.upload_aos(z3)
+    np.testing.assert_array_equal(d.download_aos(3), z3)
+    np.testing.assert_array_equal(d.particles.z, z3[:2])
+
+
+# ------------------------------------------------------------------------------------- Strang steppers
+@pytest.mark.parametrize("name", ["vp_k4_n16", "vp_k3_n16_cfg1", "vp_k5_n11_chi"])
+def test_strang_golden(vpm, name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    K, nh, L, dt, ns, chi = int(g["K"]), int(g["nh"]), float(g["L"]), float(g["dt"]), int(g["nsteps"]), float(g["chi"])
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), K, nh))
+    # self-consistent, exact legacy diagnostics
+    d = make_particles(vpm, g["x"], g["v"], g["w"])
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, dt * ns), dt, field="selfconsistent", chi=chi)
+    vpm.run_(m, diag_mode=2)
+    x1, v1, _ = d.get()
+    assert nrm(x1, g["x1"]) < TOL and nrm(v1, g["v1"]) < TOL
+    assert np.abs(m.diagnostics - g["diag"]).max() < 1e-11 * np.abs(g["diag"]).max()
+    # fused one-pass-per-step path (diag_mode 1 and 0) gives the same particles
+    for dm in (1, 0):
+        d2 = make_particles(vpm, g["x"], g["v"], g["w"])
+        m2 = vpm.SplittingMethod(vpm.VlasovPoisson(d2, pot), (0.0, dt * ns), dt, field="selfconsistent", chi=chi)
+        vpm.run_(m2, diag_mode=dm)
+        x2, v2, _ = d2.get()
+        assert nrm(x2, g["x1"]) < TOL and nrm(v2, g["v1"]) < TOL
+        if dm == 1:
+            np.testing.assert_allclose(m2.diagnostics[:, 1:], g["diag"][:, 1:], rtol=1e-11)   # K, M exact
+            np.testing.assert_allclose(m2.diagnostics[0, 0], g["diag"][0, 0], rtol=1e-10)     # W(0) exact
+            assert np.all(m2.diagnostics[:, 0] > 0)
+    # frozen field == the shipped SplittingMethod behaviour
+    d3 = make_particles(vpm, g["x"], g["v"], g["w"])
+    m3 = vpm.SplittingMethod(vpm.VlasovPoisson(d3, pot), (0.0, dt * ns), dt, field="frozen")
+    vpm.run_(m3)
+    x3, v3, _ = d3.get()
+    assert nrm(x3, g["xf"]) < TOL and nrm(v3, g["vf"]) < TOL
+    assert nrm(pot.coefficients, g["phif"]) < 1e-11
+
+
+def test_strang_vs_oracle_long(vpm, oracle):
+    """40 steps, N=2e5: error growth stays far below the tolerance; bitwise run-to-run determinism."""
+    n, K, nh, L = 200001, 4, 16, 2 * np.pi / 0.3
+    x, v, w = oracle.sample_bump_on_tail(n)
+    oracle.set_threads(min(8, oracle.max_threads()))
+    xs = oracle.XSpace(0.0, L, K, nh)
+    xo, vo, do, _ = xs.strang_selfconsistent(x, v, w, 0.1, 40)
+    oracle.set_threads(1)
+    res = []
+    for rep in range(2):
+        d = make_particles(vpm, x, v, w)
+        pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), K, nh))
+        m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 4.0), 0.1, field="selfconsistent")
+        vpm.run_(m, diag_mode=1)
+        res.append(d.get() + (m.diagnostics,))
+    assert nrm(res[0][0], xo) < TOL and nrm(res[0][1], vo) < TOL
+    np.testing.assert_allclose(res[0][3][:, 1:], do[:, 1:], rtol=1e-10)
+    for a, b in zip(res[0], res[1]):
+        np.testing.assert_array_equal(a, b)     # fixed-order reductions: bitwise reproducible
+
+
+def test_strang_step_host(vpm, oracle):
+    n, K, nh, L = 40001, 4, 16, 2 * np.pi / 0.3
+    x, v, w = oracle.sample_bump_on_tail(n)
+    xs = oracle.XSpace(0.0, L, K, nh)
+    d = make_particles(vpm, x, v, w)
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), K, nh))
+    lib = vpm._cabi.lib()
+    zin = np.ascontiguousarray(np.vstack([x, v]).T)
+    zout = np.empty_like(zin)
+    vpm.check(lib.vpm_vp_strang_step_host(pot._h, d._h, zin.ctypes.data, zout.ctypes.data, 0.1, 1.0, 0))
+    xo, vo, _, _ = xs.strang_selfconsistent(x, v, w, 0.1, 1, diag=False)
+    assert nrm(zout[:, 0], xo) < TOL and nrm(zout[:, 1], vo) < TOL
+    # frozen: field from the resident distribution (x0), state z evolves separately
+    z2 = np.ascontiguousarray(np.vstack([xo, vo]).T)
+    vpm.check(lib.vpm_vp_strang_step_host(pot._h, d._h, z2.ctypes.data, zout.ctypes.data, 0.1, 1.0, 1))
+    xf, vf, _ = xs.strang_frozen(xo, vo, x, w, 0.1, 1)
+    assert nrm(zout[:, 0], xf) < TOL and nrm(zout[:, 1], vf) < TOL
+
+
+def test_large_properties(vpm):
+    """Size-independent properties at 2e7 particles (oracle would take too long): partition of unity,
+    exact reversibility of the drift, K/M invariance under a zero-field kick."""
+    n = 20_000_001
+    d = vpm.ParticleDistribution(1, 1, n)
+    bot = vpm.BumpOnTail()
+    vpm.initialize_(d, bot)
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, bot.L), 4, 16))
+    vpm.projection_(pot, d)
+    assert abs(pot.rhs.sum() - bot.L) < 1e-12 * bot.L
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 0.3), 0.1, field="selfconsistent")
+    vpm.run_(m, diag_mode=1)
+    dg = m.diagnostics
+    assert np.all(np.isfinite(dg))
+    # total energy W + K drifts by << 1e-4 over 3 steps at this N; momentum is noise-small
+    E = dg[:, 0] + dg[:, 1]
+    assert abs(E[-1] - E[1]) < 1e-4 * E[1]
+
+
+# ------------------------------------------------------------------------------------- v-space / LB
+@pytest.mark.parametrize("name", ["lb_k4_n41", "lb_k5_n12"])
+def test_lb_golden(vpm, name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    K, nk, dt, ns, nu = int(g["K"]), int(g["nknots"]), float(g["dt"]), int(g["nsteps"]), float(g["nu"])
+    v, w = g["v"], g["w"]
+    sd = vpm.SplineDistribution(1, 1, nk, K, (-10.0, 10.0), "Dirichlet")
+    assert len(sd) == nk + K - 4
+    np.testing.assert_allclose(sd.mass_matrix, g["mass"], atol=1e-14)
+    d = make_particles(vpm, np.zeros(v.size), v, w)
+    fs = vpm.projection(v, d, sd)
+    assert nrm(sd.rhs, g["rhs"]) < TOL
+    assert nrm(fs.coefficients, g["coef"]) < 1e-11
+    assert nrm(sd.mass_solve(g["rhs"]), g["coef"]) < 1e-11
+    assert nrm(fs(v), g["f"]) < 1e-11
+    assert nrm((vpm.Derivative(1) * fs)(v), g["df"]) < 1e-11
+    # f, f' of boundary cells, end points and out-of-domain particles individually
+    np.testing.assert_allclose(fs(v[:6]), g["f"][:6], atol=1e-13 * np.abs(g["f"]).max())
+    m5 = np.array(vpm.compute_f_densities(sd, v) + vpm.compute_df_densities(sd, v))
+    scale = np.array([np.abs(g["f"]).sum(), np.abs(v * g["f"]).sum(), np.abs(v * v * g["f"]).sum(),
+                      np.abs(g["df"]).sum(), np.abs(v * g["df"]).sum()])
+    assert np.all(np.abs(m5 - g["m5"]) < 1e-12 * scale)   # judged relative to sum |.| (SURVEY 8a note)
+    params = {"nu": nu, "idist": d, "fdist": sd}
+    ent = vpm.CollisionEntropy(sd)
+    for cons, key in ((False, "vdot_lb"), (True, "vdot_clb")):
+        model = (vpm.ConservativeLenardBernstein if cons else vpm.LenardBernstein)(d, ent, nu=nu)
+        params["model"] = model
+        vdot = np.zeros(v.size)
+        (vpm.CLB_rhs_ if cons else vpm.LB_rhs_)(vdot, v, params, 0.0)
+        assert nrm(vdot, g[key]) < 1e-10, (cons, nrm(vdot, g[key]))
+    A = vpm.compute_coefficients(sd, d, v)
+    np.testing.assert_allclose(A, g["A"], rtol=1e-8, atol=1e-10)
+    # RK438 steppers
+    for cons, kv, kd in ((False, "v_lb", "d_lb"), (True, "v_clb", "d_clb")):
+        d2 = make_particles(vpm, np.zeros(v.size), v, w)
+        model = (vpm.ConservativeLenardBernstein if cons else vpm.LenardBernstein)(d2, ent, nu=nu)
+        gi = vpm.GeometricIntegrator(model, (0.0, dt * ns), dt)
+        vpm.run_(gi)
+        assert nrm(d2.get("v"), g[kv]) < 1e-11, (cons, nrm(d2.get("v"), g[kv]))
+        np.testing.assert_allclose(gi.diagnostics, g[kd], rtol=1e-11)
+
+
+def test_lb_relaxation_physics(vpm):
+    """KAT-7: CLB conserves sum v and sum v^2 to integrator order; plain LB does not conserve energy."""
+    n = 200000
+    sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
+    ent = vpm.CollisionEntropy(sd)
+    out = {}
+    for cons in (True, False):
+        d = vpm.ParticleDistribution(1, 1, n)
+        vpm.initialize_(d, vpm.DoubleMaxwellian((-10.0, 10.0), 2.0))
+        model = (vpm.ConservativeLenardBernstein if cons else vpm.LenardBernstein)(d, ent, nu=1.0)
+        gi = vpm.GeometricIntegrator(model, (0.0, 0.5), 1e-2)
+        vpm.run_(gi)
+        out[cons] = gi.diagnostics
+    dc, dl = out[True], out[False]
+    assert abs(dc[-1, 0] - dc[0, 0]) < 1e-7 * n
+    assert abs(dc[-1, 1] - dc[0, 1]) / dc[0, 1] < 1e-7
+    assert abs(dl[-1, 1] - dl[0, 1]) / dl[0, 1] > 1e-5
+
+
+def test_samplers_match_cpu_twin(vpm, oracle):
+    n, off, ntot = 100003, 12345, 1_000_000
+    d = vpm.ParticleDistribution(1, 1, n)
+    vpm.initialize_(d, vpm.BumpOnTail(), offset=off, ntotal=ntot)
+    xo, vo, wo = oracle.sample_bump_on_tail(n, offset=off, Ntotal=ntot)
+    x, v, w = d.get()
+    np.testing.assert_allclose(x, xo, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(v, vo, rtol=1e-13, atol=1e-13)
+    np.testing.assert_array_equal(w, wo)
+    vpm.initialize_(d, vpm.DoubleMaxwellian((-10.0, 10.0), 2.0), offset=off, ntotal=ntot)
+    xo, vo, wo = oracle.sample_maxwellian(n, offset=off, Ntotal=ntot, xlo=-10, xhi=10, shift=2.0, doubled=True)
+    x, v, w = d.get()
+    np.testing.assert_allclose(v, vo, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(x, xo, rtol=1e-14, atol=1e-14)
+
+
+def test_errors_are_reported(vpm):
+    with pytest.raises(vpm.VpmError):
+        vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, 1.0), 9, 16))      # order out of range
+    with pytest.raises(vpm.VpmError):
+        vpm.Potential(vpm.PeriodicBasisBSplineKit((1.0, 0.0), 4, 16))      # empty domain
+    with pytest.raises(vpm.VpmError):
+        vpm.SplineDistribution(1, 1, 1, 4, (-1.0, 1.0))
+    with pytest.raises(ValueError):
+        vpm.ParticleDistribution(2, 2, 10)

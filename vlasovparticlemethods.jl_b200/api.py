@@ -1,0 +1,756 @@
+"""Host-side mirror of the VlasovMethods.jl interface for the particle hot path, over the C ABI.
+
+Julia is absent from this image, so the host layer the north star asks for in Julia is
+written in Python with the reference's names, argument meaning and error behaviour; the same calls
+as `ccall`s are in julia/VPMB200.jl.  Julia's `f!` becomes `f_` here.  Nothing in this module
+computes: every operation is one call into libvpm_b200.so (no CPU fallback).
+
+Reference files mirrored (paths relative to the reference checkout):
+  ParticleDistribution      src/distributions/particle_distribution.jl:2-24
+  SplineDistribution        src/distributions/spline_distribution.jl:1-36
+  Potential / projection!   scripts/vlasov_poisson.jl:21, src/projections/potential.jl:2-22
+  projection, moments       src/projections/distribution.jl:35-55, src/projections/density.jl:6-52
+  VlasovPoisson, flows      src/models/vlasov_poisson.jl:2-89
+  LenardBernstein (+cons.)  src/models/lenard_bernstein.jl, src/models/lenard_bernstein_conservative.jl
+  SplittingMethod, run!     src/methods/splitting.jl:2-52 ; GeometricIntegrator: src/methods/geometric_integrator.jl
+  examples / initialize!    src/examples/{normal,bumpontail,doublemaxwellian,uniform}.jl
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import VpmError, check
+
+_vp = C.c_void_p
+
+
+def _lib():
+    return _cabi.lib()
+
+
+def _hp(a):
+    """host pointer of a contiguous float64 array (or None)"""
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+# ------------------------------------------------------------------------------------------------
+# context
+# ------------------------------------------------------------------------------------------------
+class Context:
+    """One per GPU (vpm_ctx).  `stream`: raw cudaStream_t (int) to enqueue on, or None for a private one."""
+
+    def __init__(self, device=0, stream=None):
+        h = _vp()
+        check(_lib().vpm_ctx_create(int(device), _vp(stream) if stream else None, C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().vpm_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(_lib().vpm_sync(self._h))
+
+    @property
+    def launches(self):
+        return int(_lib().vpm_launch_count(self._h))
+
+    def device_info(self):
+        sm, sh, tot = C.c_int(), C.c_int64(), C.c_int64()
+        check(_lib().vpm_device_info(self._h, C.byref(sm), C.byref(sh), C.byref(tot)))
+        return {"sm_count": sm.value, "smem_optin": sh.value, "total_mem": tot.value}
+
+    # multi-GPU: particle slabs + all-reduce of the coefficient vectors
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_char * 128)()
+        check(_lib().vpm_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, nranks, rank, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        check(_lib().vpm_comm_init(self._h, int(nranks), int(rank), buf))
+
+    def comm_destroy(self):
+        check(_lib().vpm_comm_destroy(self._h))
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def set_default_context(ctx):
+    global _default_ctx
+    _default_ctx = ctx
+
+
+class DeviceVector:
+    """Plain device buffer of doubles (vpm_dev_alloc) for integrator states handed to the operators."""
+
+    def __init__(self, ctx, n, data=None):
+        self.ctx, self.n = ctx, int(n)
+        p = _vp()
+        check(_lib().vpm_dev_alloc(ctx._h, self.n, C.byref(p)))
+        self.ptr = p
+        if data is not None:
+            self.upload(data)
+
+    def upload(self, a):
+        a = _f64(a).ravel()
+        assert a.size == self.n
+        check(_lib().vpm_memcpy_h2d(self.ctx._h, self.ptr, _hp(a), self.n))
+
+    def download(self):
+        out = np.empty(self.n)
+        check(_lib().vpm_memcpy_d2h(self.ctx._h, _hp(out), self.ptr, self.n))
+        return out
+
+    def free(self):
+        if getattr(self, "ptr", None) and self.ctx._h:
+            _lib().vpm_dev_free(self.ctx._h, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
+# distributions
+# ------------------------------------------------------------------------------------------------
+class DistributionFunction:
+    """abstract type DistributionFunction{XD,VD} (src/distributions/distribution.jl:2)"""
+
+
+class _ParticleViews:
+    """`.particles` of the reference ParticleDistribution: named row views x, v, w, z of the
+    (xdim+vdim+1) x N matrix (particle_distribution.jl:11-17).  Reads download, writes upload."""
+
+    def __init__(self, dist):
+        self._d = dist
+
+    def __len__(self):
+        return self._d.npart
+
+    @property
+    def x(self):
+        return self._d.get("x")[None, :]
+
+    @x.setter
+    def x(self, val):
+        self._d.set(x=np.asarray(val).reshape(-1))
+
+    @property
+    def v(self):
+        return self._d.get("v")[None, :]
+
+    @v.setter
+    def v(self, val):
+        self._d.set(v=np.asarray(val).reshape(-1))
+
+    @property
+    def w(self):
+        return self._d.get("w")[None, :]
+
+    @w.setter
+    def w(self, val):
+        self._d.set(w=np.asarray(val).reshape(-1))
+
+    @property
+    def z(self):
+        return self._d.download_aos(2)
+
+    @z.setter
+    def z(self, val):
+        self._d.upload_aos(np.asarray(val))
+
+
+class ParticleDistribution(DistributionFunction):
+    """ParticleDistribution(xdim, vdim, npart): device-resident SoA particle store."""
+
+    def __init__(self, xdim, vdim, npart, ctx=None):
+        if xdim != 1 or vdim != 1:
+            raise ValueError("the B200 hot path is 1D1V (VlasovPoisson{1,1}, LenardBernstein{1,1})")
+        self.xdim, self.vdim, self.npart = 1, 1, int(npart)
+        self.ctx = ctx or default_context()
+        h = _vp()
+        check(_lib().vpm_particles_create(self.ctx._h, self.npart, C.byref(h)))
+        self._h = h
+        self.particles = _ParticleViews(self)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self.ctx._h:
+                _lib().vpm_particles_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def size(self):
+        return self.npart
+
+    def __len__(self):
+        return self.npart
+
+    def ptrs(self):
+        x, v, w = _vp(), _vp(), _vp()
+        check(_lib().vpm_particles_ptrs(self._h, C.byref(x), C.byref(v), C.byref(w)))
+        return x, v, w
+
+    def set(self, x=None, v=None, w=None):
+        x = None if x is None else _f64(x)
+        v = None if v is None else _f64(v)
+        w = None if w is None else _f64(w)
+        for a in (x, v, w):
+            if a is not None and a.size != self.npart:
+                raise ValueError("array length does not match the number of particles")
+        check(_lib().vpm_particles_upload_soa(self._h, _hp(x), _hp(v), _hp(w)))
+        return self
+
+    def get(self, which=None):
+        if which is not None:
+            out = np.empty(self.npart)
+            args = {"x": (_hp(out), None, None), "v": (None, _hp(out), None), "w": (None, None, _hp(out))}[which]
+            check(_lib().vpm_particles_download_soa(self._h, *args))
+            return out
+        x, v, w = np.empty(self.npart), np.empty(self.npart), np.empty(self.npart)
+        check(_lib().vpm_particles_download_soa(self._h, _hp(x), _hp(v), _hp(w)))
+        return x, v, w
+
+    def upload_aos(self, z):
+        """z: (ld, N) Julia column-major matrix == C-order (N, ld) array; rows x, v[, w]."""
+        z = np.asarray(z, dtype=np.float64)
+        ld = z.shape[0]
+        if z.ndim != 2 or ld not in (2, 3) or z.shape[1] != self.npart:
+            raise ValueError("expected a (2|3) x N matrix")
+        zz = np.ascontiguousarray(z.T)  # memory order of Julia's column-major ld x N
+        check(_lib().vpm_particles_upload_aos(self._h, _hp(zz), ld))
+        return self
+
+    def download_aos(self, ld=3):
+        zz = np.empty((self.npart, ld))
+        check(_lib().vpm_particles_download_aos(self._h, _hp(zz), ld))
+        return zz.T
+
+
+class SplineDistribution(DistributionFunction):
+    """SplineDistribution(xdim, vdim, nknots, order, domain, bc=:Dirichlet)"""
+
+    def __init__(self, xdim, vdim, nknots, order, domain, bc="Dirichlet", ctx=None):
+        self.ctx = ctx or default_context()
+        self.nknots, self.order, self.domain = int(nknots), int(order), (float(domain[0]), float(domain[1]))
+        self.bc = str(bc).lstrip(":")
+        h = _vp()
+        check(_lib().vpm_vspace_create(self.ctx._h, self.domain[0], self.domain[1], self.nknots, self.order,
+                                       1 if self.bc == "Dirichlet" else 0, C.byref(h)))
+        self._h = h
+        self.nbasis = int(_lib().vpm_vspace_size(h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self.ctx._h:
+                _lib().vpm_vspace_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def size(self):
+        return (self.nbasis,)
+
+    def __len__(self):
+        return self.nbasis
+
+    @property
+    def coefficients(self):
+        c = np.empty(self.nbasis)
+        check(_lib().vpm_vspace_get(self._h, None, _hp(c)))
+        return c
+
+    @coefficients.setter
+    def coefficients(self, c):
+        self._set_coefficients(_f64(c))
+
+    def _set_coefficients(self, c):
+        # uploading coefficients == evaluating with an explicit coefficient vector once (rebuilds the tables)
+        dummy = DeviceVector(self.ctx, 2, np.zeros(2))
+        check(_lib().vpm_gather_v(self._h, _hp(c), dummy.ptr, 0, None, None))
+        dummy.free()
+
+    @property
+    def rhs(self):
+        r = np.empty(self.nbasis)
+        check(_lib().vpm_vspace_get(self._h, _hp(r), None))
+        return r
+
+    @property
+    def mass_matrix(self):
+        M = np.empty((self.nbasis, self.nbasis))
+        check(_lib().vpm_vspace_mass(self._h, _hp(M)))
+        return M
+
+    def mass_solve(self, rhs):
+        """mass_fact \\ rhs (ldiv!, src/projections/distribution.jl:52)"""
+        rhs = _f64(rhs)
+        c = np.empty(self.nbasis)
+        check(_lib().vpm_mass_solve_v(self._h, _hp(rhs), _hp(c)))
+        return c
+
+    def evaluate(self, v, coefficients=None, derivative=False):
+        """spline.(v) / (Derivative(1)*spline).(v) for a host array v"""
+        v = _f64(np.atleast_1d(v)).ravel()
+        dv = DeviceVector(self.ctx, v.size, v)
+        out = DeviceVector(self.ctx, v.size)
+        c = None if coefficients is None else _f64(coefficients)
+        if derivative:
+            check(_lib().vpm_gather_v(self._h, _hp(c), dv.ptr, v.size, None, out.ptr))
+        else:
+            check(_lib().vpm_gather_v(self._h, _hp(c), dv.ptr, v.size, out.ptr, None))
+        r = out.download()
+        dv.free(); out.free()
+        return r
+
+    def __call__(self, v):
+        return self.evaluate(v)
+
+
+class Spline:
+    """Result of `projection`: aliases the SplineDistribution's coefficients (spline_distribution.jl:9)."""
+
+    def __init__(self, sdist, derivative=False):
+        self.sdist, self.derivative = sdist, derivative
+
+    @property
+    def coefficients(self):
+        return self.sdist.coefficients
+
+    def __call__(self, v):
+        return self.sdist.evaluate(v, derivative=self.derivative)
+
+
+def Derivative(n=1):
+    class _D:
+        order = n
+
+        def __mul__(self, spline):
+            if n != 1 or not isinstance(spline, Spline) or spline.derivative:
+                raise VpmError(-5, "only Derivative(1) * Spline is on the hot path")
+            return Spline(spline.sdist, derivative=True)
+    return _D()
+
+
+# ------------------------------------------------------------------------------------------------
+# potential (PoissonSolvers.Potential over a periodic B-spline basis)
+# ------------------------------------------------------------------------------------------------
+class PeriodicBasisBSplineKit:
+    """PeriodicBasisBSplineKit(domain, order, n): n = number of periodic basis functions
+    (whether PoissonSolvers' `nknot` means n or n+1 is unpinned; here it is n)."""
+
+    def __init__(self, domain, order, n):
+        self.domain, self.order, self.n = (float(domain[0]), float(domain[1])), int(order), int(n)
+
+
+class Potential:
+    def __init__(self, basis, ctx=None):
+        self.ctx = ctx or default_context()
+        self.basis = basis
+        h = _vp()
+        check(_lib().vpm_xspace_create(self.ctx._h, basis.domain[0], basis.domain[1], basis.order, basis.n, C.byref(h)))
+        self._h = h
+        self.n = basis.n
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self.ctx._h:
+                _lib().vpm_xspace_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def rhs(self):
+        r = np.empty(self.n)
+        check(_lib().vpm_xspace_get(self._h, _hp(r), None))
+        return r
+
+    @property
+    def coefficients(self):
+        c = np.empty(self.n)
+        check(_lib().vpm_xspace_get(self._h, None, _hp(c)))
+        return c
+
+    def stencils(self):
+        K = self.basis.order
+        m, s = np.empty(2 * K - 1), np.empty(2 * K - 1)
+        check(_lib().vpm_xspace_stencils(self._h, _hp(m), _hp(s)))
+        return m, s
+
+    def mass_solve(self, rhs):
+        """potential.solver.Mfac \\ rhs (test/projections_tests.jl:27)"""
+        rhs = _f64(rhs)
+        out = np.empty(self.n)
+        check(_lib().vpm_mass_solve_x(self._h, _hp(rhs), _hp(out)))
+        return out
+
+    def solve(self, rhs):
+        rhs = _f64(rhs)
+        phi = np.empty(self.n)
+        check(_lib().vpm_poisson_solve(self._h, _hp(rhs), _hp(phi)))
+        return phi
+
+    def energy(self, phi=None):
+        phi = self.coefficients if phi is None else _f64(phi)
+        e = C.c_double()
+        check(_lib().vpm_field_energy(self._h, _hp(phi), C.byref(e)))
+        return e.value
+
+    def evaluate(self, x, derivative=0, coefficients=None):
+        """phi(x) / phi(x, Derivative(1)) for host positions x"""
+        x = _f64(np.atleast_1d(x)).ravel()
+        dx = DeviceVector(self.ctx, x.size, x)
+        out = DeviceVector(self.ctx, x.size)
+        c = None if coefficients is None else _f64(coefficients)
+        check(_lib().vpm_gather_x(self._h, _hp(c), dx.ptr, x.size, int(derivative), out.ptr))
+        r = out.download()
+        dx.free(); out.free()
+        return r
+
+    def __call__(self, x, derivative=None):
+        d = 0 if derivative is None else getattr(derivative, "order", int(derivative))
+        r = self.evaluate(x, d)
+        return r if np.ndim(x) else float(r[0])
+
+
+def update_(potential):
+    """PoissonSolvers.update!(potential): rhs -> coefficients (call site vlasov_poisson.jl:14)"""
+    check(_lib().vpm_poisson_solve(potential._h, None, None))
+    return potential
+
+
+def projection_(potential, distribution):
+    """projection!(potential, distribution): src/projections/potential.jl:2-22"""
+    x, v, w = distribution.ptrs()
+    check(_lib().vpm_deposit_x(potential._h, x, w, distribution.npart, None))
+    return potential
+
+
+def projection(velocities, dist, final_dist):
+    """projection(velocities, dist, final_dist) -> Spline: src/projections/distribution.jl:35-55"""
+    x, v, w = dist.ptrs()
+    if velocities is None:
+        check(_lib().vpm_project_v(final_dist._h, v, w, dist.npart, None))
+    else:
+        vel = _f64(velocities).ravel()
+        if vel.size != dist.npart:
+            raise ValueError("velocities must have one entry per particle")
+        dv = DeviceVector(dist.ctx, vel.size, vel)
+        check(_lib().vpm_project_v(final_dist._h, dv.ptr, w, dist.npart, None))
+        dv.free()
+    return Spline(final_dist)
+
+
+def _moments(distribution, vp):
+    vp = _f64(vp).ravel()
+    dv = DeviceVector(distribution.ctx, vp.size, vp)
+    out = np.empty(5)
+    check(_lib().vpm_moments(distribution._h, None, dv.ptr, vp.size, _hp(out)))
+    dv.free()
+    return out
+
+
+def projection_density(distribution, vp, isDerivative=False):
+    m = _moments(distribution, vp)
+    return m[3] if isDerivative else m[0]
+
+
+def projection_momentum(distribution, vp, isDerivative=False):
+    m = _moments(distribution, vp)
+    return m[4] if isDerivative else m[1]
+
+
+def projection_energy(distribution, vp, isDerivative=False):
+    if isDerivative:
+        raise VpmError(-5, "the reference never takes the energy moment of f' (density.jl:15-20)")
+    return _moments(distribution, vp)[2]
+
+
+def compute_f_densities(distribution, vp):
+    m = _moments(distribution, vp)
+    return m[0], m[1], m[2]
+
+
+def compute_df_densities(distribution, vp):
+    m = _moments(distribution, vp)
+    return m[3], m[4]
+
+
+def compute_coefficients(distribution, particle_dist, vp):
+    """lenard_bernstein_conservative.jl:11-21"""
+    n, nu, neps, B1, B2 = _moments(distribution, vp)
+    B1, B2 = -B1, -B2
+    A1 = (neps * B1 - nu * B2) / (n * neps - nu ** 2)
+    A2 = -(nu * B1 - n * B2) / (n * neps - nu ** 2)
+    return A1, A2
+
+
+# ------------------------------------------------------------------------------------------------
+# models
+# ------------------------------------------------------------------------------------------------
+class VlasovPoisson:
+    def __init__(self, dist, potential):
+        self.distribution, self.potential = dist, potential
+
+
+def update_potential_(model):
+    """update_potential!(model): src/models/vlasov_poisson.jl:12-15"""
+    d = model.distribution
+    check(_lib().vpm_update_potential(model.potential._h, d._h, None, None))
+
+
+def s_advection_(dist, potential, tau):
+    """exact flow of the drift on a device-resident distribution (vlasov_poisson.jl:53-58)"""
+    check(_lib().vpm_push_drift(potential._h, dist._h, float(tau)))
+
+
+def s_acceleration_(dist, potential, tau, field_dist=None, scale=1.0):
+    """exact flow of the kick (vlasov_poisson.jl:61-67): field from field_dist (default: dist itself)"""
+    src = field_dist or dist
+    check(_lib().vpm_update_potential(potential._h, src._h, None, None))
+    check(_lib().vpm_push_kick(potential._h, dist._h, None, float(tau), float(scale)))
+
+
+class Entropy:
+    pass
+
+
+class CollisionEntropy(Entropy):
+    """holder of the SplineDistribution (src/entropies/collision_entropy.jl:1-10)"""
+
+    def __init__(self, dist):
+        self.dist = dist
+        self.cache = {np.float64: dist, float: dist}
+
+
+class LenardBernstein:
+    conservative = False
+
+    def __init__(self, dist, ent, nu=1.0):
+        self.dist, self.ent, self.nu = dist, ent, float(nu)
+
+
+class ConservativeLenardBernstein(LenardBernstein):
+    conservative = True
+
+
+def _lb_rhs(vdot, v, params, conservative):
+    model = params["model"]
+    idist, sdist = params["idist"], model.ent.dist
+    v = _f64(v).ravel()
+    dv = DeviceVector(idist.ctx, v.size, v)
+    out = DeviceVector(idist.ctx, v.size)
+    _, _, w = idist.ptrs()
+    A = np.zeros(2)
+    check(_lib().vpm_lb_rhs(sdist._h, dv.ptr, w, v.size, float(params["nu"]), int(conservative), out.ptr, None, _hp(A)))
+    vdot[...] = out.download().reshape(np.shape(vdot))
+    dv.free(); out.free()
+    return vdot
+
+
+def LB_rhs_(vdot, v, params, t=0.0):
+    """LB_rhs!(v̇, v, params, t): src/models/lenard_bernstein.jl:20-30"""
+    return _lb_rhs(vdot, v, params, False)
+
+
+def CLB_rhs_(vdot, v, params, t=0.0):
+    """CLB_rhs!(v̇, v, params, t): src/models/lenard_bernstein_conservative.jl:24-36"""
+    return _lb_rhs(vdot, v, params, True)
+
+
+# ------------------------------------------------------------------------------------------------
+# methods (drivers)
+# ------------------------------------------------------------------------------------------------
+def _ntime(tspan, tstep):
+    return int(round((tspan[1] - tspan[0]) / tstep))
+
+
+class _Trajectory:
+    """run! output: the reference writes HDF5 datasets z[nd,np,nt+1] (splitting.jl:32-34) or z[np,nt+1], t
+    (geometric_integrator.jl:21-25).  h5py is not in this image, so the same arrays go to an .npz with
+    the same dataset names; if h5py is importable an HDF5 file with the reference layout is written."""
+
+    def __init__(self, path):
+        self.path, self.data = path, {}
+
+    def save(self):
+        if self.path is None:
+            return
+        try:
+            import h5py  # noqa
+            with h5py.File(self.path, "w") as f:
+                for k, a in self.data.items():
+                    f.create_dataset(k, data=np.ascontiguousarray(a.T))  # Julia column-major on disk
+        except ImportError:
+            np.savez(self.path if str(self.path).endswith(".npz") else str(self.path) + ".npz", **self.data)
+
+
+class SplittingMethod:
+    """SplittingMethod(model::VlasovPoisson{1,1}, tspan, tstep): Strang splitting (vlasov_poisson.jl:73-89).
+
+    field="frozen" reproduces the shipped behaviour (potential always deposited from model.distribution,
+    SURVEY F4); field="selfconsistent" is the physical loop of the legacy integrate_vp! (src/vlasov_poisson.jl:94-115).
+    """
+
+    def __init__(self, model, tspan, tstep, field="frozen", chi=1.0):
+        if field not in ("frozen", "selfconsistent"):
+            raise ValueError("field must be 'frozen' or 'selfconsistent'")
+        self.model, self.tspan, self.tstep, self.field, self.chi = model, tspan, float(tstep), field, float(chi)
+        self.diagnostics = None
+
+
+def _vp_steps(method, nsteps, diag_mode):
+    d, pot = method.model.distribution, method.model.potential
+    diag = np.zeros((nsteps + 1, 3)) if diag_mode else None
+    mode = _cabi.VP_FROZEN if method.field == "frozen" else _cabi.VP_SELFCONSISTENT
+    check(_lib().vpm_vp_strang_steps(pot._h, d._h, method.tstep, method.chi, int(nsteps), mode, int(diag_mode), _hp(diag)))
+    return diag
+
+
+class GeometricIntegrator:
+    """GeometricIntegrator(model::{Conservative}LenardBernstein{1,1}, tspan, tstep): RK438
+    (lenard_bernstein.jl:68-84, lenard_bernstein_conservative.jl:88-104)"""
+
+    def __init__(self, model, tspan, tstep):
+        self.model, self.tspan, self.tstep = model, tspan, float(tstep)
+        self.diagnostics = None
+
+
+def run_(method, h5file=None, save_stride=None, diag_mode=1):
+    """run!(method, h5file): src/methods/splitting.jl:23-52, src/methods/geometric_integrator.jl:12-44.
+
+    The state stays on the device between steps.  save_stride=None writes no trajectory (the reference
+    writes every step); save_stride=k stores every k-th step plus the initial state.
+    Diagnostics (W,K,M) or (sum v, sum v^2) of every step are kept in method.diagnostics.
+    """
+    nt = _ntime(method.tspan, method.tstep)
+    traj = _Trajectory(h5file if save_stride else None)
+    if isinstance(method, SplittingMethod):
+        d = method.model.distribution
+        frames = [d.download_aos(2)] if save_stride else []
+        diags = []
+        done = 0
+        while done < nt:
+            chunk = min(save_stride, nt - done) if save_stride else nt
+            dg = _vp_steps(method, chunk, diag_mode)
+            if dg is not None:
+                diags.append(dg if not diags else dg[1:])
+            done += chunk
+            if save_stride:
+                frames.append(d.download_aos(2))
+        method.diagnostics = np.concatenate(diags) if diags else None
+        if save_stride:
+            traj.data["z"] = np.stack(frames, axis=-1)  # (nd, np, nframes)
+            traj.save()
+        return d
+    if isinstance(method, GeometricIntegrator):
+        m = method.model
+        d, sd = m.dist, m.ent.dist
+        frames = [d.get("v")] if save_stride else []
+        times = [method.tspan[0]]
+        diags, done = [], 0
+        while done < nt:
+            chunk = min(save_stride, nt - done) if save_stride else nt
+            dg = np.zeros((chunk + 1, 2))
+            check(_lib().vpm_lb_rk438_steps(sd._h, d._h, m.nu, method.tstep, chunk, int(m.conservative), _hp(dg)))
+            diags.append(dg if not diags else dg[1:])
+            done += chunk
+            if save_stride:
+                frames.append(d.get("v"))
+                times.append(method.tspan[0] + done * method.tstep)
+        method.diagnostics = np.concatenate(diags)
+        if save_stride:
+            traj.data["z"] = np.stack(frames, axis=-1)  # (np, nframes)
+            traj.data["t"] = np.asarray(times)
+            traj.save()
+        return d
+    raise TypeError("run_ expects a SplittingMethod or a GeometricIntegrator")
+
+
+# ------------------------------------------------------------------------------------------------
+# examples / initial conditions
+# ------------------------------------------------------------------------------------------------
+DEFAULT_SEED = 0x5EED0001
+
+
+class NormalDistribution:
+    def __init__(self, domain=(0.0, 1.0)):
+        self.domain = domain
+
+
+class UniformDistribution:
+    def __init__(self, domain=(0.0, 1.0)):
+        self.domain = domain
+
+
+class BumpOnTail:
+    def __init__(self, eps=0.03, kappa=0.3, alpha=0.1, sigma=0.5, v0=4.5):
+        self.eps, self.kappa, self.alpha, self.sigma, self.v0 = eps, kappa, alpha, sigma, v0
+
+    @property
+    def L(self):
+        return 2 * math.pi / self.kappa
+
+
+class DoubleMaxwellian:
+    def __init__(self, domain=(-5.0, 5.0), shift=3.0):
+        self.domain, self.shift = domain, shift
+
+
+def initialize_(dist, params, seed=DEFAULT_SEED, offset=0, ntotal=None):
+    """initialize!(dist, example): device-side, counter-based in the global particle index so a slab
+    [offset, offset+npart) of an ntotal-particle ensemble is reproducible on any rank.
+
+    NormalDistribution maps x through a data-dependent affine transform (normal.jl:19-21, needs the sample
+    maximum), so it is drawn on the host with numpy's seeded generator and uploaded (config 1 is 1e4 particles).
+    """
+    n = dist.npart
+    ntotal = n if ntotal is None else int(ntotal)
+    if isinstance(params, BumpOnTail):
+        check(_lib().vpm_sample_bump_on_tail(dist._h, int(offset), ntotal, int(seed), params.eps, params.kappa,
+                                              params.alpha, params.sigma, params.v0))
+    elif isinstance(params, DoubleMaxwellian):
+        check(_lib().vpm_sample_maxwellian(dist._h, int(offset), ntotal, int(seed), params.domain[0], params.domain[1],
+                                            float(params.shift), 1, 1.0))
+    elif isinstance(params, UniformDistribution):
+        check(_lib().vpm_sample_maxwellian(dist._h, int(offset), ntotal, int(seed), params.domain[0], params.domain[1],
+                                            0.0, 0, 1.0))
+    elif isinstance(params, NormalDistribution):
+        rng = np.random.default_rng(seed)
+        x0, v0 = rng.standard_normal(n), rng.standard_normal(n)
+        xmax = math.ceil(np.abs(x0).max())
+        x0 = (x0 + xmax) / (2 * xmax)
+        x0 = x0 * (params.domain[1] - params.domain[0]) + params.domain[0]
+        dist.set(x0, v0, np.full(n, 1.0 / n))
+    else:
+        raise TypeError(f"no initialize_ method for {type(params).__name__}")
+    return dist

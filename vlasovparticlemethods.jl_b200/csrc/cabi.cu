@@ -1,0 +1,967 @@
+// extern "C" surface of libvpm_b200.so (declared in include/vpm_b200.h): contexts, particle storage,
+// spaces, operator-level entry points and the whole-step device-resident steppers.
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "vpm_internal.h"
+
+namespace vpm {
+
+static thread_local std::string g_err;
+
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+static int grow(double** buf, size_t* cap, size_t doubles, cudaStream_t stream)
+{
+    if (*cap >= doubles) return VPM_OK;
+    if (*buf) {
+        VPM_CUDA(cudaStreamSynchronize(stream));
+        VPM_CUDA(cudaFree(*buf));
+        *buf = nullptr;
+        *cap = 0;
+    }
+    size_t want = doubles + doubles / 4 + 64;
+    cudaError_t e = cudaMalloc((void**)buf, want * sizeof(double));
+    if (e != cudaSuccess) return fail(VPM_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    *cap = want;
+    return VPM_OK;
+}
+
+int ensure_partials(vpm_ctx* ctx, size_t doubles) { return grow(&ctx->partials, &ctx->partials_cap, doubles, ctx->stream); }
+int ensure_red(vpm_ctx* ctx, size_t doubles) { return grow(&ctx->red, &ctx->red_cap, doubles, ctx->stream); }
+int ensure_staging(vpm_ctx* ctx, size_t doubles) { return grow(&ctx->staging, &ctx->staging_cap, doubles, ctx->stream); }
+
+// ---- NCCL through dlopen: no link-time dependency, works with torch's bundled libnccl.so.2 ----
+struct NcclUniqueId {
+    char internal[128];
+};
+struct Nccl {
+    void* handle = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+static Nccl* nccl_api()
+{
+    static Nccl api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (api.handle) {
+            api.GetUniqueId = (int (*)(NcclUniqueId*))dlsym(api.handle, "ncclGetUniqueId");
+            api.CommInitRank = (int (*)(void**, int, NcclUniqueId, int))dlsym(api.handle, "ncclCommInitRank");
+            api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
+            api.CommDestroy = (int (*)(void*))dlsym(api.handle, "ncclCommDestroy");
+            api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+        }
+    }
+    if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) return nullptr;
+    return &api;
+}
+
+int comm_allreduce(vpm_ctx* ctx, double* buf, size_t count)
+{
+    if (!ctx->comm.comm) return VPM_OK;
+    const int kFloat64 = 8, kSum = 0;
+    int r = ctx->comm.api->AllReduce(buf, buf, count, kFloat64, kSum, ctx->comm.comm, ctx->stream);
+    if (r != 0)
+        return fail(VPM_ERR_COMM, std::string("ncclAllReduce: ") + (ctx->comm.api->GetErrorString ? ctx->comm.api->GetErrorString(r) : "error"));
+    return VPM_OK;
+}
+
+template <typename T>
+static int upload(vpm_ctx* ctx, double** dst, const std::vector<T>& src)
+{
+    VPM_CUDA(cudaMalloc((void**)dst, sizeof(double) * (src.empty() ? 1 : src.size())));
+    if (!src.empty()) VPM_CUDA(cudaMemcpy(*dst, src.data(), sizeof(double) * src.size(), cudaMemcpyHostToDevice));
+    return VPM_OK;
+}
+
+static int grow_diag(vpm_ctx* ctx, double** buf, size_t* cap, size_t doubles)
+{
+    int rc = grow(buf, cap, doubles, ctx->stream);
+    if (rc) return rc;
+    VPM_CUDA(cudaMemsetAsync(*buf, 0, sizeof(double) * doubles, ctx->stream));
+    return VPM_OK;
+}
+
+}  // namespace vpm
+
+using namespace vpm;
+
+#define VPM_CHECK(expr)             \
+    do {                            \
+        int _rc = (expr);           \
+        if (_rc != VPM_OK) return _rc; \
+    } while (0)
+#define VPM_REQUIRE(cond, msg) \
+    do {                       \
+        if (!(cond)) return fail(VPM_ERR_INVALID, msg); \
+    } while (0)
+
+extern "C" {
+
+const char* vpm_last_error(void) { return g_err.c_str(); }
+int vpm_version(void) { return 100; }
+
+int vpm_ctx_create(int device, void* stream, vpm_ctx** out)
+{
+    VPM_REQUIRE(out, "vpm_ctx_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(VPM_ERR_CUDA, std::string("no CUDA device available (libvpm_b200 has no CPU fallback): ") + cudaGetErrorString(e));
+    VPM_REQUIRE(device >= 0 && device < ndev, "vpm_ctx_create: bad device index");
+    VPM_CUDA(cudaSetDevice(device));
+    vpm_ctx* c = new (std::nothrow) vpm_ctx();
+    if (!c) return fail(VPM_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t es = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (es != cudaSuccess) {
+            delete c;
+            return fail(VPM_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(es));
+        }
+        c->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    VPM_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = c;
+    return VPM_OK;
+}
+
+int vpm_ctx_destroy(vpm_ctx* ctx)
+{
+    if (!ctx) return VPM_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    vpm_comm_destroy(ctx);
+    cudaFree(ctx->partials);
+    cudaFree(ctx->red);
+    cudaFree(ctx->staging);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return VPM_OK;
+}
+
+int vpm_sync(vpm_ctx* ctx)
+{
+    VPM_REQUIRE(ctx, "vpm_sync: ctx is NULL");
+    VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VPM_OK;
+}
+
+int vpm_device_info(vpm_ctx* ctx, int* sm_count, int64_t* smem_optin_bytes, int64_t* total_mem_bytes)
+{
+    VPM_REQUIRE(ctx, "vpm_device_info: ctx is NULL");
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (smem_optin_bytes) *smem_optin_bytes = (int64_t)ctx->smem_optin;
+    if (total_mem_bytes) {
+        size_t fr = 0, tot = 0;
+        VPM_CUDA(cudaMemGetInfo(&fr, &tot));
+        *total_mem_bytes = (int64_t)tot;
+    }
+    return VPM_OK;
+}
+
+int64_t vpm_launch_count(vpm_ctx* ctx) { return ctx ? (int64_t)ctx->launches : 0; }
+
+int vpm_host_alloc(int64_t bytes, void** out)
+{
+    VPM_REQUIRE(out && bytes >= 0, "vpm_host_alloc: bad arguments");
+    VPM_CUDA(cudaMallocHost(out, (size_t)(bytes > 0 ? bytes : 1)));
+    return VPM_OK;
+}
+
+int vpm_host_free(void* p)
+{
+    if (p) VPM_CUDA(cudaFreeHost(p));
+    return VPM_OK;
+}
+
+int vpm_dev_alloc(vpm_ctx* ctx, int64_t n_doubles, double** out_dev)
+{
+    VPM_REQUIRE(ctx && out_dev && n_doubles >= 0, "vpm_dev_alloc: bad arguments");
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc((void**)out_dev, sizeof(double) * (size_t)(n_doubles + 2));
+    if (e != cudaSuccess) return fail(VPM_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return VPM_OK;
+}
+
+int vpm_dev_free(vpm_ctx* ctx, double* dev)
+{
+    VPM_REQUIRE(ctx, "vpm_dev_free: ctx is NULL");
+    if (!dev) return VPM_OK;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    VPM_CUDA(cudaFree(dev));
+    return VPM_OK;
+}
+
+int vpm_memcpy_h2d(vpm_ctx* ctx, double* dst_dev, const double* src_host, int64_t n_doubles)
+{
+    VPM_REQUIRE(ctx && (n_doubles == 0 || (dst_dev && src_host)) && n_doubles >= 0, "vpm_memcpy_h2d: bad arguments");
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    VPM_CUDA(cudaMemcpyAsync(dst_dev, src_host, sizeof(double) * (size_t)n_doubles, cudaMemcpyHostToDevice, ctx->stream));
+    VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VPM_OK;
+}
+
+int vpm_memcpy_d2h(vpm_ctx* ctx, double* dst_host, const double* src_dev, int64_t n_doubles)
+{
+    VPM_REQUIRE(ctx && (n_doubles == 0 || (dst_host && src_dev)) && n_doubles >= 0, "vpm_memcpy_d2h: bad arguments");
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    VPM_CUDA(cudaMemcpyAsync(dst_host, src_dev, sizeof(double) * (size_t)n_doubles, cudaMemcpyDeviceToHost, ctx->stream));
+    VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VPM_OK;
+}
+
+/* ---------------------------------------------------------------- particles */
+
+int vpm_particles_create(vpm_ctx* ctx, int64_t n, vpm_particles** out)
+{
+    VPM_REQUIRE(ctx && out && n >= 0, "vpm_particles_create: bad arguments");
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    vpm_particles* p = new (std::nothrow) vpm_particles();
+    if (!p) return fail(VPM_ERR_NOMEM, "out of host memory");
+    p->ctx = ctx;
+    p->n = n;
+    const size_t bytes = sizeof(double) * (size_t)(n > 0 ? n + (n & 1) : 2);
+    cudaError_t e1 = cudaMalloc((void**)&p->x, bytes), e2 = cudaMalloc((void**)&p->v, bytes), e3 = cudaMalloc((void**)&p->w, bytes);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        cudaFree(p->x); cudaFree(p->v); cudaFree(p->w);
+        delete p;
+        return fail(VPM_ERR_NOMEM, "cudaMalloc of particle arrays failed");
+    }
+    cudaMemsetAsync(p->x, 0, bytes, ctx->stream);
+    cudaMemsetAsync(p->v, 0, bytes, ctx->stream);
+    cudaMemsetAsync(p->w, 0, bytes, ctx->stream);
+    *out = p;
+    return VPM_OK;
+}
+
+int vpm_particles_destroy(vpm_particles* p)
+{
+    if (!p) return VPM_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    cudaFree(p->x); cudaFree(p->v); cudaFree(p->w);
+    cudaFree(p->q); cudaFree(p->acc); cudaFree(p->d);
+    delete p;
+    return VPM_OK;
+}
+
+int64_t vpm_particles_size(const vpm_particles* p) { return p ? p->n : 0; }
+
+int vpm_particles_ptrs(vpm_particles* p, double** x, double** v, double** w)
+{
+    VPM_REQUIRE(p, "vpm_particles_ptrs: p is NULL");
+    if (x) *x = p->x;
+    if (v) *v = p->v;
+    if (w) *w = p->w;
+    return VPM_OK;
+}
+
+int vpm_particles_upload_aos(vpm_particles* p, const double* z, int ld)
+{
+    VPM_REQUIRE(p && z && (ld == 2 || ld == 3), "vpm_particles_upload_aos: bad arguments (ld must be 2 or 3)");
+    vpm_ctx* ctx = p->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    const int64_t chunk = 1 << 24;
+    VPM_CHECK(ensure_staging(ctx, (size_t)std::min<int64_t>(chunk, std::max<int64_t>(p->n, 1)) * ld));
+    for (int64_t o = 0; o < p->n; o += chunk) {
+        const int64_t m = std::min(chunk, p->n - o);
+        VPM_CUDA(cudaMemcpyAsync(ctx->staging, z + o * ld, sizeof(double) * m * ld, cudaMemcpyHostToDevice, ctx->stream));
+        VPM_CHECK(launch_aos_to_soa(ctx, ctx->staging, ld, m, p->x + o, p->v + o, ld == 3 ? p->w + o : nullptr));
+    }
+    VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VPM_OK;
+}
+
+int vpm_particles_download_aos(vpm_particles* p, double* z, int ld)
+{
+    VPM_REQUIRE(p && z && (ld == 2 || ld == 3), "vpm_particles_download_aos: bad arguments (ld must be 2 or 3)");
+    vpm_ctx* ctx = p->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    const int64_t chunk = 1 << 24;
+    VPM_CHECK(ensure_staging(ctx, (size_t)std::min<int64_t>(chunk, std::max<int64_t>(p->n, 1)) * ld));
+    for (int64_t o = 0; o < p->n; o += chunk) {
+        const int64_t m = std::min(chunk, p->n - o);
+        VPM_CHECK(launch_soa_to_aos(ctx, p->x + o, p->v + o, ld == 3 ? p->w + o : nullptr, ld, m, ctx->staging));
+        VPM_CUDA(cudaMemcpyAsync(z + o * ld, ctx->staging, sizeof(double) * m * ld, cudaMemcpyDeviceToHost, ctx->stream));
+        VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return VPM_OK;
+}
+
+int vpm_particles_upload_soa(vpm_particles* p, const double* x, const double* v, const double* w)
+{
+    VPM_REQUIRE(p, "vpm_particles_upload_soa: p is NULL");
+    vpm_ctx* ctx = p->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = sizeof(double) * (size_t)p->n;
+    if (x) VPM_CUDA(cudaMemcpyAsync(p->x, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (v) VPM_CUDA(cudaMemcpyAsync(p->v, v, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (w) VPM_CUDA(cudaMemcpyAsync(p->w, w, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VPM_OK;
+}
+
+int vpm_particles_download_soa(vpm_particles* p, double* x, double* v, double* w)
+{
+    VPM_REQUIRE(p, "vpm_particles_download_soa: p is NULL");
+    vpm_ctx* ctx = p->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = sizeof(double) * (size_t)p->n;
+    if (x) VPM_CUDA(cudaMemcpyAsync(x, p->x, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (v) VPM_CUDA(cudaMemcpyAsync(v, p->v, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (w) VPM_CUDA(cudaMemcpyAsync(w, p->w, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VPM_OK;
+}
+
+int vpm_sample_bump_on_tail(vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed, double eps, double kappa,
+                            double alpha, double sigma, double v0)
+{
+    VPM_REQUIRE(p && ntotal > 0 && kappa > 0, "vpm_sample_bump_on_tail: bad arguments");
+    VPM_CUDA(cudaSetDevice(p->ctx->device));
+    return launch_sample_bump_on_tail(p->ctx, p, offset, ntotal, seed, eps, kappa, alpha, sigma, v0);
+}
+
+int vpm_sample_maxwellian(vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed, double xlo, double xhi,
+                          double shift, int doubled, double wnum)
+{
+    VPM_REQUIRE(p && ntotal > 0, "vpm_sample_maxwellian: bad arguments");
+    VPM_CUDA(cudaSetDevice(p->ctx->device));
+    return launch_sample_maxwellian(p->ctx, p, offset, ntotal, seed, xlo, xhi, shift, doubled, wnum);
+}
+
+/* ---------------------------------------------------------------- x-space */
+
+int vpm_xspace_create(vpm_ctx* ctx, double lo, double hi, int order, int n_basis, vpm_xspace** out)
+{
+    VPM_REQUIRE(ctx && out, "vpm_xspace_create: NULL argument");
+    VPM_REQUIRE(order >= 2 && order <= kMaxOrder, "vpm_xspace_create: spline order must be 2..6");
+    VPM_REQUIRE(n_basis >= 1 && n_basis <= (1 << 20), "vpm_xspace_create: n_basis out of range");
+    VPM_REQUIRE(hi > lo && std::isfinite(lo) && std::isfinite(hi), "vpm_xspace_create: need finite lo < hi");
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    vpm_xspace* xs = new (std::nothrow) vpm_xspace();
+    if (!xs) return fail(VPM_ERR_NOMEM, "out of host memory");
+    xs->ctx = ctx;
+    xs->lo = lo; xs->hi = hi; xs->K = order; xs->nh = n_basis;
+    xs->h = (hi - lo) / n_basis;
+    xs->invh = 1.0 / xs->h;
+    xs->fm = make_fastmod(n_basis);
+    periodic_stencils(order, xs->h, xs->mass_stencil, xs->stiff_stencil);
+    std::vector<double> mrow, srow, dpiece;
+    circulant_first_row(xs->mass_stencil, order, n_basis, mrow);
+    circulant_first_row(xs->stiff_stencil, order, n_basis, srow);
+    circulant_pinv(srow, true, xs->ginv_host);
+    circulant_pinv(mrow, false, xs->minv_host);
+    uniform_piece_table(order - 1, dpiece);
+    const int ES = (order - 1) | 1;
+    int rc = VPM_OK;
+    if ((rc = upload(ctx, &xs->ginv, xs->ginv_host)) || (rc = upload(ctx, &xs->minv, xs->minv_host)) ||
+        (rc = upload(ctx, &xs->stiff, xs->stiff_stencil)) || (rc = upload(ctx, &xs->dpiece, dpiece))) {
+        vpm_xspace_destroy(xs);
+        return rc;
+    }
+    std::vector<double> z1((size_t)n_basis + 2, 0.0), z2((size_t)n_basis, 0.0), z3((size_t)n_basis * ES, 0.0);
+    if ((rc = upload(ctx, &xs->rhs, z1)) || (rc = upload(ctx, &xs->phi, z2)) || (rc = upload(ctx, &xs->etab, z3))) {
+        vpm_xspace_destroy(xs);
+        return rc;
+    }
+    *out = xs;
+    return VPM_OK;
+}
+
+int vpm_xspace_destroy(vpm_xspace* xs)
+{
+    if (!xs) return VPM_OK;
+    cudaSetDevice(xs->ctx->device);
+    cudaStreamSynchronize(xs->ctx->stream);
+    cudaFree(xs->ginv); cudaFree(xs->minv); cudaFree(xs->stiff); cudaFree(xs->dpiece);
+    cudaFree(xs->rhs); cudaFree(xs->phi); cudaFree(xs->etab); cudaFree(xs->diag);
+    delete xs;
+    return VPM_OK;
+}
+
+int vpm_xspace_stencils(const vpm_xspace* xs, double* mass, double* stiffness)
+{
+    VPM_REQUIRE(xs, "vpm_xspace_stencils: xs is NULL");
+    const size_t n = 2 * xs->K - 1;
+    if (mass) std::memcpy(mass, xs->mass_stencil.data(), n * sizeof(double));
+    if (stiffness) std::memcpy(stiffness, xs->stiff_stencil.data(), n * sizeof(double));
+    return VPM_OK;
+}
+
+static int d2h(vpm_ctx* ctx, double* dst, const double* src, size_t n)
+{
+    VPM_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VPM_OK;
+}
+
+static int h2d(vpm_ctx* ctx, double* dst, const double* src, size_t n)
+{
+    VPM_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    VPM_CUDA(cudaStreamSynchronize(ctx->stream));  // src may be pageable / reused by the caller
+    return VPM_OK;
+}
+
+int vpm_deposit_x(vpm_xspace* xs, const double* x_dev, const double* w_dev, int64_t n, double* rhs_host)
+{
+    VPM_REQUIRE(xs && x_dev && w_dev && n >= 0, "vpm_deposit_x: bad arguments");
+    vpm_ctx* ctx = xs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    VpPass p{};
+    p.x_in = x_dev; p.w = w_dev; p.n = n; p.flags = VP_DEPOSIT;
+    int grid = 0;
+    VPM_CHECK(launch_vp_pass(ctx, xs, p, &grid));
+    VPM_CHECK(launch_vp_field(ctx, xs, FIELD_REDUCE, grid, 1, 0, -1.0, 1.0, -1, -1));
+    if (rhs_host) VPM_CHECK(d2h(ctx, rhs_host, xs->rhs, xs->nh));
+    return VPM_OK;
+}
+
+int vpm_poisson_solve(vpm_xspace* xs, const double* rhs_host, double* phi_host)
+{
+    VPM_REQUIRE(xs, "vpm_poisson_solve: xs is NULL");
+    vpm_ctx* ctx = xs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    if (rhs_host) VPM_CHECK(h2d(ctx, xs->rhs, rhs_host, xs->nh));
+    // solve only: the rhs is taken as given (already global), so bypass the all-reduce split
+    vpm::Comm saved = ctx->comm;
+    ctx->comm.comm = nullptr;
+    int rc = launch_vp_field(ctx, xs, FIELD_SOLVE | FIELD_TABLE, 0, 0, 0, -1.0, 1.0, -1, -1);
+    ctx->comm = saved;
+    VPM_CHECK(rc);
+    if (phi_host) VPM_CHECK(d2h(ctx, phi_host, xs->phi, xs->nh));
+    return VPM_OK;
+}
+
+int vpm_mass_solve_x(vpm_xspace* xs, const double* rhs_host, double* rho_host)
+{
+    VPM_REQUIRE(xs && rhs_host && rho_host, "vpm_mass_solve_x: NULL argument");
+    vpm_ctx* ctx = xs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    VPM_CHECK(ensure_red(ctx, 2 * (size_t)xs->nh));
+    VPM_CHECK(h2d(ctx, ctx->red, rhs_host, xs->nh));
+    VPM_CHECK(launch_circulant_apply(ctx, xs->minv, ctx->red, ctx->red + xs->nh, xs->nh));
+    return d2h(ctx, rho_host, ctx->red + xs->nh, xs->nh);
+}
+
+int vpm_gather_x(vpm_xspace* xs, const double* coef_host, const double* x_dev, int64_t n, int deriv, double* out_dev)
+{
+    VPM_REQUIRE(xs && x_dev && out_dev && n >= 0 && (deriv == 0 || deriv == 1), "vpm_gather_x: bad arguments");
+    vpm_ctx* ctx = xs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    const int nh = xs->nh, K = xs->K;
+    // scratch in staging: coef (nh) | table (nh * (K|1))
+    VPM_CHECK(ensure_staging(ctx, (size_t)nh * (2 + (K | 1))));
+    double* coef = ctx->staging;
+    double* tab = ctx->staging + nh;
+    if (coef_host) VPM_CHECK(h2d(ctx, coef, coef_host, nh));
+    else VPM_CUDA(cudaMemcpyAsync(coef, xs->phi, sizeof(double) * nh, cudaMemcpyDeviceToDevice, ctx->stream));
+    int nc = 0;
+    VPM_CHECK(launch_x_table(ctx, xs, coef, deriv, tab, &nc));
+    return launch_x_gather(ctx, xs, tab, nc, x_dev, n, out_dev);
+}
+
+int vpm_field_energy(vpm_xspace* xs, const double* phi_host, double* energy)
+{
+    VPM_REQUIRE(xs && phi_host && energy, "vpm_field_energy: NULL argument");
+    // nh x (2K-1) flops of host arithmetic on host data: dot(phi, S, phi)/2
+    const int nh = xs->nh, K = xs->K;
+    long double e = 0;
+    for (int i = 0; i < nh; i++) {
+        long double r = 0;
+        for (int d = -(K - 1); d <= K - 1; d++) r += (long double)xs->stiff_stencil[d + K - 1] * phi_host[((i + d) % nh + nh) % nh];
+        e += (long double)phi_host[i] * r;
+    }
+    *energy = (double)(0.5L * e);
+    return VPM_OK;
+}
+
+int vpm_push_drift(vpm_xspace* xs, vpm_particles* p, double tau)
+{
+    VPM_REQUIRE(xs && p, "vpm_push_drift: NULL argument");
+    VPM_CUDA(cudaSetDevice(xs->ctx->device));
+    VpPass ps{};
+    ps.x_in = p->x; ps.v_in = p->v; ps.w = p->w; ps.x_out = p->x; ps.n = p->n;
+    ps.flags = VP_POST1 | VP_WRITE_X;
+    ps.tau_post1 = tau;
+    return launch_vp_pass(xs->ctx, xs, ps, nullptr);
+}
+
+int vpm_push_kick(vpm_xspace* xs, vpm_particles* p, const double* phi_host, double tau, double scale)
+{
+    VPM_REQUIRE(xs && p, "vpm_push_kick: NULL argument");
+    vpm_ctx* ctx = xs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    if (phi_host) VPM_CHECK(h2d(ctx, xs->phi, phi_host, xs->nh));
+    vpm::Comm saved = ctx->comm;
+    ctx->comm.comm = nullptr;
+    int rc = launch_vp_field(ctx, xs, FIELD_TABLE, 0, 0, 0, -scale, 1.0, -1, -1);
+    ctx->comm = saved;
+    VPM_CHECK(rc);
+    VpPass ps{};
+    ps.x_in = p->x; ps.v_in = p->v; ps.w = p->w; ps.v_out = p->v; ps.n = p->n;
+    ps.flags = VP_KICK1 | VP_WRITE_V;
+    ps.tau_kick = tau;
+    return launch_vp_pass(ctx, xs, ps, nullptr);
+}
+
+int vpm_update_potential(vpm_xspace* xs, vpm_particles* p, double* rhs_host, double* phi_host)
+{
+    VPM_REQUIRE(xs && p, "vpm_update_potential: NULL argument");
+    vpm_ctx* ctx = xs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    VpPass ps{};
+    ps.x_in = p->x; ps.w = p->w; ps.n = p->n; ps.flags = VP_DEPOSIT;
+    int grid = 0;
+    VPM_CHECK(launch_vp_pass(ctx, xs, ps, &grid));
+    VPM_CHECK(launch_vp_field(ctx, xs, FIELD_REDUCE | FIELD_SOLVE | FIELD_TABLE, grid, 1, 0, -1.0, 1.0, -1, -1));
+    if (rhs_host) VPM_CHECK(d2h(ctx, rhs_host, xs->rhs, xs->nh));
+    if (phi_host) VPM_CHECK(d2h(ctx, phi_host, xs->phi, xs->nh));
+    return VPM_OK;
+}
+
+int vpm_xspace_get(vpm_xspace* xs, double* rhs_host, double* phi_host)
+{
+    VPM_REQUIRE(xs, "vpm_xspace_get: xs is NULL");
+    VPM_CUDA(cudaSetDevice(xs->ctx->device));
+    if (rhs_host) VPM_CHECK(d2h(xs->ctx, rhs_host, xs->rhs, xs->nh));
+    if (phi_host) VPM_CHECK(d2h(xs->ctx, phi_host, xs->phi, xs->nh));
+    return VPM_OK;
+}
+
+// Strang stepping on SoA arrays (x, v evolve; w and the frozen-field deposit positions are inputs)
+static int vp_steps(vpm_xspace* xs, double* x, double* v, const double* w, int64_t n, const double* xdep,
+                    const double* wdep, int64_t ndep, double dt, double chi, int nsteps, int mode, int diag_mode)
+{
+    vpm_ctx* ctx = xs->ctx;
+    const double Dt = dt * chi, escale = -1.0 / (chi * chi), wscale = 1.0 / (chi * chi);
+    const int ALL = FIELD_REDUCE | FIELD_SOLVE | FIELD_TABLE;
+    int grid = 0;
+    if (diag_mode) VPM_CHECK(grow_diag(ctx, &xs->diag, &xs->diag_cap, 3 * ((size_t)nsteps + 2)));
+
+    VpPass ps{};
+    ps.x_in = x; ps.v_in = v; ps.w = w; ps.x_out = x; ps.v_out = v; ps.n = n;
+
+    if (mode == VPM_VP_FROZEN) {
+        // field of model.distribution, fixed for the whole run
+        VpPass pd{};
+        pd.x_in = xdep; pd.w = wdep; pd.n = ndep; pd.flags = VP_DEPOSIT;
+        VPM_CHECK(launch_vp_pass(ctx, xs, pd, &grid));
+        VPM_CHECK(launch_vp_field(ctx, xs, ALL, grid, 1, 0, escale, wscale, diag_mode ? 0 : -1, -1));
+        if (diag_mode) {
+            VpPass pk = ps;
+            pk.flags = VP_DIAG;
+            VPM_CHECK(launch_vp_pass(ctx, xs, pk, &grid));
+            VPM_CHECK(launch_vp_field(ctx, xs, FIELD_REDUCE, grid, 0, 1, escale, wscale, -1, 0));
+        }
+        ps.flags = VP_PRE | VP_KICK1 | VP_KICK2 | VP_POST1 | VP_DIAG | VP_WRITE_X | VP_WRITE_V;
+        ps.tau_pre = 0.5 * Dt; ps.tau_kick = 0.5 * Dt; ps.tau_post1 = 0.5 * Dt;
+        for (int it = 1; it <= nsteps; it++) {
+            VPM_CHECK(launch_vp_pass(ctx, xs, ps, &grid));
+            if (diag_mode) VPM_CHECK(launch_vp_field(ctx, xs, FIELD_REDUCE, grid, 0, 1, escale, wscale, -1, it));
+        }
+        return VPM_OK;
+    }
+
+    // self-consistent (legacy integrate_vp!): passes are staggered by half a drift so that one pass per
+    // step does kick(n) + drift/2 + drift/2 + deposit(n+1)
+    if (diag_mode) {
+        VpPass p0 = ps;
+        p0.flags = VP_DEPOSIT | VP_DIAG;
+        VPM_CHECK(launch_vp_pass(ctx, xs, p0, &grid));
+        VPM_CHECK(launch_vp_field(ctx, xs, FIELD_REDUCE | FIELD_SOLVE, grid, 1, 1, escale, wscale, 0, 0));
+    }
+    if (nsteps <= 0) return VPM_OK;
+    {
+        VpPass p1 = ps;
+        p1.flags = VP_POST2 | VP_DEPOSIT | VP_WRITE_X;
+        p1.tau_post2 = 0.5 * Dt;
+        VPM_CHECK(launch_vp_pass(ctx, xs, p1, &grid));
+        VPM_CHECK(launch_vp_field(ctx, xs, ALL, grid, 1, 0, escale, wscale, diag_mode == 1 ? 1 : -1, -1));
+    }
+    ps.tau_kick = Dt; ps.tau_post1 = 0.5 * Dt; ps.tau_post2 = 0.5 * Dt;
+    for (int it = 1; it <= nsteps; it++) {
+        const bool last = it == nsteps;
+        if (diag_mode == 2) {
+            ps.flags = VP_KICK1 | VP_POST1 | VP_DIAG | VP_DEPOSIT | VP_WRITE_X | VP_WRITE_V;
+            VPM_CHECK(launch_vp_pass(ctx, xs, ps, &grid));
+            VPM_CHECK(launch_vp_field(ctx, xs, FIELD_REDUCE | FIELD_SOLVE, grid, 1, 1, escale, wscale, it, it));
+            if (!last) {
+                VpPass p2 = ps;
+                p2.flags = VP_POST2 | VP_DEPOSIT | VP_WRITE_X;
+                VPM_CHECK(launch_vp_pass(ctx, xs, p2, &grid));
+                VPM_CHECK(launch_vp_field(ctx, xs, ALL, grid, 1, 0, escale, wscale, -1, -1));
+            }
+        } else if (!last) {
+            ps.flags = VP_KICK1 | VP_POST1 | VP_DIAG | VP_POST2 | VP_DEPOSIT | VP_WRITE_X | VP_WRITE_V;
+            VPM_CHECK(launch_vp_pass(ctx, xs, ps, &grid));
+            VPM_CHECK(launch_vp_field(ctx, xs, ALL, grid, 1, 1, escale, wscale, diag_mode ? it + 1 : -1, diag_mode ? it : -1));
+        } else {
+            ps.flags = VP_KICK1 | VP_POST1 | VP_DIAG | VP_WRITE_X | VP_WRITE_V;
+            VPM_CHECK(launch_vp_pass(ctx, xs, ps, &grid));
+            if (diag_mode) VPM_CHECK(launch_vp_field(ctx, xs, FIELD_REDUCE, grid, 0, 1, escale, wscale, -1, it));
+        }
+    }
+    return VPM_OK;
+}
+
+int vpm_vp_strang_steps_async(vpm_xspace* xs, vpm_particles* p, double dt, double chi, int nsteps, int mode, int diag_mode)
+{
+    VPM_REQUIRE(xs && p && xs->ctx == p->ctx, "vpm_vp_strang_steps: bad handles");
+    VPM_REQUIRE(nsteps >= 0 && chi > 0 && (mode == VPM_VP_SELFCONSISTENT || mode == VPM_VP_FROZEN) && diag_mode >= 0 && diag_mode <= 2,
+                "vpm_vp_strang_steps: bad arguments");
+    VPM_CUDA(cudaSetDevice(xs->ctx->device));
+    const double* xdep = p->x;
+    if (mode == VPM_VP_FROZEN) {
+        // the deposit positions are the particles' positions at call time; the pass that computes the field
+        // runs before any push on the same stream, so no copy is needed
+    }
+    return vp_steps(xs, p->x, p->v, p->w, p->n, xdep, p->w, p->n, dt, chi, nsteps, mode, diag_mode);
+}
+
+int vpm_vp_strang_steps(vpm_xspace* xs, vpm_particles* p, double dt, double chi, int nsteps, int mode, int diag_mode,
+                        double* diag_host)
+{
+    if (!diag_host) diag_mode = 0;
+    VPM_CHECK(vpm_vp_strang_steps_async(xs, p, dt, chi, nsteps, mode, diag_mode));
+    vpm_ctx* ctx = xs->ctx;
+    if (diag_host && diag_mode) {
+        VPM_CHECK(d2h(ctx, diag_host, xs->diag, 3 * ((size_t)nsteps + 1)));
+        if (mode == VPM_VP_FROZEN)
+            for (int it = 1; it <= nsteps; it++) diag_host[3 * it] = diag_host[0];  // the field never changes
+        if (mode == VPM_VP_SELFCONSISTENT && diag_mode == 1 && nsteps == 0) { /* row 0 only */ }
+    } else {
+        VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return VPM_OK;
+}
+
+int vpm_vp_strang_step_host(vpm_xspace* xs, vpm_particles* p, const double* z_in, double* z_out, double dt, double chi, int mode)
+{
+    VPM_REQUIRE(xs && p && z_in && z_out && xs->ctx == p->ctx, "vpm_vp_strang_step_host: bad arguments");
+    VPM_REQUIRE(chi > 0 && (mode == VPM_VP_SELFCONSISTENT || mode == VPM_VP_FROZEN), "vpm_vp_strang_step_host: bad arguments");
+    vpm_ctx* ctx = xs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = p->n, npad = n + (n & 1);
+    // staging: z (2n) | x (npad) | v (npad)
+    VPM_CHECK(ensure_staging(ctx, (size_t)(2 * n + 2 * npad + 4)));
+    double* z = ctx->staging;
+    double* x = z + 2 * npad;
+    double* v = x + npad;
+    VPM_CUDA(cudaMemcpyAsync(z, z_in, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    VPM_CHECK(launch_aos_to_soa(ctx, z, 2, n, x, v, nullptr));
+    VPM_CHECK(vp_steps(xs, x, v, p->w, n, p->x, p->w, n, dt, chi, 1, mode, 0));
+    VPM_CHECK(launch_soa_to_aos(ctx, x, v, nullptr, 2, n, z));
+    VPM_CUDA(cudaMemcpyAsync(z_out, z, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VPM_OK;
+}
+
+/* ---------------------------------------------------------------- v-space */
+
+int vpm_vspace_create(vpm_ctx* ctx, double lo, double hi, int nknots, int order, int dirichlet, vpm_vspace** out)
+{
+    VPM_REQUIRE(ctx && out, "vpm_vspace_create: NULL argument");
+    VPM_REQUIRE(order >= 2 && order <= kMaxOrder, "vpm_vspace_create: spline order must be 2..6");
+    VPM_REQUIRE(nknots >= 2 && nknots <= (1 << 16), "vpm_vspace_create: nknots out of range");
+    VPM_REQUIRE(hi > lo && std::isfinite(lo) && std::isfinite(hi), "vpm_vspace_create: need finite lo < hi");
+    VPM_REQUIRE(!dirichlet || nknots + order - 4 >= 1, "vpm_vspace_create: Dirichlet basis would be empty");
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    vpm_vspace* vs = new (std::nothrow) vpm_vspace();
+    if (!vs) return fail(VPM_ERR_NOMEM, "out of host memory");
+    vs->ctx = ctx;
+    vs->lo = lo; vs->hi = hi; vs->K = order; vs->nknots = nknots; vs->ncell = nknots - 1;
+    vs->h = (hi - lo) / (nknots - 1);
+    vs->invh = 1.0 / vs->h;
+    vs->nbfull = nknots + order - 2;
+    vs->dirichlet = dirichlet ? 1 : 0;
+    vs->nv = vs->nbfull - 2 * vs->dirichlet;
+    std::vector<double> pieces;
+    clamped_piece_table(lo, hi, nknots, order, pieces);
+    clamped_mass(pieces, vs->ncell, order, vs->h, vs->dirichlet, vs->mass_host);
+    if (banded_cholesky(vs->mass_host, vs->nv, order, vs->chol_host) != 0) {
+        delete vs;
+        return fail(VPM_ERR_INVALID, "vpm_vspace_create: mass matrix is not positive definite");
+    }
+    const int TS = 2 * order - 1;
+    std::vector<double> z1((size_t)vs->nv + 8, 0.0), z2((size_t)vs->nv, 0.0), z3((size_t)vs->ncell * TS, 0.0), z4(8, 0.0);
+    int rc = VPM_OK;
+    if ((rc = upload(ctx, &vs->pieces, pieces)) || (rc = upload(ctx, &vs->chol, vs->chol_host)) || (rc = upload(ctx, &vs->rhs, z1)) ||
+        (rc = upload(ctx, &vs->coef, z2)) || (rc = upload(ctx, &vs->ftab, z3)) || (rc = upload(ctx, &vs->scal, z4))) {
+        vpm_vspace_destroy(vs);
+        return rc;
+    }
+    *out = vs;
+    return VPM_OK;
+}
+
+int vpm_vspace_destroy(vpm_vspace* vs)
+{
+    if (!vs) return VPM_OK;
+    cudaSetDevice(vs->ctx->device);
+    cudaStreamSynchronize(vs->ctx->stream);
+    cudaFree(vs->pieces); cudaFree(vs->chol); cudaFree(vs->rhs); cudaFree(vs->coef); cudaFree(vs->ftab);
+    cudaFree(vs->scal); cudaFree(vs->diag);
+    delete vs;
+    return VPM_OK;
+}
+
+int vpm_vspace_size(const vpm_vspace* vs) { return vs ? vs->nv : 0; }
+
+int vpm_vspace_mass(const vpm_vspace* vs, double* M)
+{
+    VPM_REQUIRE(vs && M, "vpm_vspace_mass: NULL argument");
+    std::memcpy(M, vs->mass_host.data(), sizeof(double) * vs->mass_host.size());
+    return VPM_OK;
+}
+
+int vpm_deposit_v(vpm_vspace* vs, const double* v_dev, const double* w_dev, int64_t n, double* rhs_host)
+{
+    VPM_REQUIRE(vs && v_dev && w_dev && n >= 0, "vpm_deposit_v: bad arguments");
+    vpm_ctx* ctx = vs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    LbPass p{};
+    p.mode = LB_DEPOSIT_ONLY; p.q = v_dev; p.w = w_dev; p.n = n;
+    int grid = 0;
+    VPM_CHECK(launch_lb_pass(ctx, vs, p, &grid));
+    VPM_CHECK(launch_lb_field(ctx, vs, LBF_REDUCE, grid, 0, -1));
+    if (rhs_host) VPM_CHECK(d2h(ctx, rhs_host, vs->rhs, vs->nv));
+    return VPM_OK;
+}
+
+static int lb_field_local(vpm_ctx* ctx, vpm_vspace* vs, int phases)
+{
+    vpm::Comm saved = ctx->comm;
+    ctx->comm.comm = nullptr;
+    int rc = launch_lb_field(ctx, vs, phases, 0, 0, -1);
+    ctx->comm = saved;
+    return rc;
+}
+
+int vpm_mass_solve_v(vpm_vspace* vs, const double* rhs_host, double* coef_host)
+{
+    VPM_REQUIRE(vs, "vpm_mass_solve_v: vs is NULL");
+    vpm_ctx* ctx = vs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    if (rhs_host) VPM_CHECK(h2d(ctx, vs->rhs, rhs_host, vs->nv));
+    VPM_CHECK(lb_field_local(ctx, vs, LBF_SOLVE | LBF_TABLE));
+    if (coef_host) VPM_CHECK(d2h(ctx, coef_host, vs->coef, vs->nv));
+    return VPM_OK;
+}
+
+int vpm_project_v(vpm_vspace* vs, const double* v_dev, const double* w_dev, int64_t n, double* coef_host)
+{
+    VPM_REQUIRE(vs && v_dev && w_dev && n >= 0, "vpm_project_v: bad arguments");
+    vpm_ctx* ctx = vs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    LbPass p{};
+    p.mode = LB_DEPOSIT_ONLY; p.q = v_dev; p.w = w_dev; p.n = n;
+    int grid = 0;
+    VPM_CHECK(launch_lb_pass(ctx, vs, p, &grid));
+    VPM_CHECK(launch_lb_field(ctx, vs, LBF_REDUCE | LBF_SOLVE | LBF_TABLE, grid, 0, -1));
+    if (coef_host) VPM_CHECK(d2h(ctx, coef_host, vs->coef, vs->nv));
+    return VPM_OK;
+}
+
+static int set_coef(vpm_vspace* vs, const double* coef_host)
+{
+    if (!coef_host) return VPM_OK;
+    VPM_CHECK(h2d(vs->ctx, vs->coef, coef_host, vs->nv));
+    return lb_field_local(vs->ctx, vs, LBF_TABLE);
+}
+
+int vpm_gather_v(vpm_vspace* vs, const double* coef_host, const double* v_dev, int64_t n, double* f_dev, double* df_dev)
+{
+    VPM_REQUIRE(vs && v_dev && n >= 0, "vpm_gather_v: bad arguments");
+    vpm_ctx* ctx = vs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    VPM_CHECK(set_coef(vs, coef_host));
+    LbPass p{};
+    p.mode = LB_EVAL; p.q = v_dev; p.n = n; p.out = f_dev; p.out2 = df_dev;
+    return launch_lb_pass(ctx, vs, p, nullptr);
+}
+
+int vpm_moments(vpm_vspace* vs, const double* coef_host, const double* v_dev, int64_t n, double* out5_host)
+{
+    VPM_REQUIRE(vs && v_dev && n >= 0 && out5_host, "vpm_moments: bad arguments");
+    vpm_ctx* ctx = vs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    VPM_CHECK(set_coef(vs, coef_host));
+    LbPass p{};
+    p.mode = LB_MOMENTS; p.q = v_dev; p.n = n;
+    int grid = 0;
+    VPM_CHECK(launch_lb_pass(ctx, vs, p, &grid));
+    VPM_CHECK(launch_lb_field(ctx, vs, LBF_SCALRED, grid, 5, -1));
+    return d2h(ctx, out5_host, vs->rhs + vs->nv, 5);
+}
+
+// projection + (CLB: moments + coefficients) for the stage input q; leaves tables and A on the device
+static int lb_prepare_clb(vpm_ctx* ctx, vpm_vspace* vs, const double* q, int64_t n)
+{
+    LbPass pm{};
+    pm.mode = LB_MOMENTS; pm.q = q; pm.n = n;
+    int grid = 0;
+    VPM_CHECK(launch_lb_pass(ctx, vs, pm, &grid));
+    return launch_lb_field(ctx, vs, LBF_SCALRED | LBF_COEFF, grid, 5, -1);
+}
+
+int vpm_lb_rhs(vpm_vspace* vs, const double* v_dev, const double* w_dev, int64_t n, double nu, int conservative, double* vdot_dev,
+               double* coef_host, double* A_host)
+{
+    VPM_REQUIRE(vs && v_dev && w_dev && vdot_dev && n >= 0, "vpm_lb_rhs: bad arguments");
+    vpm_ctx* ctx = vs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    VPM_CHECK(vpm_project_v(vs, v_dev, w_dev, n, coef_host));
+    if (conservative) VPM_CHECK(lb_prepare_clb(ctx, vs, v_dev, n));
+    LbPass p{};
+    p.mode = LB_RHS_OUT; p.q = v_dev; p.n = n; p.out = vdot_dev; p.nu = nu; p.conservative = conservative;
+    VPM_CHECK(launch_lb_pass(ctx, vs, p, nullptr));
+    if (A_host) {
+        if (conservative) VPM_CHECK(d2h(ctx, A_host, vs->scal, 2));
+        else { A_host[0] = 0.0; A_host[1] = 1.0; }
+    }
+    return VPM_OK;
+}
+
+static int alloc_scratch(vpm_particles* p)
+{
+    if (p->q) return VPM_OK;
+    const size_t bytes = sizeof(double) * (size_t)(p->n > 0 ? p->n + (p->n & 1) : 2);
+    cudaError_t e1 = cudaMalloc((void**)&p->q, bytes), e2 = cudaMalloc((void**)&p->acc, bytes), e3 = cudaMalloc((void**)&p->d, bytes);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        cudaFree(p->q); cudaFree(p->acc); cudaFree(p->d);
+        p->q = p->acc = p->d = nullptr;
+        return fail(VPM_ERR_NOMEM, "cudaMalloc of RK438 stage arrays failed");
+    }
+    return VPM_OK;
+}
+
+int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double dt, int nsteps, int conservative)
+{
+    VPM_REQUIRE(vs && p && vs->ctx == p->ctx && nsteps >= 0, "vpm_lb_rk438_steps: bad arguments");
+    vpm_ctx* ctx = vs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    VPM_CHECK(alloc_scratch(p));
+    VPM_CHECK(grow_diag(ctx, &vs->diag, &vs->diag_cap, 2 * ((size_t)nsteps + 2)));
+    const int PROJ = LBF_REDUCE | LBF_SOLVE | LBF_TABLE;
+    int grid = 0;
+    LbPass ps{};
+    ps.n = p->n; ps.w = p->w; ps.nu = nu; ps.dt = dt; ps.conservative = conservative;
+    ps.acc = p->acc; ps.d = p->d;
+    {   // projection of the initial state + step-0 diagnostics
+        LbPass p0 = ps;
+        p0.mode = LB_DEPOSIT_ONLY; p0.q = p->v; p0.diag = 1;
+        VPM_CHECK(launch_lb_pass(ctx, vs, p0, &grid));
+        VPM_CHECK(launch_lb_field(ctx, vs, PROJ | LBF_SCALRED | LBF_DIAG, grid, 2, 0));
+    }
+    for (int it = 1; it <= nsteps; it++) {
+        for (int s = 1; s <= 4; s++) {
+            const double* q = s == 1 ? p->v : p->q;
+            if (conservative) VPM_CHECK(lb_prepare_clb(ctx, vs, q, p->n));
+            LbPass st = ps;
+            st.mode = LB_STAGE1 + (s - 1);
+            st.q = q; st.v0 = p->v;
+            st.qout = s == 4 ? p->v : p->q;
+            st.diag = s == 4;
+            VPM_CHECK(launch_lb_pass(ctx, vs, st, &grid));
+            if (s == 4) VPM_CHECK(launch_lb_field(ctx, vs, PROJ | LBF_SCALRED | LBF_DIAG, grid, 2, it));
+            else VPM_CHECK(launch_lb_field(ctx, vs, PROJ, grid, 0, -1));
+        }
+    }
+    return VPM_OK;
+}
+
+int vpm_lb_rk438_steps(vpm_vspace* vs, vpm_particles* p, double nu, double dt, int nsteps, int conservative, double* diag_host)
+{
+    VPM_CHECK(vpm_lb_rk438_steps_async(vs, p, nu, dt, nsteps, conservative));
+    if (diag_host) return d2h(vs->ctx, diag_host, vs->diag, 2 * ((size_t)nsteps + 1));
+    VPM_CUDA(cudaStreamSynchronize(vs->ctx->stream));
+    return VPM_OK;
+}
+
+int vpm_vspace_get(vpm_vspace* vs, double* rhs_host, double* coef_host)
+{
+    VPM_REQUIRE(vs, "vpm_vspace_get: vs is NULL");
+    VPM_CUDA(cudaSetDevice(vs->ctx->device));
+    if (rhs_host) VPM_CHECK(d2h(vs->ctx, rhs_host, vs->rhs, vs->nv));
+    if (coef_host) VPM_CHECK(d2h(vs->ctx, coef_host, vs->coef, vs->nv));
+    return VPM_OK;
+}
+
+/* ---------------------------------------------------------------- multi-GPU */
+
+int vpm_comm_unique_id(void* unique_id_128)
+{
+    VPM_REQUIRE(unique_id_128, "vpm_comm_unique_id: NULL argument");
+    Nccl* api = nccl_api();
+    if (!api) return fail(VPM_ERR_COMM, "libnccl.so.2 could not be loaded");
+    NcclUniqueId id;
+    int r = api->GetUniqueId(&id);
+    if (r != 0) return fail(VPM_ERR_COMM, "ncclGetUniqueId failed");
+    std::memcpy(unique_id_128, &id, sizeof(id));
+    return VPM_OK;
+}
+
+int vpm_comm_init(vpm_ctx* ctx, int nranks, int rank, const void* unique_id_128)
+{
+    VPM_REQUIRE(ctx && unique_id_128 && nranks >= 1 && rank >= 0 && rank < nranks, "vpm_comm_init: bad arguments");
+    Nccl* api = nccl_api();
+    if (!api) return fail(VPM_ERR_COMM, "libnccl.so.2 could not be loaded");
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    vpm_comm_destroy(ctx);
+    NcclUniqueId id;
+    std::memcpy(&id, unique_id_128, sizeof(id));
+    void* comm = nullptr;
+    int r = api->CommInitRank(&comm, nranks, id, rank);
+    if (r != 0) return fail(VPM_ERR_COMM, std::string("ncclCommInitRank: ") + (api->GetErrorString ? api->GetErrorString(r) : "error"));
+    ctx->comm.api = api;
+    ctx->comm.comm = comm;
+    ctx->comm.nranks = nranks;
+    ctx->comm.rank = rank;
+    return VPM_OK;
+}
+
+int vpm_comm_destroy(vpm_ctx* ctx)
+{
+    if (!ctx || !ctx->comm.comm) return VPM_OK;
+    cudaStreamSynchronize(ctx->stream);
+    ctx->comm.api->CommDestroy(ctx->comm.comm);
+    ctx->comm = vpm::Comm{};
+    return VPM_OK;
+}
+
+int vpm_comm_allreduce(vpm_ctx* ctx, double* buf_dev, int64_t count)
+{
+    VPM_REQUIRE(ctx && buf_dev && count >= 0, "vpm_comm_allreduce: bad arguments");
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    return comm_allreduce(ctx, buf_dev, (size_t)count);
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+// Layout conversion at the host boundary and device-side initial conditions.
+//   AoS <-> SoA: Julia's (x;v;w) x N matrix (src/distributions/particle_distribution.jl:11-17) and the
+//                integrator's 2 x N state (src/models/vlasov_poisson.jl:81)
+//   samplers:    BumpOnTail (src/examples/bumpontail.jl:43-75), NormalDistribution v-part
+//                (src/examples/normal.jl:16), DoubleMaxwellian (src/examples/doublemaxwellian.jl:15-35)
+#include "vpm_internal.h"
+
+namespace vpm {
+
+namespace {
+
+__global__ void aos_to_soa_kernel(const double* __restrict__ z, int ld, long long n, double* __restrict__ x,
+                                  double* __restrict__ v, double* __restrict__ w)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double* r = z + i * ld;
+        x[i] = r[0];
+        v[i] = r[1];
+        if (ld > 2 && w) w[i] = r[2];
+    }
+}
+
+__global__ void soa_to_aos_kernel(const double* __restrict__ x, const double* __restrict__ v, const double* __restrict__ w,
+                                  int ld, long long n, double* __restrict__ z)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double* r = z + i * ld;
+        r[0] = x[i];
+        r[1] = v[i];
+        if (ld > 2 && w) r[2] = w[i];
+    }
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+// counter-based uniform in (0,1): the same function of (seed, global index, stream) on every rank
+__device__ __forceinline__ double uniform01(uint64_t seed, uint64_t idx, uint32_t stream)
+{
+    const uint64_t key = mix64(seed + 0x632BE59BD9B4E019ULL * (uint64_t)(stream + 1u));
+    const uint64_t r = mix64(key + idx * 0x9E3779B97F4A7C15ULL);
+    return ((double)(r >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// Wichura AS241 (PPND16) inverse normal CDF; sqrt(2) erfinv(2y-1) of bumpontail.jl:68-69
+__device__ double norminv(double p)
+{
+    const double q = p - 0.5;
+    double r, val;
+    if (fabs(q) <= 0.425) {
+        r = 0.180625 - q * q;
+        val = q * (((((((2.5090809287301226727e3 * r + 3.3430575583588128105e4) * r + 6.7265770927008700853e4) * r + 4.5921953931549871457e4) * r + 1.3731693765509461125e4) * r + 1.9715909503065514427e3) * r + 1.3314166789178437745e2) * r + 3.3871328727963666080e0) /
+              (((((((5.2264952788528545610e3 * r + 2.8729085735721942674e4) * r + 3.9307895800092710610e4) * r + 2.1213794301586595867e4) * r + 5.3941960214247511077e3) * r + 6.8718700749205790830e2) * r + 4.2313330701600911252e1) * r + 1.0);
+        return val;
+    }
+    r = q < 0 ? p : 1.0 - p;
+    r = sqrt(-log(r));
+    if (r <= 5.0) {
+        r -= 1.6;
+        val = (((((((7.74545014278341407640e-4 * r + 2.27238449892691845833e-2) * r + 2.41780725177450611770e-1) * r + 1.27045825245236838258e0) * r + 3.64784832476320460504e0) * r + 5.76949722146069140550e0) * r + 4.63033784615654529590e0) * r + 1.42343711074968357734e0) /
+              (((((((1.05075007164441684324e-9 * r + 5.47593808499534494600e-4) * r + 1.51986665636164571966e-2) * r + 1.48103976427480074590e-1) * r + 6.89767334985100004550e-1) * r + 1.67638483018380384940e0) * r + 2.05319162663775882187e0) * r + 1.0);
+    } else {
+        r -= 5.0;
+        val = (((((((2.01033439929228813265e-7 * r + 2.71155556874348757815e-5) * r + 1.24266094738807843860e-3) * r + 2.65321895265761230930e-2) * r + 2.96560571828504891230e-1) * r + 1.78482653991729133580e0) * r + 5.46378491116411436990e0) * r + 6.65790464350110377720e0) /
+              (((((((2.04426310338993978564e-15 * r + 1.42151175831644588870e-7) * r + 1.84631831751005468180e-5) * r + 7.86869131145613259100e-4) * r + 1.48753612908506148525e-2) * r + 1.36929880922735805310e-1) * r + 5.99832206555887937690e-1) * r + 1.0);
+    }
+    return q < 0 ? -val : val;
+}
+
+// inverse CDF of the x-marginal 1 - eps cos(kappa x) on [0, 2 pi / kappa)  (bumpontail.jl:27-30)
+__device__ double inv_cdf_cos(double u, double eps, double kappa)
+{
+    const double L = 6.283185307179586476925286766559 / kappa, target = u * L;
+    double x = target;
+    for (int it = 0; it < 8; it++) {
+        const double F = x - eps * sin(kappa * x) / kappa - target;
+        const double dF = 1.0 - eps * cos(kappa * x);
+        x -= F / dF;
+    }
+    return x;
+}
+
+__global__ void sample_bot_kernel(long long n, long long offset, long long ntotal, uint64_t seed, double eps, double kappa,
+                                  double alpha, double sigma, double v0, double* __restrict__ x, double* __restrict__ v,
+                                  double* __restrict__ w)
+{
+    const double L = 6.283185307179586476925286766559 / kappa;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t gi = (uint64_t)(offset + i);
+        x[i] = inv_cdf_cos(uniform01(seed, gi, 0), eps, kappa);
+        double vv = norminv(uniform01(seed, gi, 1));
+        if (uniform01(seed, gi, 2) > 1.0 - alpha) vv = vv * sigma + v0;
+        v[i] = vv;
+        w[i] = L / (double)ntotal;
+    }
+}
+
+__global__ void sample_maxwellian_kernel(long long n, long long offset, long long ntotal, uint64_t seed, double xlo, double xhi,
+                                         double shift, int doubled, double wnum, double* __restrict__ x,
+                                         double* __restrict__ v, double* __restrict__ w)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t gi = (uint64_t)(offset + i);
+        x[i] = xlo + (xhi - xlo) * uniform01(seed, gi, 0);
+        double vv = norminv(uniform01(seed, gi, 1));
+        if (doubled) vv += ((long long)gi < ntotal / 2) ? shift : -shift;
+        else vv += shift;
+        v[i] = vv;
+        w[i] = wnum / (double)ntotal;
+    }
+}
+
+unsigned grid_for(vpm_ctx* ctx, long long n, int block)
+{
+    long long g = (n + block - 1) / block;
+    const long long cap = (long long)ctx->sm_count * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+}  // namespace
+
+int launch_aos_to_soa(vpm_ctx* ctx, const double* z, int ld, int64_t n, double* x, double* v, double* w)
+{
+    aos_to_soa_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(z, ld, n, x, v, w);
+    ctx->launches++;
+    VPM_CUDA(cudaGetLastError());
+    return VPM_OK;
+}
+
+int launch_soa_to_aos(vpm_ctx* ctx, const double* x, const double* v, const double* w, int ld, int64_t n, double* z)
+{
+    soa_to_aos_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(x, v, w, ld, n, z);
+    ctx->launches++;
+    VPM_CUDA(cudaGetLastError());
+    return VPM_OK;
+}
+
+int launch_sample_bump_on_tail(vpm_ctx* ctx, vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed, double eps,
+                               double kappa, double alpha, double sigma, double v0)
+{
+    sample_bot_kernel<<<grid_for(ctx, p->n, 256), 256, 0, ctx->stream>>>(p->n, offset, ntotal, seed, eps, kappa, alpha, sigma, v0,
+                                                                      p->x, p->v, p->w);
+    ctx->launches++;
+    VPM_CUDA(cudaGetLastError());
+    return VPM_OK;
+}
+
+int launch_sample_maxwellian(vpm_ctx* ctx, vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed, double xlo,
+                             double xhi, double shift, int doubled, double wnum)
+{
+    sample_maxwellian_kernel<<<grid_for(ctx, p->n, 256), 256, 0, ctx->stream>>>(p->n, offset, ntotal, seed, xlo, xhi, shift, doubled,
+                                                                             wnum, p->x, p->v, p->w);
+    ctx->launches++;
+    VPM_CUDA(cudaGetLastError());
+    return VPM_OK;
+}
+
+}  // namespace vpm

@@ -1,0 +1,423 @@
+// Vlasov-Poisson particle passes and the single-CTA field kernel.
+//
+// Replaces (behaviour, not code) the Julia loops of
+//   projection!(potential, distribution)       src/projections/potential.jl:2-22     (deposit)
+//   PoissonSolvers.update!(potential)          call site src/models/vlasov_poisson.jl:14 (solve)
+//   phi(x, Derivative(1)) + s_acceleration!    src/models/vlasov_poisson.jl:61-67    (gather + kick)
+//   s_advection!                               src/models/vlasov_poisson.jl:53-58    (drift)
+//   save_timestep! diagnostics                 src/vlasov_poisson.jl:58-67           (W, K, M)
+//
+// Design: one streaming pass per Strang step does kick + drift + deposit-for-the-
+// next-step (40 B/particle).  The scatter is atomics-free: every thread owns a private histogram of
+// the nh+K-1 unwrapped bins in shared memory (bin-major, so a warp's 64-bit accesses are
+// conflict-free), the CTA reduces its histograms in a fixed order and writes one partial row; the
+// single-CTA field kernel sums the rows in a fixed order, (all-reduces across GPUs,) solves the
+// circulant Poisson system by convolution with the precomputed pseudo-inverse and emits the per-cell
+// polynomial table of E that the next pass evaluates by Horner.  Results are bitwise reproducible
+// run to run.
+#include <cstdlib>
+
+#include "splines.cuh"
+#include "vpm_internal.h"
+
+namespace vpm {
+
+namespace {
+
+struct VpDev {
+    const double *x_in, *v_in, *w;
+    double *x_out, *v_out;
+    long long n;
+    int flags;
+    double tau_pre, tau_kick, tau_post1, tau_post2;
+    double lo, invh;
+    int nh;
+    FastMod fm;
+    const double* etab;
+    double* partials;
+    double* kin_partials;
+    int nbp;
+};
+
+template <int K>
+struct VpCfg {
+    static constexpr int ES = (K - 1) | 1;  // odd row stride of the E table: conflict-free for <= 16 cells
+};
+
+constexpr int kMainFlags = VP_KICK1 | VP_POST1 | VP_DIAG | VP_POST2 | VP_DEPOSIT | VP_WRITE_X | VP_WRITE_V;
+constexpr int kFrozenFlags = VP_PRE | VP_KICK1 | VP_KICK2 | VP_POST1 | VP_DIAG | VP_WRITE_X | VP_WRITE_V;
+
+template <int K, int FLAGS>
+__device__ __forceinline__ void vp_particle(const VpDev& P, const int flags_rt, const double* __restrict__ s_etab,
+                                            double* __restrict__ s_hist, double& x, double& v, const double w,
+                                            double& ksum, double& msum)
+{
+    constexpr int ES = VpCfg<K>::ES;
+    const int flags = FLAGS >= 0 ? FLAGS : flags_rt;
+    if (flags & VP_PRE) x = fma(P.tau_pre, v, x);
+    if (flags & VP_KICK1) {
+        int ci;
+        double u;
+        split_floor((x - P.lo) * P.invh, ci, u);
+        const double* e = s_etab + wrap_index(ci, P.fm) * ES;
+        double E = e[K - 2];
+#pragma unroll
+        for (int m = K - 3; m >= 0; m--) E = fma(E, u, e[m]);
+        v = fma(P.tau_kick, E, v);
+        if (flags & VP_KICK2) v = fma(P.tau_kick, E, v);
+    }
+    if (flags & VP_POST1) x = fma(P.tau_post1, v, x);
+    if (flags & VP_DIAG) {
+        const double wv = w * v;
+        msum += wv;
+        ksum = fma(wv, v, ksum);
+    }
+    if (flags & VP_POST2) x = fma(P.tau_post2, v, x);
+    if (flags & VP_DEPOSIT) {
+        int ci;
+        double u, b[K];
+        split_floor((x - P.lo) * P.invh, ci, u);
+        basis_uniform<K>(u, b);
+        // bins are unwrapped: cell c feeds bins c..c+K-1 (function c-K+1+j lives in bin c+j, folded
+        // mod nh by the field kernel) -> one address computation, K immediate-offset RMWs
+        double* hcell = s_hist + wrap_index(ci, P.fm) * kBlock;
+#pragma unroll
+        for (int j = 0; j < K; j++) hcell[j * kBlock] = fma(w, b[j], hcell[j * kBlock]);
+    }
+}
+
+// VEC = 2: 16-byte loads/stores, two particles per thread per trip, next trip prefetched.
+template <int K, int FLAGS, int VEC, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
+{
+    extern __shared__ double smem[];
+    constexpr int ES = VpCfg<K>::ES;
+    const int flags = FLAGS >= 0 ? FLAGS : P.flags;
+    const int tid = threadIdx.x;
+    const int nb = P.nh + K - 1;
+    double* s_red = smem;                       // 2 * warps
+    double* s_etab = smem + 2 * (kBlock / 32);  // nh * ES
+    double* s_hist = s_etab + ((P.nh * ES + 1) & ~1) + tid;  // nb * kBlock, this thread's column
+
+    if (flags & VP_KICK1)
+        for (int i = tid; i < P.nh * ES; i += kBlock) s_etab[i] = P.etab[i];
+    if (flags & VP_DEPOSIT)
+        for (int b = 0; b < nb; b++) s_hist[b * kBlock] = 0.0;
+    __syncthreads();
+
+    double ksum = 0.0, msum = 0.0;
+    const bool need_v = flags & (VP_PRE | VP_KICK1 | VP_POST1 | VP_POST2 | VP_DIAG);
+    const bool need_w = flags & (VP_DIAG | VP_DEPOSIT);
+    const long long stride = (long long)gridDim.x * kBlock;
+    const long long gtid = (long long)blockIdx.x * kBlock + tid;
+
+    if (VEC == 2) {
+        const long long nvec = P.n >> 1;
+        long long i = gtid;
+        double2 xa = make_double2(0, 0), va = xa, wa = xa;
+        bool have = i < nvec;
+        if (have) {
+            xa = ld_stream2(P.x_in + 2 * i);
+            if (need_v) va = ld_stream2(P.v_in + 2 * i);
+            if (need_w) wa = ld_stream2(P.w + 2 * i);
+        }
+        while (have) {
+            const long long inext = i + stride;
+            const bool hn = inext < nvec;
+            double2 xn = make_double2(0, 0), vn = xn, wn = xn;
+            if (hn) {
+                xn = ld_stream2(P.x_in + 2 * inext);
+                if (need_v) vn = ld_stream2(P.v_in + 2 * inext);
+                if (need_w) wn = ld_stream2(P.w + 2 * inext);
+            }
+            vp_particle<K, FLAGS>(P, flags, s_etab, s_hist, xa.x, va.x, wa.x, ksum, msum);
+            vp_particle<K, FLAGS>(P, flags, s_etab, s_hist, xa.y, va.y, wa.y, ksum, msum);
+            if (flags & VP_WRITE_X) st_stream2(P.x_out + 2 * i, xa);
+            if (flags & VP_WRITE_V) st_stream2(P.v_out + 2 * i, va);
+            xa = xn; va = vn; wa = wn;
+            i = inext;
+            have = hn;
+        }
+        if ((P.n & 1) && gtid == 0) {  // odd tail
+            const long long t = P.n - 1;
+            double x = P.x_in[t], v = need_v ? P.v_in[t] : 0.0, w = need_w ? P.w[t] : 0.0;
+            vp_particle<K, FLAGS>(P, flags, s_etab, s_hist, x, v, w, ksum, msum);
+            if (flags & VP_WRITE_X) P.x_out[t] = x;
+            if (flags & VP_WRITE_V) P.v_out[t] = v;
+        }
+    } else {
+        for (long long i = gtid; i < P.n; i += stride) {
+            double x = P.x_in[i], v = need_v ? P.v_in[i] : 0.0, w = need_w ? P.w[i] : 0.0;
+            vp_particle<K, FLAGS>(P, flags, s_etab, s_hist, x, v, w, ksum, msum);
+            if (flags & VP_WRITE_X) P.x_out[i] = x;
+            if (flags & VP_WRITE_V) P.v_out[i] = v;
+        }
+    }
+
+    const int lane = tid & 31, warp = tid >> 5;
+    if (flags & VP_DEPOSIT) {
+        __syncthreads();
+        const double* hist = s_hist - tid;
+        for (int b = warp; b < nb; b += kBlock / 32) {
+            double s = 0.0;
+#pragma unroll
+            for (int t = 0; t < kBlock / 32; t++) s += hist[b * kBlock + t * 32 + lane];
+            s = warp_sum(s);
+            if (lane == 0) P.partials[(size_t)blockIdx.x * P.nbp + b] = s;
+        }
+    }
+    if (flags & VP_DIAG) {
+        ksum = warp_sum(ksum);
+        msum = warp_sum(msum);
+        if (lane == 0) {
+            s_red[2 * warp] = ksum;
+            s_red[2 * warp + 1] = msum;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double k = 0.0, m = 0.0;
+            for (int wi = 0; wi < kBlock / 32; wi++) {
+                k += s_red[2 * wi];
+                m += s_red[2 * wi + 1];
+            }
+            P.kin_partials[2 * blockIdx.x] = k;
+            P.kin_partials[2 * blockIdx.x + 1] = m;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Field kernel: one CTA.  rhs buffer layout: rhs[0..nh) | Ksum | Msum  (one all-reduce payload).
+// ---------------------------------------------------------------------------------------------
+struct FieldDev {
+    const double* partials;
+    const double* kin_partials;
+    int nparts, nbp, nb, has_dep, has_kin;
+    double *rhs, *phi, *etab, *diag;
+    const double *ginv, *stiff, *dpiece;
+    int nh, K, ES;
+    double invh, escale, wscale;
+    int phases, w_slot, km_slot;
+};
+
+__global__ void __launch_bounds__(kFieldThreads) vp_field_kernel(const FieldDev F)
+{
+    extern __shared__ double sm[];
+    double* s_ru = sm;               // nb (unwrapped bins) + 2
+    double* s_b = s_ru + F.nb + 2;   // nh
+    double* s_phi = s_b + F.nh;      // nh
+    double* s_d = s_phi + F.nh;      // nh
+    __shared__ double s_scal[4];
+    __shared__ double s_w[kFieldThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kFieldThreads / 32;
+    const int nh = F.nh, K = F.K;
+
+    if (F.phases & FIELD_REDUCE) {
+        // fixed-order reduction of the per-CTA partial rows: lane-strided partial sums + xor tree
+        if (F.has_dep) {
+            for (int b = warp; b < F.nb; b += nwarps) {
+                double s = 0.0;
+                for (int p = lane; p < F.nparts; p += 32) s += F.partials[(size_t)p * F.nbp + b];
+                s = warp_sum(s);
+                if (lane == 0) s_ru[b] = s;
+            }
+        }
+        if (F.has_kin && warp < 2) {
+            double s = 0.0;
+            for (int p = lane; p < F.nparts; p += 32) s += F.kin_partials[2 * p + warp];
+            s = warp_sum(s);
+            if (lane == 0) F.rhs[nh + warp] = s;
+        }
+        __syncthreads();
+        if (F.has_dep)
+            for (int i = tid; i < nh; i += kFieldThreads) {
+                // bin b holds basis function (b - (K-1)) mod nh: fold the wrapped bins
+                double s = 0.0;
+                for (int b = (i + K - 1) % nh; b < F.nb; b += nh) s += s_ru[b];
+                F.rhs[i] = s;
+            }
+        __syncthreads();
+    }
+
+    if (F.phases & FIELD_SOLVE) {
+        // S phi = rhs - mean(rhs), zero-mean gauge: phi = pinv(S) (rhs - mean) by circular convolution
+        for (int i = tid; i < nh; i += kFieldThreads) s_b[i] = F.rhs[i];
+        __syncthreads();
+        if (warp == 0) {
+            double s = 0.0;
+            for (int i = lane; i < nh; i += 32) s += s_b[i];
+            s = warp_sum(s);
+            if (lane == 0) s_scal[0] = s / (double)nh;
+        }
+        __syncthreads();
+        const double mean = s_scal[0];
+        for (int i = tid; i < nh; i += kFieldThreads) {
+            double s = 0.0;
+            for (int j = 0; j < nh; j++) {
+                int d = i - j;
+                if (d < 0) d += nh;
+                s = fma(F.ginv[d], s_b[j] - mean, s);
+            }
+            s_phi[i] = s;
+            F.phi[i] = s;
+        }
+        __syncthreads();
+        if (F.w_slot >= 0 && F.diag) {
+            // W = phi' S phi / 2 (src/electric_field.jl:47), scaled by 1/chi^2 (:33)
+            double s = 0.0;
+            for (int i = tid; i < nh; i += kFieldThreads) {
+                double r = 0.0;
+                for (int d = -(K - 1); d <= K - 1; d++) {
+                    int j = (i + d) % nh;
+                    if (j < 0) j += nh;
+                    r = fma(F.stiff[d + K - 1], s_phi[j], r);
+                }
+                s = fma(s_phi[i], r, s);
+            }
+            s = warp_sum(s);
+            if (lane == 0) s_w[warp] = s;
+            __syncthreads();
+            if (tid == 0) {
+                double t = 0.0;
+                for (int wi = 0; wi < nwarps; wi++) t += s_w[wi];
+                F.diag[3 * F.w_slot] = 0.5 * t * F.wscale;
+            }
+            __syncthreads();
+        }
+    } else if (F.phases & FIELD_TABLE) {
+        for (int i = tid; i < nh; i += kFieldThreads) s_phi[i] = F.phi[i];
+        __syncthreads();
+    }
+
+    if (F.phases & FIELD_TABLE) {
+        // phi' = sum_i d_i B^{K-1}_i, d_i = (phi_i - phi_{i-1})/h ; on cell c the functions
+        // i = c-K+2..c are the pieces dpiece[j][m]; E-table = escale * phi' in monomials of u
+        for (int i = tid; i < nh; i += kFieldThreads) s_d[i] = (s_phi[i] - s_phi[(i + nh - 1) % nh]) * F.invh;
+        __syncthreads();
+        const int K1 = K - 1;
+        for (int idx = tid; idx < nh * K1; idx += kFieldThreads) {
+            const int c = idx / K1, m = idx - c * K1;
+            double s = 0.0;
+            for (int j = 0; j < K1; j++) {
+                int i = (c - K + 2 + j) % nh;
+                if (i < 0) i += nh;
+                s = fma(s_d[i], F.dpiece[j * K1 + m], s);
+            }
+            F.etab[c * F.ES + m] = F.escale * s;
+        }
+    }
+
+    __syncthreads();
+    if (F.km_slot >= 0 && F.diag && tid == 0) {
+        F.diag[3 * F.km_slot + 1] = 0.5 * F.rhs[nh];
+        F.diag[3 * F.km_slot + 2] = F.rhs[nh + 1];
+    }
+}
+
+template <int K>
+int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* grid_out)
+{
+    constexpr int ES = VpCfg<K>::ES;
+    VpDev P{};
+    P.x_in = p.x_in; P.v_in = p.v_in; P.w = p.w; P.x_out = p.x_out; P.v_out = p.v_out;
+    P.n = p.n; P.flags = p.flags;
+    P.tau_pre = p.tau_pre; P.tau_kick = p.tau_kick; P.tau_post1 = p.tau_post1; P.tau_post2 = p.tau_post2;
+    P.lo = xs->lo; P.invh = xs->invh; P.nh = xs->nh; P.fm = xs->fm;
+    P.etab = xs->etab;
+    const int nb = xs->nh + K - 1;
+    P.nbp = nb;
+
+    const bool dep = p.flags & VP_DEPOSIT;
+    size_t smem = sizeof(double) * (2 * (kBlock / 32) + ((xs->nh * ES + 1) & ~1) + (dep ? (size_t)nb * kBlock : 0));
+    if (smem > ctx->smem_optin)
+        return fail(VPM_ERR_UNSUPPORTED, "x-space too large for the shared-memory privatised deposit (n_basis + order - 1 bins x 2 KiB per CTA)");
+
+    auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const bool vec = aligned16(p.x_in) && aligned16(p.v_in) && aligned16(p.w) && aligned16(p.x_out) && aligned16(p.v_out);
+
+    // VPM_TUNE_MINB = 2|3|4 selects the register/occupancy trade-off of the fused step kernel
+    // (91 / 85 / 64 registers per thread); default chosen from ncu runs, see DESIGN.md
+    static const int tune_minb = [] {
+        const char* e = getenv("VPM_TUNE_MINB");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 2 && v <= 4) ? v : 3;
+    }();
+    void (*kern)(const VpDev) = nullptr;
+    if (vec && p.flags == kMainFlags) {
+        kern = tune_minb == 2 ? vp_pass_kernel<K, kMainFlags, 2, 2>
+             : tune_minb == 4 ? vp_pass_kernel<K, kMainFlags, 2, 4> : vp_pass_kernel<K, kMainFlags, 2, 3>;
+    } else if (vec && p.flags == kFrozenFlags) kern = vp_pass_kernel<K, kFrozenFlags, 2, 3>;
+    else if (vec) kern = vp_pass_kernel<K, -1, 2, 3>;
+    else kern = vp_pass_kernel<K, -1, 1, 3>;
+
+    VPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    VPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem));
+    if (occ < 1) return fail(VPM_ERR_UNSUPPORTED, "vp pass kernel does not fit on an SM");
+    long long want = (p.n / (vec ? 2 : 1) + kBlock - 1) / kBlock;
+    if (want < 1) want = 1;
+    long long grid = (long long)ctx->sm_count * occ;
+    if (grid > want) grid = want;
+
+    int rc = ensure_partials(ctx, (size_t)grid * (nb + 2));
+    if (rc) return rc;
+    P.partials = ctx->partials;
+    P.kin_partials = ctx->partials + (size_t)grid * nb;
+
+    kern<<<(unsigned)grid, kBlock, smem, ctx->stream>>>(P);
+    ctx->launches++;
+    VPM_CUDA(cudaGetLastError());
+    if (grid_out) *grid_out = (int)grid;
+    return VPM_OK;
+}
+
+}  // namespace
+
+int launch_vp_pass(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* grid_out)
+{
+    switch (xs->K) {
+        case 2: return launch_vp_pass_k<2>(ctx, xs, p, grid_out);
+        case 3: return launch_vp_pass_k<3>(ctx, xs, p, grid_out);
+        case 4: return launch_vp_pass_k<4>(ctx, xs, p, grid_out);
+        case 5: return launch_vp_pass_k<5>(ctx, xs, p, grid_out);
+        case 6: return launch_vp_pass_k<6>(ctx, xs, p, grid_out);
+    }
+    return fail(VPM_ERR_UNSUPPORTED, "spline order must be 2..6");
+}
+
+int launch_vp_field(vpm_ctx* ctx, vpm_xspace* xs, int phases, int nparts, int has_dep, int has_kin, double escale,
+                    double wscale, int w_slot, int km_slot)
+{
+    FieldDev F{};
+    const int nb = xs->nh + xs->K - 1;
+    F.partials = ctx->partials;
+    F.kin_partials = ctx->partials + (size_t)nparts * nb;
+    F.nparts = nparts; F.nbp = nb; F.nb = nb; F.has_dep = has_dep; F.has_kin = has_kin;
+    F.rhs = xs->rhs; F.phi = xs->phi; F.etab = xs->etab; F.diag = xs->diag;
+    F.ginv = xs->ginv; F.stiff = xs->stiff; F.dpiece = xs->dpiece;
+    F.nh = xs->nh; F.K = xs->K; F.ES = (xs->K - 1) | 1;
+    F.invh = xs->invh; F.escale = escale; F.wscale = wscale;
+    F.w_slot = w_slot; F.km_slot = km_slot;
+    const size_t smem = sizeof(double) * ((size_t)nb + 2 + 3 * (size_t)xs->nh);
+
+    // multi-GPU: reduce locally, all-reduce rhs|K|M, then solve
+    if (ctx->comm.comm && (phases & FIELD_REDUCE) && (has_dep || has_kin)) {
+        F.phases = FIELD_REDUCE;
+        F.w_slot = F.km_slot = -1;
+        vp_field_kernel<<<1, kFieldThreads, smem, ctx->stream>>>(F);
+        ctx->launches++;
+        VPM_CUDA(cudaGetLastError());
+        int rc = comm_allreduce(ctx, xs->rhs, (size_t)xs->nh + 2);
+        if (rc) return rc;
+        phases &= ~FIELD_REDUCE;
+        F.w_slot = w_slot; F.km_slot = km_slot;
+        if (!(phases & (FIELD_SOLVE | FIELD_TABLE)) && km_slot < 0) return VPM_OK;
+    }
+    F.phases = phases;
+    vp_field_kernel<<<1, kFieldThreads, smem, ctx->stream>>>(F);
+    ctx->launches++;
+    VPM_CUDA(cudaGetLastError());
+    return VPM_OK;
+}
+
+}  // namespace vpm
