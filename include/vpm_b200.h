@@ -56,6 +56,11 @@ int vpm_sync(vpm_ctx* ctx);
 int vpm_device_info(vpm_ctx* ctx, int* sm_count, int64_t* smem_optin_bytes, int64_t* total_mem_bytes);
 /* number of kernels this ctx has launched so far (bench.py "gpu_launches") */
 int64_t vpm_launch_count(vpm_ctx* ctx);
+/* Per-launch timing with CUDA events on the ctx stream (bench.py roofline): enable != 0 clears and starts
+ * recording, 0 stops.  vpm_profile_get sums elapsed milliseconds and launch counts by kernel kind
+ * (8 entries each): 0 = VP particle pass, 1 = VP field kernel, 2 = LB particle pass, 3 = LB field kernel. */
+int vpm_profile(vpm_ctx* ctx, int enable);
+int vpm_profile_get(vpm_ctx* ctx, double* ms_by_kind, int64_t* count_by_kind);
 /* pinned host buffers for the host-array entry points */
 int vpm_host_alloc(int64_t bytes, void** out);
 int vpm_host_free(void* p);

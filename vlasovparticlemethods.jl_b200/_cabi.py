@@ -26,6 +26,8 @@ SIGNATURES = {
     "vpm_sync": (_i32, [_vp]),
     "vpm_device_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i64)]),
     "vpm_launch_count": (_i64, [_vp]),
+    "vpm_profile": (_i32, [_vp, _i32]),
+    "vpm_profile_get": (_i32, [_vp, _vp, _vp]),
     "vpm_host_alloc": (_i32, [_i64, C.POINTER(_vp)]),
     "vpm_host_free": (_i32, [_vp]),
     "vpm_dev_alloc": (_i32, [_vp, _i64, C.POINTER(_vp)]),

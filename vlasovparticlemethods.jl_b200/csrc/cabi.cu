@@ -86,6 +86,24 @@ int comm_allreduce(vpm_ctx* ctx, double* buf, size_t count)
     return VPM_OK;
 }
 
+void prof_begin(vpm_ctx* ctx, int kind)
+{
+    if (!ctx->profile) return;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    ctx->prof_events.push_back(e0);
+    ctx->prof_events.push_back(e1);
+    ctx->prof_kinds.push_back(kind);
+    cudaEventRecord(e0, ctx->stream);
+}
+
+void prof_end(vpm_ctx* ctx)
+{
+    if (!ctx->profile) return;
+    cudaEventRecord(ctx->prof_events.back(), ctx->stream);
+}
+
 template <typename T>
 static int upload(vpm_ctx* ctx, double** dst, const std::vector<T>& src)
 {
@@ -186,6 +204,31 @@ int vpm_device_info(vpm_ctx* ctx, int* sm_count, int64_t* smem_optin_bytes, int6
 }
 
 int64_t vpm_launch_count(vpm_ctx* ctx) { return ctx ? (int64_t)ctx->launches : 0; }
+
+int vpm_profile(vpm_ctx* ctx, int enable)
+{
+    VPM_REQUIRE(ctx, "vpm_profile: ctx is NULL");
+    VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    ctx->prof_events.clear();
+    ctx->prof_kinds.clear();
+    ctx->profile = enable != 0;
+    return VPM_OK;
+}
+
+int vpm_profile_get(vpm_ctx* ctx, double* ms_by_kind, int64_t* count_by_kind)
+{
+    VPM_REQUIRE(ctx && ms_by_kind && count_by_kind, "vpm_profile_get: NULL argument");
+    VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < PROF_NKIND; k++) { ms_by_kind[k] = 0.0; count_by_kind[k] = 0; }
+    for (size_t i = 0; i < ctx->prof_kinds.size(); i++) {
+        float ms = 0.f;
+        VPM_CUDA(cudaEventElapsedTime(&ms, ctx->prof_events[2 * i], ctx->prof_events[2 * i + 1]));
+        ms_by_kind[ctx->prof_kinds[i]] += ms;
+        count_by_kind[ctx->prof_kinds[i]] += 1;
+    }
+    return VPM_OK;
+}
 
 int vpm_host_alloc(int64_t bytes, void** out)
 {

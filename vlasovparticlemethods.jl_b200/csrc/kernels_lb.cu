@@ -432,7 +432,9 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
     if (rc) return rc;
     P.partials = ctx->partials;
     P.red_partials = ctx->partials + (size_t)grid * vs->nbfull;
+    prof_begin(ctx, PROF_LB_PASS);
     kern<<<(unsigned)grid, kBlock, smem, ctx->stream>>>(P);
+    prof_end(ctx);
     ctx->launches++;
     VPM_CUDA(cudaGetLastError());
     if (grid_out) *grid_out = (int)grid;
@@ -468,7 +470,9 @@ int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nr
     const int red = phases & (LBF_REDUCE | LBF_SCALRED);
     if (ctx->comm.comm && red) {
         F.phases = red;
-        lb_field_kernel<<<1, kFieldThreads, smem, ctx->stream>>>(F);
+        prof_begin(ctx, PROF_LB_FIELD);
+    lb_field_kernel<<<1, kFieldThreads, smem, ctx->stream>>>(F);
+    prof_end(ctx);
         ctx->launches++;
         VPM_CUDA(cudaGetLastError());
         // rhs | scalars are contiguous: one all-reduce
@@ -481,7 +485,9 @@ int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nr
         if (!phases) return VPM_OK;
     }
     F.phases = phases;
+    prof_begin(ctx, PROF_LB_FIELD);
     lb_field_kernel<<<1, kFieldThreads, smem, ctx->stream>>>(F);
+    prof_end(ctx);
     ctx->launches++;
     VPM_CUDA(cudaGetLastError());
     return VPM_OK;

@@ -364,7 +364,9 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     P.partials = ctx->partials;
     P.kin_partials = ctx->partials + (size_t)grid * nb;
 
+    prof_begin(ctx, PROF_VP_PASS);
     kern<<<(unsigned)grid, kBlock, smem, ctx->stream>>>(P);
+    prof_end(ctx);
     ctx->launches++;
     VPM_CUDA(cudaGetLastError());
     if (grid_out) *grid_out = (int)grid;
@@ -404,7 +406,9 @@ int launch_vp_field(vpm_ctx* ctx, vpm_xspace* xs, int phases, int nparts, int ha
     if (ctx->comm.comm && (phases & FIELD_REDUCE) && (has_dep || has_kin)) {
         F.phases = FIELD_REDUCE;
         F.w_slot = F.km_slot = -1;
-        vp_field_kernel<<<1, kFieldThreads, smem, ctx->stream>>>(F);
+        prof_begin(ctx, PROF_VP_FIELD);
+    vp_field_kernel<<<1, kFieldThreads, smem, ctx->stream>>>(F);
+    prof_end(ctx);
         ctx->launches++;
         VPM_CUDA(cudaGetLastError());
         int rc = comm_allreduce(ctx, xs->rhs, (size_t)xs->nh + 2);
@@ -414,7 +418,9 @@ int launch_vp_field(vpm_ctx* ctx, vpm_xspace* xs, int phases, int nparts, int ha
         if (!(phases & (FIELD_SOLVE | FIELD_TABLE)) && km_slot < 0) return VPM_OK;
     }
     F.phases = phases;
+    prof_begin(ctx, PROF_VP_FIELD);
     vp_field_kernel<<<1, kFieldThreads, smem, ctx->stream>>>(F);
+    prof_end(ctx);
     ctx->launches++;
     VPM_CUDA(cudaGetLastError());
     return VPM_OK;

@@ -58,6 +58,10 @@ struct vpm_ctx {
     size_t staging_cap = 0;    // doubles
     vpm::Comm comm;
     uint64_t launches = 0;     // kernels launched by this library (bench "gpu_launches")
+    // optional per-launch CUDA-event timing (vpm_profile): pairs of events on the launching stream
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<int> prof_kinds;
 };
 
 struct vpm_particles {
@@ -109,6 +113,9 @@ int ensure_partials(vpm_ctx* ctx, size_t doubles);
 int ensure_red(vpm_ctx* ctx, size_t doubles);
 int ensure_staging(vpm_ctx* ctx, size_t doubles);
 int comm_allreduce(vpm_ctx* ctx, double* buf, size_t count);
+enum ProfKind : int { PROF_VP_PASS = 0, PROF_VP_FIELD = 1, PROF_LB_PASS = 2, PROF_LB_FIELD = 3, PROF_OTHER = 4, PROF_NKIND = 8 };
+void prof_begin(vpm_ctx* ctx, int kind);   // no-ops unless ctx->profile
+void prof_end(vpm_ctx* ctx);
 
 // ---------------- Vlasov-Poisson passes (kernels_vp.cu) ----------------
 enum VpFlags : int {
