@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the fused Vlasov-Poisson Strang step on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, via the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: oracle port of the reference algorithm
+
+Workload (config.workload): BASELINE.json configs[1], scripts/bump_on_tail.jl at 1e8 particles per GPU:
+L = 2 pi / 0.3, n_h = 16 periodic splines of degree 3 (order 4), dt = 0.1, chi = 1, self-consistent Strang
+(legacy integrate_vp!, src/vlasov_poisson.jl:94-115).  A "step" is one Strang step of every particle.
+N > 1 (torchrun, one rank per GPU) is BASELINE configs[4]: the same physics with 1e8 particles per GPU
+(weak scaling), particle slabs per rank and one all-reduce of the 16+2 coefficient vector per step.
+
+Timed region: ONE call of the whole-step stepper for K steps (K+1 streaming passes: the half-drift
+staggering costs one extra pass per call), CUDA events on the launching stream, barrier + synchronize on
+both sides, max over ranks.  Inputs (2.4 GB/GPU) are far larger than L2, so no flush is needed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+KAPPA, NH, ORDER, DT, CHI = 0.3, 16, 4, 0.1, 1.0
+L = 2 * np.pi / KAPPA
+BYTES_PER_STEP = 40  # read x,v,w + write x,v (fp64 SoA), SURVEY 8d / BASELINE.md section 3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=float, default=1e8, help="particles per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-sample", type=float, default=1e7, help="particles of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="vp", choices=["vp", "lb", "clb"])
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, c in zip(names, r[5:9]) if c.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_rate(nsample, nsteps, threads):
+    """particle-steps/s of the oracle port (faithful restatement of the reference loops) on the host cores."""
+    from oracle import oracle as orc
+    orc.set_threads(threads)
+    x, v, w = orc.sample_bump_on_tail(int(nsample), kappa=KAPPA)
+    xs = orc.XSpace(0.0, L, ORDER, NH)
+    t0 = time.perf_counter()
+    xs.strang_selfconsistent(x, v, w, DT, nsteps, chi=CHI, diag=False)
+    dt = time.perf_counter() - t0
+    orc.set_threads(1)
+    return nsample * nsteps / dt, dt
+
+
+def run_reference(args):
+    """CPU arm: the reference is pure Julia and cannot run here (no Julia toolchain), so this
+    times the oracle port of its algorithm with all host threads on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    cores = orc.max_threads()
+    nsample = int(args.cpu_sample)
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_rate(nsample // 4, 1, cores)
+    rate, dt = cpu_port_rate(nsample, args.steps if args.steps <= 20 else 20, cores)
+    ksteps = args.steps if args.steps <= 20 else 20
+    line = {
+        "impl": "reference", "metric": "particle-steps/sec", "value": rate, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": ksteps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / ksteps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "vp_bump_on_tail_strang_selfconsistent", "particles_per_step": nsample, "n_basis": NH,
+                   "order": ORDER, "dt": DT, "note": "bounded sample of the 1e8-particle workload; throughput per particle-step"},
+        "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{nsample} particles x {ksteps} Strang steps, OpenMP {cores} threads, oracle C port (reference is Julia: not runnable here)"},
+        "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import vpm_b200 as vpm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libvpm_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # a dedicated non-default stream shared by torch (events) and the library (kernels): the legacy default
+    # stream has handle 0, which the C ABI reads as "create a private stream"
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx = vpm.Context(local, stream.cuda_stream)
+    vpm.set_default_context(ctx)
+    if world > 1:
+        obj = [vpm.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        ctx.comm_init(world, rank, obj[0])
+
+    n = int(args.particles)
+    ntotal = n * world
+    lib = vpm._cabi.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == "vp":
+        d = vpm.ParticleDistribution(1, 1, n, ctx)
+        vpm.initialize_(d, vpm.BumpOnTail(kappa=KAPPA), offset=rank * n, ntotal=ntotal)
+        pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), ORDER, NH), ctx)
+
+        def run_steps(k):
+            vpm.check(lib.vpm_vp_strang_steps_async(pot._h, d._h, DT, CHI, int(k), 0, 0))
+        kind_pass, bytes_unit, wl = 0, BYTES_PER_STEP, "vp_bump_on_tail_strang_selfconsistent"
+        passes_per_call = lambda k: k + 1
+    else:
+        cons = args.workload == "clb"
+        d = vpm.ParticleDistribution(1, 1, n, ctx)
+        vpm.initialize_(d, vpm.DoubleMaxwellian((-10.0, 10.0), 2.0), offset=rank * n, ntotal=ntotal)
+        sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet", ctx)
+
+        def run_steps(k):
+            vpm.check(lib.vpm_lb_rk438_steps_async(sd._h, d._h, 1.0, 1e-2, int(k), int(cons)))
+        # RK438 particle-step: stage passes 32+56+56+40 B (+ 4 x 8 B moment passes for CLB), DESIGN.md
+        kind_pass, bytes_unit, wl = 2, (184 + (32 if cons else 0)), ("clb" if cons else "lb") + "_rk438_double_maxwellian"
+        passes_per_call = lambda k: 4 * k * (2 if cons else 1) + 1
+
+    # ---- warm-up, then the timed region ----
+    run_steps(max(args.warmup, 3))
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    run_steps(args.steps)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = ntotal * args.steps / (ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream ----
+    vpm.check(lib.vpm_profile(ctx._h, 1))
+    ksteps = min(args.steps, 20)
+    run_steps(ksteps)
+    msk = (np.zeros(8), np.zeros(8, dtype=np.int64))
+    vpm.check(lib.vpm_profile_get(ctx._h, msk[0].ctypes.data, msk[1].ctypes.data))
+    vpm.check(lib.vpm_profile(ctx._h, 0))
+    pass_ms, pass_cnt = float(msk[0][kind_pass]), int(msk[1][kind_pass])
+    field_ms = float(msk[0][kind_pass + 1])
+    if args.workload == "vp":
+        bytes_per_launch = BYTES_PER_STEP * n           # one fused pass = one particle-step of every particle
+    else:
+        bytes_per_launch = bytes_unit * n * ksteps / max(pass_cnt, 1)   # mean over the stage / moment passes
+    achieved = bytes_per_launch / (pass_ms / max(pass_cnt, 1) * 1e-3) / 1e9
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload)
+
+    # ---- e2e: the host-array drop-in step (z = 2 x N host matrix in, out), PCIe copies inside the timing ----
+    e2e = None
+    if args.workload == "vp" and not args.no_e2e:
+        import ctypes as C
+        zin, zout = C.c_void_p(), C.c_void_p()
+        vpm.check(lib.vpm_host_alloc(16 * n, C.byref(zin)))
+        vpm.check(lib.vpm_host_alloc(16 * n, C.byref(zout)))
+        vpm.check(lib.vpm_particles_download_aos(d._h, zin, 2))
+        vpm.check(lib.vpm_vp_strang_step_host(pot._h, d._h, zin, zout, DT, CHI, 0))  # warm-up (allocates staging)
+        barrier()
+        t0 = time.perf_counter()
+        cur, nxt = zin, zout
+        for _ in range(args.e2e_steps):
+            vpm.check(lib.vpm_vp_strang_step_host(pot._h, d._h, cur, nxt, DT, CHI, 0))
+            cur, nxt = nxt, cur
+        barrier()
+        t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e = {"value": ntotal * args.e2e_steps / float(t_e2e.item()), "unit": "particle-steps/s",
+               "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n, "steps": args.e2e_steps,
+               "api": "vpm_vp_strang_step_host (pinned 2 x N integrator state in/out per step; weights resident)"}
+        lib.vpm_host_free(zin)
+        lib.vpm_host_free(zout)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu and args.workload == "vp":
+        from oracle import oracle as orc
+        cores = orc.max_threads()
+        r1, _ = cpu_port_rate(int(args.cpu_sample) // 4, 2, 1)
+        rall, _ = cpu_port_rate(int(args.cpu_sample), 10, cores)
+        cpu = {"value": rall, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+               "sample": f"{int(args.cpu_sample)} particles x 10 Strang steps on {cores} OpenMP threads; "
+                         f"1 thread ({int(args.cpu_sample) // 4} x 2): {r1:.3e}/s; C port of the reference algorithm (Julia not runnable here)",
+               "single_thread_value": r1}
+
+    if rank == 0:
+        line = {
+            "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl, "particles_per_gpu": n, "n_basis": NH if args.workload == "vp" else 41,
+                       "order": ORDER, "dt": DT if args.workload == "vp" else 1e-2,
+                       "l2": "inputs (24 B x particles per GPU) larger than L2, no flush needed",
+                       "parallelism": f"particle slabs x{world}, coefficient all-reduce per field update" if world > 1 else "single GPU",
+                       "passes_in_timed_region": passes_per_call(args.steps)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "vp_pass_kernel" if args.workload == "vp" else "lb_pass_kernel",
+                         "bytes_per_launch": bytes_per_launch, "avg_launch_ms": pass_ms / max(pass_cnt, 1),
+                         "launches_timed": pass_cnt, "field_kernel_share": field_ms / max(pass_ms + field_ms, 1e-30),
+                         "frac_of_8TBs_nominal": achieved / 8000.0},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        ctx.comm_destroy()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

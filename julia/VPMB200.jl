@@ -1,0 +1,221 @@
+# VPMB200.jl — Julia host shim over libvpm_b200.so (include/vpm_b200.h).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia toolchain (SURVEY F3).  The same C ABI
+# is exercised end to end from Python (vlasovparticlemethods.jl_b200/api.py); this file is the binding a
+# VlasovMethods.jl maintainer would add.  It defines device-backed subtypes of the package's own abstract
+# types and adds methods to the package's generic functions, so scripts/*.jl change only in their
+# constructor lines (see INTEGRATION.md).
+module VPMB200
+
+using VlasovMethods
+import VlasovMethods: projection!, projection, run!, initialize!, DistributionFunction,
+                      SplittingMethod, GeometricIntegrator, VlasovPoisson,
+                      LenardBernstein, ConservativeLenardBernstein, BumpOnTail, DoubleMaxwellian
+
+const libvpm = get(ENV, "LIBVPM_B200", "libvpm_b200.so")
+
+struct VPMError <: Exception
+    code::Cint
+    msg::String
+end
+
+@inline function check(rc::Cint)
+    rc == 0 && return nothing
+    throw(VPMError(rc, unsafe_string(ccall((:vpm_last_error, libvpm), Cstring, ()))))
+end
+
+# ---------------------------------------------------------------------------------- context
+mutable struct Context
+    h::Ptr{Cvoid}
+    function Context(device::Integer = 0; stream::Ptr{Cvoid} = C_NULL)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:vpm_ctx_create, libvpm), Cint, (Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), device, stream, r))
+        finalizer(c -> ccall((:vpm_ctx_destroy, libvpm), Cint, (Ptr{Cvoid},), c.h), new(r[]))
+    end
+end
+const DEFAULT = Ref{Union{Nothing,Context}}(nothing)
+context() = something(DEFAULT[], (DEFAULT[] = Context(0)))
+
+# ---------------------------------------------------------------------------------- distributions
+# replaces ParticleDistribution (src/distributions/particle_distribution.jl:2-20): SoA on the device
+mutable struct DeviceParticleDistribution <: DistributionFunction{1,1}
+    h::Ptr{Cvoid}
+    n::Int
+    ctx::Context
+    function DeviceParticleDistribution(npart::Integer; ctx = context())
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:vpm_particles_create, libvpm), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), ctx.h, npart, r))
+        finalizer(p -> ccall((:vpm_particles_destroy, libvpm), Cint, (Ptr{Cvoid},), p.h), new(r[], npart, ctx))
+    end
+end
+Base.size(d::DeviceParticleDistribution) = (d.n,)
+Base.length(d::DeviceParticleDistribution) = d.n
+
+# host <-> device with the reference's own (x;v;w) x N matrix (ld = 3) or the integrator state z (ld = 2)
+function upload!(d::DeviceParticleDistribution, z::Matrix{Float64})
+    check(ccall((:vpm_particles_upload_aos, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), d.h, z, size(z, 1)))
+    d
+end
+function download!(z::Matrix{Float64}, d::DeviceParticleDistribution)
+    check(ccall((:vpm_particles_download_aos, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), d.h, z, size(z, 1)))
+    z
+end
+DeviceParticleDistribution(dist::VlasovMethods.ParticleDistribution; kw...) =
+    upload!(DeviceParticleDistribution(length(dist.particles); kw...), Matrix(dist.particles.list))
+
+# replaces SplineDistribution (src/distributions/spline_distribution.jl:23-36)
+mutable struct DeviceSplineDistribution <: DistributionFunction{1,1}
+    h::Ptr{Cvoid}
+    n::Int
+    ctx::Context
+    function DeviceSplineDistribution(nknots::Integer, order::Integer, domain::Tuple, bc::Symbol = :Dirichlet; ctx = context())
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:vpm_vspace_create, libvpm), Cint, (Ptr{Cvoid}, Float64, Float64, Cint, Cint, Cint, Ref{Ptr{Cvoid}}),
+                    ctx.h, domain[1], domain[2], nknots, order, bc == :Dirichlet, r))
+        n = ccall((:vpm_vspace_size, libvpm), Cint, (Ptr{Cvoid},), r[])
+        finalizer(s -> ccall((:vpm_vspace_destroy, libvpm), Cint, (Ptr{Cvoid},), s.h), new(r[], n, ctx))
+    end
+end
+Base.size(s::DeviceSplineDistribution) = (s.n,)
+function coefficients(s::DeviceSplineDistribution)
+    c = Vector{Float64}(undef, s.n)
+    check(ccall((:vpm_vspace_get, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), s.h, C_NULL, c))
+    c
+end
+
+# replaces Potential(PeriodicBasisBSplineKit(domain, order, n)) (scripts/vlasov_poisson.jl:21)
+mutable struct DevicePotential
+    h::Ptr{Cvoid}
+    n::Int
+    ctx::Context
+    function DevicePotential(domain::Tuple, order::Integer, n::Integer; ctx = context())
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:vpm_xspace_create, libvpm), Cint, (Ptr{Cvoid}, Float64, Float64, Cint, Cint, Ref{Ptr{Cvoid}}),
+                    ctx.h, domain[1], domain[2], order, n, r))
+        finalizer(p -> ccall((:vpm_xspace_destroy, libvpm), Cint, (Ptr{Cvoid},), p.h), new(r[], n, ctx))
+    end
+end
+function Base.getproperty(p::DevicePotential, s::Symbol)
+    if s === :rhs || s === :coefficients
+        out = Vector{Float64}(undef, getfield(p, :n))
+        a, b = s === :rhs ? (out, C_NULL) : (C_NULL, out)
+        check(ccall((:vpm_xspace_get, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), getfield(p, :h), a, b))
+        return out
+    end
+    getfield(p, s)
+end
+
+# ---------------------------------------------------------------------------------- seam functions
+function ptrs(d::DeviceParticleDistribution)
+    x = Ref{Ptr{Float64}}(); v = Ref{Ptr{Float64}}(); w = Ref{Ptr{Float64}}()
+    check(ccall((:vpm_particles_ptrs, libvpm), Cint, (Ptr{Cvoid}, Ref{Ptr{Float64}}, Ref{Ptr{Float64}}, Ref{Ptr{Float64}}), d.h, x, v, w))
+    x[], v[], w[]
+end
+
+# projection!(potential, distribution): src/projections/potential.jl:2-22
+function projection!(potential::DevicePotential, distribution::DeviceParticleDistribution)
+    x, _, w = ptrs(distribution)
+    check(ccall((:vpm_deposit_x, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
+                potential.h, x, w, distribution.n, C_NULL))
+    potential
+end
+
+# PoissonSolvers.update!(potential): call site src/models/vlasov_poisson.jl:14
+update!(potential::DevicePotential) =
+    (check(ccall((:vpm_poisson_solve, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), potential.h, C_NULL, C_NULL)); potential)
+
+# update_potential!(model): src/models/vlasov_poisson.jl:12-15
+VlasovMethods.update_potential!(model::VlasovPoisson{1,1,DeviceParticleDistribution,DevicePotential}) =
+    check(ccall((:vpm_update_potential, libvpm), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+                model.potential.h, model.distribution.h, C_NULL, C_NULL))
+
+# projection(velocities, dist, final_dist): src/projections/distribution.jl:35-55 (velocities on the host)
+function projection(velocities::AbstractVector{Float64}, dist::DeviceParticleDistribution, final_dist::DeviceSplineDistribution)
+    ctx = dist.ctx
+    dv = Ref{Ptr{Float64}}()
+    check(ccall((:vpm_dev_alloc, libvpm), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Float64}}), ctx.h, length(velocities), dv))
+    try
+        check(ccall((:vpm_memcpy_h2d, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), ctx.h, dv[], velocities, length(velocities)))
+        _, _, w = ptrs(dist)
+        check(ccall((:vpm_project_v, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
+                    final_dist.h, dv[], w, dist.n, C_NULL))
+    finally
+        ccall((:vpm_dev_free, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx.h, dv[])
+    end
+    final_dist
+end
+
+# LB_rhs! / CLB_rhs!: src/models/lenard_bernstein.jl:20-30, lenard_bernstein_conservative.jl:24-36
+function lb_rhs!(v̇::Vector{Float64}, v::Vector{Float64}, params, conservative::Bool)
+    dist, sdist, ctx = params.idist, params.model.ent.dist, params.idist.ctx
+    n = length(v)
+    dv = Ref{Ptr{Float64}}(); dout = Ref{Ptr{Float64}}()
+    check(ccall((:vpm_dev_alloc, libvpm), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Float64}}), ctx.h, n, dv))
+    check(ccall((:vpm_dev_alloc, libvpm), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Float64}}), ctx.h, n, dout))
+    try
+        check(ccall((:vpm_memcpy_h2d, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), ctx.h, dv[], v, n))
+        _, _, w = ptrs(dist)
+        check(ccall((:vpm_lb_rhs, libvpm), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Float64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    sdist.h, dv[], w, n, params.ν, conservative, dout[], C_NULL, C_NULL))
+        check(ccall((:vpm_memcpy_d2h, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), ctx.h, v̇, dout[], n))
+    finally
+        ccall((:vpm_dev_free, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx.h, dv[])
+        ccall((:vpm_dev_free, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx.h, dout[])
+    end
+    v̇
+end
+
+# ---------------------------------------------------------------------------------- whole-run drivers
+# SplittingMethod(model, tspan, tstep) + run!: src/models/vlasov_poisson.jl:73-89, src/methods/splitting.jl:23-52
+struct DeviceSplittingMethod{MT}
+    model::MT
+    tspan::Tuple{Float64,Float64}
+    tstep::Float64
+    field::Symbol          # :frozen == as shipped (SURVEY F4), :selfconsistent == legacy integrate_vp!
+    χ::Float64
+end
+SplittingMethod(model::VlasovPoisson{1,1,DeviceParticleDistribution,DevicePotential}, tspan::Tuple, tstep::Real;
+                field::Symbol = :frozen, χ::Real = 1.0) = DeviceSplittingMethod(model, Float64.(tspan), Float64(tstep), field, Float64(χ))
+
+function run!(m::DeviceSplittingMethod; diag_mode::Integer = 1)
+    nt = round(Int, (m.tspan[2] - m.tspan[1]) / m.tstep)
+    diag = zeros(3, nt + 1)          # rows W, K, M (src/vlasov_poisson.jl:58-67)
+    check(ccall((:vpm_vp_strang_steps, libvpm), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, Cint, Cint, Cint, Ptr{Float64}),
+                m.model.potential.h, m.model.distribution.h, m.tstep, m.χ, nt, m.field === :frozen ? 1 : 0, diag_mode, diag))
+    m.model.distribution, diag
+end
+
+# GeometricIntegrator(model, tspan, tstep) + run! with RK438: src/models/lenard_bernstein.jl:68-84,
+# lenard_bernstein_conservative.jl:88-104, src/methods/geometric_integrator.jl:12-44
+struct DeviceRK438{MT}
+    model::MT
+    tspan::Tuple{Float64,Float64}
+    tstep::Float64
+end
+GeometricIntegrator(model::Union{LenardBernstein{1,1,DeviceParticleDistribution},ConservativeLenardBernstein{1,1,DeviceParticleDistribution}},
+                    tspan::Tuple, tstep::Real) = DeviceRK438(model, Float64.(tspan), Float64(tstep))
+
+function run!(m::DeviceRK438)
+    nt = round(Int, (m.tspan[2] - m.tspan[1]) / m.tstep)
+    diag = zeros(2, nt + 1)          # rows Σv, Σv² (scripts/lenard_bernstein_conservative.jl:49-50)
+    check(ccall((:vpm_lb_rk438_steps, libvpm), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, Cint, Cint, Ptr{Float64}),
+                m.model.ent.dist.h, m.model.dist.h, m.model.ν, m.tstep, nt, m.model isa ConservativeLenardBernstein, diag))
+    m.model.dist, diag
+end
+
+# ---------------------------------------------------------------------------------- initial conditions
+# initialize!(dist, BumpOnTail()): src/examples/bumpontail.jl:43-75 (device-side, counter-based)
+function initialize!(d::DeviceParticleDistribution, p::BumpOnTail; seed::UInt64 = 0x000000005EED0001, offset::Integer = 0, ntotal::Integer = d.n)
+    check(ccall((:vpm_sample_bump_on_tail, libvpm), Cint, (Ptr{Cvoid}, Int64, Int64, UInt64, Float64, Float64, Float64, Float64, Float64),
+                d.h, offset, ntotal, seed, p.ε, p.κ, p.α, p.σ, p.v₀))
+    d
+end
+function initialize!(d::DeviceParticleDistribution, p::DoubleMaxwellian; seed::UInt64 = 0x000000005EED0001, offset::Integer = 0, ntotal::Integer = d.n)
+    check(ccall((:vpm_sample_maxwellian, libvpm), Cint, (Ptr{Cvoid}, Int64, Int64, UInt64, Float64, Float64, Float64, Cint, Float64),
+                d.h, offset, ntotal, seed, p.domain[1], p.domain[2], p.shift, 1, 1.0))
+    d
+end
+
+end # module

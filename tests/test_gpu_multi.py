@@ -1,0 +1,84 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): particle slabs on 2 ranks with the NCCL all-reduce
+of the coefficient vector inside the library must reproduce the single-GPU run to summation order."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nper, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import vpm_b200 as vpm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(rank)
+    ctx = vpm.Context(rank)
+    obj = [vpm.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    ctx.comm_init(world, rank, obj[0])
+    L = 2 * np.pi / 0.3
+    # Vlasov-Poisson, self-consistent, exact diagnostics
+    d = vpm.ParticleDistribution(1, 1, nper, ctx)
+    vpm.initialize_(d, vpm.BumpOnTail(), offset=rank * nper, ntotal=world * nper)
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), 4, 16), ctx)
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 0.5), 0.1, field="selfconsistent")
+    vpm.run_(m, diag_mode=2)
+    x, v, _ = d.get()
+    # conservative Lenard-Bernstein RK438
+    d2 = vpm.ParticleDistribution(1, 1, nper, ctx)
+    vpm.initialize_(d2, vpm.DoubleMaxwellian((-10.0, 10.0), 2.0), offset=rank * nper, ntotal=world * nper)
+    sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet", ctx)
+    gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d2, vpm.CollisionEntropy(sd)), (0.0, 0.03), 0.01)
+    vpm.run_(gi)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), x=x, v=v, diag=m.diagnostics, phi=pot.coefficients,
+             vlb=d2.get("v"), dlb=gi.diagnostics, coef=sd.coefficients)
+    ctx.comm_destroy()
+    dist.destroy_process_group()
+
+
+def test_two_rank_slabs_match_single_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    import vpm_b200 as vpm
+    world, nper = 2, 150001
+    mp.spawn(_worker, args=(world, _free_port(), nper, str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
+    np.testing.assert_array_equal(r[0]["phi"], r[1]["phi"])      # replicated solve on identical input
+    np.testing.assert_array_equal(r[0]["diag"], r[1]["diag"])
+    nrm = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    L = 2 * np.pi / 0.3
+    d = vpm.ParticleDistribution(1, 1, world * nper)
+    vpm.initialize_(d, vpm.BumpOnTail())
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), 4, 16))
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 0.5), 0.1, field="selfconsistent")
+    vpm.run_(m, diag_mode=2)
+    x, v, _ = d.get()
+    assert nrm(np.concatenate([r[0]["x"], r[1]["x"]]), x) < 1e-12
+    assert nrm(np.concatenate([r[0]["v"], r[1]["v"]]), v) < 1e-12
+    np.testing.assert_allclose(r[0]["diag"], m.diagnostics, rtol=1e-11)
+    d2 = vpm.ParticleDistribution(1, 1, world * nper)
+    vpm.initialize_(d2, vpm.DoubleMaxwellian((-10.0, 10.0), 2.0))
+    sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
+    gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d2, vpm.CollisionEntropy(sd)), (0.0, 0.03), 0.01)
+    vpm.run_(gi)
+    assert nrm(np.concatenate([r[0]["vlb"], r[1]["vlb"]]), d2.get("v")) < 1e-11
+    np.testing.assert_allclose(r[0]["dlb"], gi.diagnostics, rtol=1e-11)
+    assert nrm(r[0]["coef"], sd.coefficients) < 1e-10
