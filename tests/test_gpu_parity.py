@@ -290,3 +290,55 @@ def test_errors_are_reported(vpm):
         vpm.SplineDistribution(1, 1, 1, 4, (-1.0, 1.0))
     with pytest.raises(ValueError):
         vpm.ParticleDistribution(2, 2, 10)
+
+
+# ------------------------------------------------------------------------------------- large grids
+@pytest.mark.parametrize("hm", ["1", "2"])
+def test_histogram_fallback_modes(vpm, oracle, hm, monkeypatch):
+    """Grids too large for per-thread histogram copies fall back to per-warp / per-CTA copies with
+    shared-memory atomics; VPM_TUNE_HM forces those code paths on a small grid."""
+    monkeypatch.setenv("VPM_TUNE_HM", hm)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "vp_k4_n16.npz"))
+    K, nh, L, dt, ns = int(g["K"]), int(g["nh"]), float(g["L"]), float(g["dt"]), int(g["nsteps"])
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), K, nh))
+    d = make_particles(vpm, g["x"], g["v"], g["w"])
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, dt * ns), dt, field="selfconsistent")
+    vpm.run_(m, diag_mode=2)
+    x1, v1, _ = d.get()
+    assert nrm(x1, g["x1"]) < TOL and nrm(v1, g["v1"]) < TOL
+    assert np.abs(m.diagnostics - g["diag"]).max() < 1e-11 * np.abs(g["diag"]).max()
+    gl = np.load(os.path.join(ROOT, "tests", "golden", "lb_k4_n41.npz"))
+    sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
+    d2 = make_particles(vpm, np.zeros(gl["v"].size), gl["v"], gl["w"])
+    gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d2, vpm.CollisionEntropy(sd), nu=float(gl["nu"])),
+                                 (0.0, float(gl["dt"]) * int(gl["nsteps"])), float(gl["dt"]))
+    vpm.run_(gi)
+    assert nrm(d2.get("v"), gl["v_clb"]) < 1e-11
+
+
+def test_large_grids_natural(vpm, oracle):
+    rng = np.random.default_rng(3)
+    n, K, nh, lo, hi = 60000, 4, 400, 0.0, 50.0       # 403 bins: per-warp copies
+    x, v, w = rng.uniform(lo - 100, hi + 100, n), rng.standard_normal(n), rng.uniform(0.5, 1.5, n) / n
+    d = make_particles(vpm, x, v, w)
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((lo, hi), K, nh))
+    xs = oracle.XSpace(lo, hi, K, nh)
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 0.2), 0.1, field="selfconsistent")
+    vpm.run_(m, diag_mode=0)
+    xo, vo, _, _ = xs.strang_selfconsistent(x, v, w, 0.1, 2, diag=False)
+    xg, vg, _ = d.get()
+    assert nrm(xg, xo) < TOL and nrm(vg, vo) < TOL
+    # v-space with 300 breakpoints
+    vs = oracle.VSpace(-10.0, 10.0, 300, 4)
+    sd = vpm.SplineDistribution(1, 1, 300, 4, (-10.0, 10.0), "Dirichlet")
+    vv = rng.standard_normal(n) * 1.5
+    d2 = make_particles(vpm, np.zeros(n), vv, w)
+    vdot = np.zeros(n)
+    model = vpm.ConservativeLenardBernstein(d2, vpm.CollisionEntropy(sd), nu=1.0)
+    vpm.CLB_rhs_(vdot, vv, {"nu": 1.0, "idist": d2, "fdist": sd, "model": model}, 0.0)
+    ref, _, _ = vs.lb_rhs(vv, w, 1.0, True)
+    assert nrm(vdot, ref) < 1e-9
+    # beyond the shared-memory capacity the library refuses instead of falling back
+    with pytest.raises(vpm.VpmError):
+        big = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, 1.0), 4, 20000))
+        vpm.projection_(big, d)

@@ -68,16 +68,18 @@ void circulant_pinv(const std::vector<double>& row, bool singular, std::vector<d
 {
     const int n = (int)row.size();
     const long double two_pi = 6.283185307179586476925286766559005768L;
-    std::vector<long double> lam(n);
+    std::vector<long double> lam(n), ctab(n);
+    for (int r = 0; r < n; r++) ctab[r] = cosl(two_pi * (long double)r / n);
     for (int m = 0; m < n; m++) {
         long double s = 0;
-        for (int j = 0; j < n; j++) s += (long double)row[j] * cosl(two_pi * (long double)((int64_t)m * j % n) / n);
+        for (int j = 0; j < n; j++)
+            if (row[j] != 0.0) s += (long double)row[j] * ctab[(int64_t)m * j % n];
         lam[m] = s;
     }
     out.assign(n, 0.0);
     for (int j = 0; j < n; j++) {
         long double s = 0;
-        for (int m = singular ? 1 : 0; m < n; m++) s += cosl(two_pi * (long double)((int64_t)m * j % n) / n) / lam[m];
+        for (int m = singular ? 1 : 0; m < n; m++) s += ctab[(int64_t)m * j % n] / lam[m];
         out[j] = (double)(s / n);
     }
 }

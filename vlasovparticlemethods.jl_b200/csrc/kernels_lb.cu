@@ -10,6 +10,8 @@
 // One streaming pass per Runge-Kutta stage: evaluate f_s, f_s' at the stage input from the per-cell
 // polynomial table, form the stage derivative, do the stage algebra in registers, write the next
 // stage input and deposit it for the next projection (private shared-memory histograms, no atomics).
+#include <cstdlib>
+
 #include "splines.cuh"
 #include "vpm_internal.h"
 
@@ -52,7 +54,12 @@ __device__ __forceinline__ bool v_locate(const LbDev& P, double q, int& ci, doub
     return inside;
 }
 
-template <int K>
+template <int HM>
+struct HistCfg {
+    static constexpr int copies = HM == 0 ? kBlock : (HM == 1 ? kBlock / 32 : 1);
+};
+
+template <int K, int HM>
 __device__ __forceinline__ void v_deposit(const LbDev& P, double* __restrict__ s_hist, double q, double w)
 {
     int ci;
@@ -70,9 +77,13 @@ __device__ __forceinline__ void v_deposit(const LbDev& P, double* __restrict__ s
             b[j] = r;
         }
     }
-    double* hcell = s_hist + ci * kBlock;
+    constexpr int HS = HistCfg<HM>::copies;
+    double* hcell = s_hist + ci * HS;
 #pragma unroll
-    for (int j = 0; j < K; j++) hcell[j * kBlock] = fma(b[j], w, hcell[j * kBlock]);
+    for (int j = 0; j < K; j++) {
+        if (HM == 0) hcell[j * HS] = fma(b[j], w, hcell[j * HS]);
+        else atomicAdd(hcell + j * HS, b[j] * w);
+    }
 }
 
 template <int K>
@@ -97,14 +108,14 @@ struct LbItem {
     double q, w, v0, acc, d;
 };
 
-template <int K, int MODE>
+template <int K, int MODE, int HM>
 __device__ __forceinline__ void lb_particle(const LbDev& P, const int mode_rt, const double* __restrict__ s_tab,
                                             double* __restrict__ s_hist, LbItem& it, double& o1, double& o2,
                                             double (&sums)[5], const double A1, const double A2)
 {
     const int mode = MODE >= 0 ? MODE : mode_rt;
     if (mode == LB_DEPOSIT_ONLY) {
-        v_deposit<K>(P, s_hist, it.q, it.w);
+        v_deposit<K, HM>(P, s_hist, it.q, it.w);
         if (P.diag) {
             sums[0] += it.q;
             sums[1] = fma(it.q, it.q, sums[1]);
@@ -153,7 +164,7 @@ __device__ __forceinline__ void lb_particle(const LbDev& P, const int mode_rt, c
         }
     }
     it.q = qn;
-    v_deposit<K>(P, s_hist, qn, it.w);
+    v_deposit<K, HM>(P, s_hist, qn, it.w);
 }
 
 template <int MODE>
@@ -171,7 +182,7 @@ struct LbIo {
     static constexpr bool wr_o2 = rt || MODE == LB_EVAL;
 };
 
-template <int K, int MODE, int VEC>
+template <int K, int MODE, int VEC, int HM>
 __global__ void __launch_bounds__(kBlock) lb_pass_kernel(const LbDev P)
 {
     extern __shared__ double smem[];
@@ -184,12 +195,14 @@ __global__ void __launch_bounds__(kBlock) lb_pass_kernel(const LbDev P)
     const bool ev = mode != LB_DEPOSIT_ONLY;
     double* s_red = smem;                        // 5 * warps
     double* s_tab = smem + 5 * (kBlock / 32);    // ncell * TS
-    double* s_hist = s_tab + ((P.ncell * TS + 1) & ~1) + tid;
+    constexpr int HS = HistCfg<HM>::copies;
+    double* s_hbase = s_tab + ((P.ncell * TS + 1) & ~1);
+    double* s_hist = s_hbase + (HM == 0 ? tid : (HM == 1 ? (tid >> 5) : 0));
 
     if (ev)
         for (int i = tid; i < P.ncell * TS; i += kBlock) s_tab[i] = P.ftab[i];
     if (dep)
-        for (int b = 0; b < P.nbfull; b++) s_hist[b * kBlock] = 0.0;
+        for (int i = tid; i < P.nbfull * HS; i += kBlock) s_hbase[i] = 0.0;
     __syncthreads();
     const double A1 = P.conservative && ev ? P.scal[0] : 0.0, A2 = P.conservative && ev ? P.scal[1] : 1.0;
 
@@ -234,8 +247,8 @@ __global__ void __launch_bounds__(kBlock) lb_pass_kernel(const LbDev P)
             }
             LbItem i0{qa.x, wa.x, va.x, aa.x, da.x}, i1{qa.y, wa.y, va.y, aa.y, da.y};
             double2 o1 = z2, o2 = z2;
-            lb_particle<K, MODE>(P, mode, s_tab, s_hist, i0, o1.x, o2.x, sums, A1, A2);
-            lb_particle<K, MODE>(P, mode, s_tab, s_hist, i1, o1.y, o2.y, sums, A1, A2);
+            lb_particle<K, MODE, HM>(P, mode, s_tab, s_hist, i0, o1.x, o2.x, sums, A1, A2);
+            lb_particle<K, MODE, HM>(P, mode, s_tab, s_hist, i1, o1.y, o2.y, sums, A1, A2);
             if (wr_q) st_stream2(P.qout + 2 * i, make_double2(i0.q, i1.q));
             if (wr_acc) st_stream2(P.acc + 2 * i, make_double2(i0.acc, i1.acc));
             if (wr_d) st_stream2(P.d + 2 * i, make_double2(i0.d, i1.d));
@@ -252,7 +265,7 @@ __global__ void __launch_bounds__(kBlock) lb_pass_kernel(const LbDev P)
         for (long long i = i0; i < P.n; i += stride) {
             LbItem it{P.q[i], rd_w ? P.w[i] : 0.0, rd_v0 ? P.v0[i] : 0.0, rd_acc ? P.acc[i] : 0.0, rd_d ? P.d[i] : 0.0};
             double o1 = 0.0, o2 = 0.0;
-            lb_particle<K, MODE>(P, mode, s_tab, s_hist, it, o1, o2, sums, A1, A2);
+            lb_particle<K, MODE, HM>(P, mode, s_tab, s_hist, it, o1, o2, sums, A1, A2);
             if (wr_q) P.qout[i] = it.q;
             if (wr_acc) P.acc[i] = it.acc;
             if (wr_d) P.d[i] = it.d;
@@ -263,11 +276,10 @@ __global__ void __launch_bounds__(kBlock) lb_pass_kernel(const LbDev P)
 
     if (dep) {
         __syncthreads();
-        const double* hist = s_hist - tid;
         for (int b = warp; b < P.nbfull; b += kBlock / 32) {
             double s = 0.0;
 #pragma unroll
-            for (int t = 0; t < kBlock / 32; t++) s += hist[b * kBlock + t * 32 + lane];
+            for (int t = lane; t < HS; t += 32) s += s_hbase[b * HS + t];
             s = warp_sum(s);
             if (lane == 0) P.partials[(size_t)blockIdx.x * P.nbfull + b] = s;
         }
@@ -399,25 +411,38 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
 
     const bool stage = p.mode >= LB_STAGE1 && p.mode <= LB_STAGE4;
     const bool dep = p.mode == LB_DEPOSIT_ONLY || stage;
-    const size_t smem = sizeof(double) * (5 * (kBlock / 32) + ((vs->ncell * TS + 1) & ~1) + (dep ? (size_t)vs->nbfull * kBlock : 0));
+    const size_t base = sizeof(double) * (5 * (kBlock / 32) + ((vs->ncell * TS + 1) & ~1));
+    int hm = 0;
+    if (dep) {
+        if (base + sizeof(double) * (size_t)vs->nbfull * kBlock > ctx->smem_optin / 2) hm = 1;
+        if (hm == 1 && base + sizeof(double) * (size_t)vs->nbfull * (kBlock / 32) > ctx->smem_optin / 2) hm = 2;
+    }
+    if (const char* e = getenv("VPM_TUNE_HM")) {  // test hook: force a privatisation level
+        const int f = atoi(e);
+        if (f > hm && f <= 2 && dep) hm = f;
+    }
+    const size_t copies = hm == 0 ? kBlock : (hm == 1 ? kBlock / 32 : 1);
+    const size_t smem = base + (dep ? sizeof(double) * (size_t)vs->nbfull * copies : 0);
     if (smem > ctx->smem_optin)
-        return fail(VPM_ERR_UNSUPPORTED, "v-space too large for the shared-memory privatised deposit");
+        return fail(VPM_ERR_UNSUPPORTED, "v-space too large: the f/f' table and one histogram copy must fit in shared memory");
 
     auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const bool vec = al(p.q) && al(p.w) && al(p.v0) && al(p.acc) && al(p.d) && al(p.qout) && al(p.out) && al(p.out2);
 
     void (*kern)(const LbDev) = nullptr;
-    if (!vec) kern = lb_pass_kernel<K, -1, 1>;
+    if (p.mode < LB_DEPOSIT_ONLY || p.mode > LB_EVAL) return fail(VPM_ERR_INVALID, "bad LB pass mode");
+    if (hm == 1) kern = vec ? lb_pass_kernel<K, -1, 2, 1> : lb_pass_kernel<K, -1, 1, 1>;
+    else if (hm == 2) kern = vec ? lb_pass_kernel<K, -1, 2, 2> : lb_pass_kernel<K, -1, 1, 2>;
+    else if (!vec) kern = lb_pass_kernel<K, -1, 1, 0>;
     else switch (p.mode) {
-        case LB_DEPOSIT_ONLY: kern = lb_pass_kernel<K, LB_DEPOSIT_ONLY, 2>; break;
-        case LB_STAGE1: kern = lb_pass_kernel<K, LB_STAGE1, 2>; break;
-        case LB_STAGE2: kern = lb_pass_kernel<K, LB_STAGE2, 2>; break;
-        case LB_STAGE3: kern = lb_pass_kernel<K, LB_STAGE3, 2>; break;
-        case LB_STAGE4: kern = lb_pass_kernel<K, LB_STAGE4, 2>; break;
-        case LB_RHS_OUT: kern = lb_pass_kernel<K, LB_RHS_OUT, 2>; break;
-        case LB_MOMENTS: kern = lb_pass_kernel<K, LB_MOMENTS, 2>; break;
-        case LB_EVAL: kern = lb_pass_kernel<K, LB_EVAL, 2>; break;
-        default: return fail(VPM_ERR_INVALID, "bad LB pass mode");
+        case LB_DEPOSIT_ONLY: kern = lb_pass_kernel<K, LB_DEPOSIT_ONLY, 2, 0>; break;
+        case LB_STAGE1: kern = lb_pass_kernel<K, LB_STAGE1, 2, 0>; break;
+        case LB_STAGE2: kern = lb_pass_kernel<K, LB_STAGE2, 2, 0>; break;
+        case LB_STAGE3: kern = lb_pass_kernel<K, LB_STAGE3, 2, 0>; break;
+        case LB_STAGE4: kern = lb_pass_kernel<K, LB_STAGE4, 2, 0>; break;
+        case LB_RHS_OUT: kern = lb_pass_kernel<K, LB_RHS_OUT, 2, 0>; break;
+        case LB_MOMENTS: kern = lb_pass_kernel<K, LB_MOMENTS, 2, 0>; break;
+        case LB_EVAL: kern = lb_pass_kernel<K, LB_EVAL, 2, 0>; break;
     }
     VPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -466,6 +491,8 @@ int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nr
     F.nv = vs->nv; F.nbfull = vs->nbfull; F.ncell = vs->ncell; F.K = vs->K; F.off = vs->dirichlet ? 1 : 0;
     F.invh = vs->invh;
     const size_t smem = sizeof(double) * ((size_t)vs->nbfull + vs->nv);
+    if (smem > ctx->smem_optin) return fail(VPM_ERR_UNSUPPORTED, "v-space too large for the single-CTA field kernel");
+    if (smem > 48 * 1024) VPM_CUDA(cudaFuncSetAttribute(lb_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     const int red = phases & (LBF_REDUCE | LBF_SCALRED);
     if (ctx->comm.comm && red) {

@@ -47,7 +47,14 @@ struct VpCfg {
 constexpr int kMainFlags = VP_KICK1 | VP_POST1 | VP_DIAG | VP_POST2 | VP_DEPOSIT | VP_WRITE_X | VP_WRITE_V;
 constexpr int kFrozenFlags = VP_PRE | VP_KICK1 | VP_KICK2 | VP_POST1 | VP_DIAG | VP_WRITE_X | VP_WRITE_V;
 
-template <int K, int FLAGS>
+// HM: histogram privatisation. 0 = one copy per thread (no atomics), 1 = one copy per warp, 2 = one copy per
+// CTA (shared-memory atomicAdd; for grids whose per-thread copies would not fit in shared memory)
+template <int HM>
+struct HistCfg {
+    static constexpr int copies = HM == 0 ? kBlock : (HM == 1 ? kBlock / 32 : 1);
+};
+
+template <int K, int FLAGS, int HM>
 __device__ __forceinline__ void vp_particle(const VpDev& P, const int flags_rt, const double* __restrict__ s_etab,
                                             double* __restrict__ s_hist, double& x, double& v, const double w,
                                             double& ksum, double& msum)
@@ -80,14 +87,18 @@ __device__ __forceinline__ void vp_particle(const VpDev& P, const int flags_rt, 
         basis_uniform<K>(u, b);
         // bins are unwrapped: cell c feeds bins c..c+K-1 (function c-K+1+j lives in bin c+j, folded
         // mod nh by the field kernel) -> one address computation, K immediate-offset RMWs
-        double* hcell = s_hist + wrap_index(ci, P.fm) * kBlock;
+        constexpr int HS = HistCfg<HM>::copies;
+        double* hcell = s_hist + wrap_index(ci, P.fm) * HS;
 #pragma unroll
-        for (int j = 0; j < K; j++) hcell[j * kBlock] = fma(w, b[j], hcell[j * kBlock]);
+        for (int j = 0; j < K; j++) {
+            if (HM == 0) hcell[j * HS] = fma(w, b[j], hcell[j * HS]);
+            else atomicAdd(hcell + j * HS, w * b[j]);
+        }
     }
 }
 
 // VEC = 2: 16-byte loads/stores, two particles per thread per trip, next trip prefetched.
-template <int K, int FLAGS, int VEC, int MINB>
+template <int K, int FLAGS, int VEC, int MINB, int HM>
 __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
 {
     extern __shared__ double smem[];
@@ -97,12 +108,14 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
     const int nb = P.nh + K - 1;
     double* s_red = smem;                       // 2 * warps
     double* s_etab = smem + 2 * (kBlock / 32);  // nh * ES
-    double* s_hist = s_etab + ((P.nh * ES + 1) & ~1) + tid;  // nb * kBlock, this thread's column
+    constexpr int HS = HistCfg<HM>::copies;
+    double* s_hbase = s_etab + ((P.nh * ES + 1) & ~1);                          // nb * HS
+    double* s_hist = s_hbase + (HM == 0 ? tid : (HM == 1 ? (tid >> 5) : 0));  // this thread's copy
 
     if (flags & VP_KICK1)
         for (int i = tid; i < P.nh * ES; i += kBlock) s_etab[i] = P.etab[i];
     if (flags & VP_DEPOSIT)
-        for (int b = 0; b < nb; b++) s_hist[b * kBlock] = 0.0;
+        for (int i = tid; i < nb * HS; i += kBlock) s_hbase[i] = 0.0;
     __syncthreads();
 
     double ksum = 0.0, msum = 0.0;
@@ -130,8 +143,8 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
                 if (need_v) vn = ld_stream2(P.v_in + 2 * inext);
                 if (need_w) wn = ld_stream2(P.w + 2 * inext);
             }
-            vp_particle<K, FLAGS>(P, flags, s_etab, s_hist, xa.x, va.x, wa.x, ksum, msum);
-            vp_particle<K, FLAGS>(P, flags, s_etab, s_hist, xa.y, va.y, wa.y, ksum, msum);
+            vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, xa.x, va.x, wa.x, ksum, msum);
+            vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, xa.y, va.y, wa.y, ksum, msum);
             if (flags & VP_WRITE_X) st_stream2(P.x_out + 2 * i, xa);
             if (flags & VP_WRITE_V) st_stream2(P.v_out + 2 * i, va);
             xa = xn; va = vn; wa = wn;
@@ -141,14 +154,14 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
         if ((P.n & 1) && gtid == 0) {  // odd tail
             const long long t = P.n - 1;
             double x = P.x_in[t], v = need_v ? P.v_in[t] : 0.0, w = need_w ? P.w[t] : 0.0;
-            vp_particle<K, FLAGS>(P, flags, s_etab, s_hist, x, v, w, ksum, msum);
+            vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, x, v, w, ksum, msum);
             if (flags & VP_WRITE_X) P.x_out[t] = x;
             if (flags & VP_WRITE_V) P.v_out[t] = v;
         }
     } else {
         for (long long i = gtid; i < P.n; i += stride) {
             double x = P.x_in[i], v = need_v ? P.v_in[i] : 0.0, w = need_w ? P.w[i] : 0.0;
-            vp_particle<K, FLAGS>(P, flags, s_etab, s_hist, x, v, w, ksum, msum);
+            vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, x, v, w, ksum, msum);
             if (flags & VP_WRITE_X) P.x_out[i] = x;
             if (flags & VP_WRITE_V) P.v_out[i] = v;
         }
@@ -157,11 +170,10 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
     const int lane = tid & 31, warp = tid >> 5;
     if (flags & VP_DEPOSIT) {
         __syncthreads();
-        const double* hist = s_hist - tid;
         for (int b = warp; b < nb; b += kBlock / 32) {
             double s = 0.0;
 #pragma unroll
-            for (int t = 0; t < kBlock / 32; t++) s += hist[b * kBlock + t * 32 + lane];
+            for (int t = lane; t < HS; t += 32) s += s_hbase[b * HS + t];
             s = warp_sum(s);
             if (lane == 0) P.partials[(size_t)blockIdx.x * P.nbp + b] = s;
         }
@@ -328,9 +340,21 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     P.nbp = nb;
 
     const bool dep = p.flags & VP_DEPOSIT;
-    size_t smem = sizeof(double) * (2 * (kBlock / 32) + ((xs->nh * ES + 1) & ~1) + (dep ? (size_t)nb * kBlock : 0));
+    const size_t base = sizeof(double) * (2 * (kBlock / 32) + ((xs->nh * ES + 1) & ~1));
+    // per-thread copies while at least two CTAs fit on an SM, then per-warp, then per-CTA copies with atomics
+    int hm = 0;
+    if (dep) {
+        if (base + sizeof(double) * (size_t)nb * kBlock > ctx->smem_optin / 2) hm = 1;
+        if (hm == 1 && base + sizeof(double) * (size_t)nb * (kBlock / 32) > ctx->smem_optin / 2) hm = 2;
+    }
+    if (const char* e = getenv("VPM_TUNE_HM")) {  // test hook: force a privatisation level
+        const int f = atoi(e);
+        if (f > hm && f <= 2 && dep) hm = f;
+    }
+    const size_t copies = hm == 0 ? kBlock : (hm == 1 ? kBlock / 32 : 1);
+    size_t smem = base + (dep ? sizeof(double) * (size_t)nb * copies : 0);
     if (smem > ctx->smem_optin)
-        return fail(VPM_ERR_UNSUPPORTED, "x-space too large for the shared-memory privatised deposit (n_basis + order - 1 bins x 2 KiB per CTA)");
+        return fail(VPM_ERR_UNSUPPORTED, "x-space too large: the field table and one histogram copy must fit in shared memory");
 
     auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const bool vec = aligned16(p.x_in) && aligned16(p.v_in) && aligned16(p.w) && aligned16(p.x_out) && aligned16(p.v_out);
@@ -343,12 +367,14 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
         return (v >= 2 && v <= 4) ? v : 3;
     }();
     void (*kern)(const VpDev) = nullptr;
-    if (vec && p.flags == kMainFlags) {
-        kern = tune_minb == 2 ? vp_pass_kernel<K, kMainFlags, 2, 2>
-             : tune_minb == 4 ? vp_pass_kernel<K, kMainFlags, 2, 4> : vp_pass_kernel<K, kMainFlags, 2, 3>;
-    } else if (vec && p.flags == kFrozenFlags) kern = vp_pass_kernel<K, kFrozenFlags, 2, 3>;
-    else if (vec) kern = vp_pass_kernel<K, -1, 2, 3>;
-    else kern = vp_pass_kernel<K, -1, 1, 3>;
+    if (hm == 1) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 1> : vp_pass_kernel<K, -1, 1, 3, 1>;
+    else if (hm == 2) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 2> : vp_pass_kernel<K, -1, 1, 3, 2>;
+    else if (vec && p.flags == kMainFlags) {
+        kern = tune_minb == 2 ? vp_pass_kernel<K, kMainFlags, 2, 2, 0>
+             : tune_minb == 4 ? vp_pass_kernel<K, kMainFlags, 2, 4, 0> : vp_pass_kernel<K, kMainFlags, 2, 3, 0>;
+    } else if (vec && p.flags == kFrozenFlags) kern = vp_pass_kernel<K, kFrozenFlags, 2, 3, 0>;
+    else if (vec) kern = vp_pass_kernel<K, -1, 2, 3, 0>;
+    else kern = vp_pass_kernel<K, -1, 1, 3, 0>;
 
     VPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -401,6 +427,8 @@ int launch_vp_field(vpm_ctx* ctx, vpm_xspace* xs, int phases, int nparts, int ha
     F.invh = xs->invh; F.escale = escale; F.wscale = wscale;
     F.w_slot = w_slot; F.km_slot = km_slot;
     const size_t smem = sizeof(double) * ((size_t)nb + 2 + 3 * (size_t)xs->nh);
+    if (smem > ctx->smem_optin) return fail(VPM_ERR_UNSUPPORTED, "x-space too large for the single-CTA field kernel");
+    if (smem > 48 * 1024) VPM_CUDA(cudaFuncSetAttribute(vp_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // multi-GPU: reduce locally, all-reduce rhs|K|M, then solve
     if (ctx->comm.comm && (phases & FIELD_REDUCE) && (has_dep || has_kin)) {
