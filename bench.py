@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="vp", choices=["vp", "lb", "clb"])
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: fused peer-memory all-reduce in the field kernel (default) or NCCL")
     return ap.parse_args()
 
 
@@ -147,10 +149,28 @@ def main():
     assert stream.cuda_stream != 0
     ctx = vpm.Context(local, stream.cuda_stream)
     vpm.set_default_context(ctx)
+    comm_used = "none"
     if world > 1:
-        obj = [vpm.Context.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(obj, src=0)
-        ctx.comm_init(world, rank, obj[0])
+        if args.comm == "p2p":
+            # fused peer-memory all-reduce inside the field kernel (p2p.cuh); NCCL is the fallback
+            try:
+                handles = [None] * world
+                dist.all_gather_object(handles, ctx.p2p_prepare())
+                ctx.p2p_attach(world, rank, handles)
+                ok = torch.tensor([1], device="cuda")
+            except vpm.VpmError as e:
+                print(f"[rank {rank}] p2p unavailable ({e}); falling back to NCCL", file=sys.stderr)
+                ok = torch.tensor([0], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 1:
+                comm_used = "p2p"
+            else:
+                ctx.p2p_detach()
+        if comm_used != "p2p":
+            obj = [vpm.Context.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(obj, src=0)
+            ctx.comm_init(world, rank, obj[0])
+            comm_used = "nccl"
 
     n = int(args.particles)
     ntotal = n * world
@@ -274,7 +294,7 @@ def main():
             "config": {"workload": wl, "particles_per_gpu": n, "n_basis": NH if args.workload == "vp" else 41,
                        "order": ORDER, "dt": DT if args.workload == "vp" else 1e-2,
                        "l2": "inputs (24 B x particles per GPU) larger than L2, no flush needed",
-                       "parallelism": f"particle slabs x{world}, coefficient all-reduce per field update" if world > 1 else "single GPU",
+                       "parallelism": f"particle slabs x{world}, coefficient all-reduce per field update ({comm_used})" if world > 1 else "single GPU",
                        "passes_in_timed_region": passes_per_call(args.steps)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "vp_pass_kernel" if args.workload == "vp" else "lb_pass_kernel",
@@ -285,7 +305,12 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        ctx.comm_destroy()
+        if comm_used == "p2p":
+            ctx.p2p_check()
+            dist.barrier()
+            ctx.p2p_detach()
+        else:
+            ctx.comm_destroy()
         dist.destroy_process_group()
 
 

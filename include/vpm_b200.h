@@ -185,6 +185,16 @@ int vpm_vspace_get(vpm_vspace* vs, double* rhs_host, double* coef_host);
 int vpm_comm_unique_id(void* unique_id_128);
 int vpm_comm_init(vpm_ctx* ctx, int nranks, int rank, const void* unique_id_128);
 int vpm_comm_destroy(vpm_ctx* ctx);
+/* Fused peer-memory all-reduce (preferred on NVLink/NVSwitch boxes; up to 8 ranks of one node): the field
+ * kernels push their partial coefficient vector into every peer's mailbox over NVLink, exchange sequence
+ * flags and sum in rank order inside the same kernel that then solves — no NCCL call, no extra launch, and
+ * bitwise-identical fields on all ranks.  vpm_p2p_prepare allocates this rank's mailbox and returns its
+ * 64-byte CUDA IPC handle; the host all-gathers the handles (rank order) and passes them to vpm_p2p_attach.
+ * When attached it takes precedence over the NCCL communicator.  vpm_p2p_error reports a timed-out peer. */
+int vpm_p2p_prepare(vpm_ctx* ctx, void* ipc_handle_64);
+int vpm_p2p_attach(vpm_ctx* ctx, int nranks, int rank, const void* ipc_handles);
+int vpm_p2p_detach(vpm_ctx* ctx);
+int vpm_p2p_error(vpm_ctx* ctx, uint64_t* failed_seq);
 /* in-place sum over ranks of a device buffer on the ctx stream (diagnostics, tests) */
 int vpm_comm_allreduce(vpm_ctx* ctx, double* buf_dev, int64_t count);
 

@@ -18,7 +18,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, nper, out_dir):
+def _worker(rank, world, port, nper, out_dir, comm):
     import sys
     sys.path.insert(0, ROOT)
     import torch
@@ -29,9 +29,15 @@ def _worker(rank, world, port, nper, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.cuda.set_device(rank)
     ctx = vpm.Context(rank)
-    obj = [vpm.Context.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(obj, src=0)
-    ctx.comm_init(world, rank, obj[0])
+    if comm == "nccl":
+        obj = [vpm.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        ctx.comm_init(world, rank, obj[0])
+    else:   # fused peer-memory all-reduce inside the field kernels
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.p2p_prepare())
+        ctx.p2p_attach(world, rank, handles)
+        dist.barrier()
     L = 2 * np.pi / 0.3
     # Vlasov-Poisson, self-consistent, exact diagnostics
     d = vpm.ParticleDistribution(1, 1, nper, ctx)
@@ -48,18 +54,24 @@ def _worker(rank, world, port, nper, out_dir):
     vpm.run_(gi)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), x=x, v=v, diag=m.diagnostics, phi=pot.coefficients,
              vlb=d2.get("v"), dlb=gi.diagnostics, coef=sd.coefficients)
-    ctx.comm_destroy()
+    if comm == "nccl":
+        ctx.comm_destroy()
+    else:
+        ctx.p2p_check()
+        dist.barrier()
+        ctx.p2p_detach()
     dist.destroy_process_group()
 
 
-def test_two_rank_slabs_match_single_gpu(tmp_path):
+@pytest.mark.parametrize("comm", ["p2p", "nccl"])
+def test_two_rank_slabs_match_single_gpu(tmp_path, comm):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
     import vpm_b200 as vpm
     world, nper = 2, 150001
-    mp.spawn(_worker, args=(world, _free_port(), nper, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), nper, str(tmp_path), comm), nprocs=world, join=True)
     r = [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
     np.testing.assert_array_equal(r[0]["phi"], r[1]["phi"])      # replicated solve on identical input
     np.testing.assert_array_equal(r[0]["diag"], r[1]["diag"])

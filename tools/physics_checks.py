@@ -78,6 +78,7 @@ def main(n=int(2e7)):
     # ---- Landau damping: f = (1 + a cos(k x)) Maxwellian, k = 0.5 (sampler: eps = -a, no beam) ----
     k, a, dt, ns = 0.5, 0.05, 0.05, 500
     dg = run_vp(vpm, n, k, -a, 0.0, 1.0, 0.0, 32, 4, dt, ns)
+    landau_hist = dg
     t = dt * np.arange(ns + 1)
     g, npk = fit_envelope_rate(t[1:], dg[1:, 0], 1.0, 16.0)
     w_th = most_unstable_root(k, [(1.0, 0.0, 1.0)], re_range=(1.0, 2.0), im_range=(-0.4, 0.0))
@@ -95,6 +96,21 @@ def main(n=int(2e7)):
     out["bump_on_tail"] = {"gamma_fit": g, "gamma_theory": w_th.imag, "omega_theory": w_th.real,
                            "W_first": float(W[0]), "W_max": float(W.max()), "t_sat": float(t[1:][W.argmax()]),
                            "energy_drift_rel": float(np.abs(E[1:] - E[1]).max() / E[1])}
+    # growth rate proper: same equilibrium, small perturbation (eps = 1e-3) so that the linear phase spans
+    # several e-foldings; fit log W where 50 W(0) < W < W_max / 20 (travelling unstable wave dominates)
+    dgs = run_vp(vpm, n, k, 1e-3, 0.1, 0.5, 4.5, 16, 4, dt, 600)
+    ts = dt * np.arange(601)
+    Ws = dgs[1:, 0]
+    lo_i = int(np.argmax(Ws > 50 * Ws[:20].max()))
+    hi_i = int(np.argmax(Ws > Ws.max() / 20))
+    if hi_i - lo_i < 20:
+        lo_i = max(hi_i - 60, 1)
+    gs = 0.5 * np.polyfit(ts[1:][lo_i:hi_i], np.log(Ws[lo_i:hi_i]), 1)[0]
+    out["bump_on_tail_small_eps"] = {"gamma_fit": float(gs), "gamma_theory": w_th.imag, "fit_window": [float(ts[1:][lo_i]), float(ts[1:][hi_i])],
+                                     "W_first": float(Ws[0]), "W_max": float(Ws.max())}
+    if os.path.isdir(os.path.join(ROOT, "gpurun_out")) or os.environ.get("GRAFT_REPO_ROOT"):
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.savez(os.path.join(ROOT, "gpurun_out", "physics_hist.npz"), landau=landau_hist, bot=dg, bot_small=dgs)
     print(json.dumps(out))
     return out
 

@@ -75,6 +75,10 @@ SIGNATURES = {
     "vpm_comm_unique_id": (_i32, [_vp]),
     "vpm_comm_init": (_i32, [_vp, _i32, _i32, _vp]),
     "vpm_comm_destroy": (_i32, [_vp]),
+    "vpm_p2p_prepare": (_i32, [_vp, _vp]),
+    "vpm_p2p_attach": (_i32, [_vp, _i32, _i32, _vp]),
+    "vpm_p2p_detach": (_i32, [_vp]),
+    "vpm_p2p_error": (_i32, [_vp, C.POINTER(_u64)]),
     "vpm_comm_allreduce": (_i32, [_vp, _vp, _i64]),
 }
 

@@ -88,6 +88,25 @@ class Context:
     def comm_destroy(self):
         check(_lib().vpm_comm_destroy(self._h))
 
+    # fused peer-memory all-reduce over NVLink (preferred): handles are exchanged by the host
+    def p2p_prepare(self):
+        buf = (C.c_char * 64)()
+        check(_lib().vpm_p2p_prepare(self._h, buf))
+        return bytes(buf)
+
+    def p2p_attach(self, nranks, rank, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * nranks
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        check(_lib().vpm_p2p_attach(self._h, int(nranks), int(rank), buf))
+
+    def p2p_detach(self):
+        check(_lib().vpm_p2p_detach(self._h))
+
+    def p2p_check(self):
+        seq = C.c_uint64()
+        check(_lib().vpm_p2p_error(self._h, C.byref(seq)))
+
 
 _default_ctx = None
 

@@ -175,6 +175,7 @@ int vpm_ctx_destroy(vpm_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     vpm_comm_destroy(ctx);
+    vpm_p2p_detach(ctx);
     cudaFree(ctx->partials);
     cudaFree(ctx->red);
     cudaFree(ctx->staging);
@@ -997,6 +998,82 @@ int vpm_comm_destroy(vpm_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->comm.api->CommDestroy(ctx->comm.comm);
     ctx->comm = vpm::Comm{};
+    return VPM_OK;
+}
+
+/* ---- fused peer-memory all-reduce (p2p.cuh) ---- */
+
+int vpm_p2p_prepare(vpm_ctx* ctx, void* ipc_handle_64)
+{
+    VPM_REQUIRE(ctx && ipc_handle_64, "vpm_p2p_prepare: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    vpm_p2p_detach(ctx);
+    cudaError_t e = cudaMalloc((void**)&ctx->p2p_local, sizeof(P2PMailbox));
+    if (e != cudaSuccess) return fail(VPM_ERR_NOMEM, std::string("cudaMalloc(mailbox): ") + cudaGetErrorString(e));
+    VPM_CUDA(cudaMemset(ctx->p2p_local, 0, sizeof(P2PMailbox)));
+    VPM_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    VPM_CUDA(cudaIpcGetMemHandle(&h, ctx->p2p_local));
+    std::memcpy(ipc_handle_64, &h, sizeof(h));
+    return VPM_OK;
+}
+
+int vpm_p2p_attach(vpm_ctx* ctx, int nranks, int rank, const void* ipc_handles)
+{
+    VPM_REQUIRE(ctx && ipc_handles && ctx->p2p_local, "vpm_p2p_attach: call vpm_p2p_prepare first");
+    VPM_REQUIRE(nranks >= 1 && nranks <= kP2PMaxRanks && rank >= 0 && rank < nranks, "vpm_p2p_attach: 1..8 ranks supported");
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    P2PDev d{};
+    d.nranks = nranks;
+    d.rank = rank;
+    for (int r = 0; r < nranks; r++) {
+        if (r == rank) {
+            d.mbox[r] = ctx->p2p_local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char*)ipc_handles + 64 * (size_t)r, sizeof(h));
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; q++)
+                if (ctx->p2p_opened[q]) { cudaIpcCloseMemHandle(ctx->p2p_opened[q]); ctx->p2p_opened[q] = nullptr; }
+            return fail(VPM_ERR_COMM, std::string("cudaIpcOpenMemHandle (peer access over NVLink unavailable?): ") + cudaGetErrorString(e));
+        }
+        ctx->p2p_opened[r] = ptr;
+        d.mbox[r] = (P2PMailbox*)ptr;
+    }
+    ctx->p2p = d;
+    ctx->p2p_seq = 0;
+    return VPM_OK;
+}
+
+int vpm_p2p_detach(vpm_ctx* ctx)
+{
+    if (!ctx) return VPM_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < kP2PMaxRanks; r++)
+        if (ctx->p2p_opened[r]) { cudaIpcCloseMemHandle(ctx->p2p_opened[r]); ctx->p2p_opened[r] = nullptr; }
+    if (ctx->p2p_local) cudaFree(ctx->p2p_local);
+    ctx->p2p_local = nullptr;
+    ctx->p2p = P2PDev{};
+    ctx->p2p_seq = 0;
+    return VPM_OK;
+}
+
+int vpm_p2p_error(vpm_ctx* ctx, uint64_t* failed_seq)
+{
+    VPM_REQUIRE(ctx && failed_seq, "vpm_p2p_error: NULL argument");
+    *failed_seq = 0;
+    if (!ctx->p2p_local) return VPM_OK;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    unsigned long long e = 0;
+    VPM_CUDA(cudaMemcpy(&e, &ctx->p2p_local->error, sizeof(e), cudaMemcpyDeviceToHost));
+    *failed_seq = e;
+    if (e) return fail(VPM_ERR_COMM, "peer-memory all-reduce timed out waiting for a rank (sequence " + std::to_string(e) + ")");
     return VPM_OK;
 }
 

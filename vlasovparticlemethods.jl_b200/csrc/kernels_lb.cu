@@ -312,6 +312,7 @@ struct LbFieldDev {
     const double *chol, *pieces;
     int nv, nbfull, ncell, K, off;
     double invh;
+    P2PDev p2p;
 };
 
 __global__ void __launch_bounds__(kFieldThreads) lb_field_kernel(const LbFieldDev F)
@@ -343,6 +344,12 @@ __global__ void __launch_bounds__(kFieldThreads) lb_field_kernel(const LbFieldDe
             if (lane == 0) F.rhs[nv + warp] = s;
         }
         __syncthreads();
+    }
+    if (F.p2p.seq && (F.phases & (LBF_REDUCE | LBF_SCALRED))) {
+        // multi-GPU: rhs | scalar sums are contiguous; one fused peer-memory all-reduce
+        const int start = (F.phases & LBF_REDUCE) ? 0 : nv;
+        const int cnt = ((F.phases & LBF_REDUCE) ? nv : 0) + ((F.phases & LBF_SCALRED) ? F.nred : 0);
+        p2p_allreduce(F.p2p, F.rhs + start, cnt);
     }
     if (F.phases & LBF_SOLVE) {
         // ldiv!(coefficients, cholesky(M), rhs): banded forward / backward substitution
@@ -495,7 +502,12 @@ int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nr
     if (smem > 48 * 1024) VPM_CUDA(cudaFuncSetAttribute(lb_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     const int red = phases & (LBF_REDUCE | LBF_SCALRED);
-    if (ctx->comm.comm && red) {
+    F.p2p = P2PDev{};
+    if (ctx->p2p.nranks > 1 && red) {
+        if ((size_t)vs->nv + 8 > (size_t)kP2PCap) return fail(VPM_ERR_UNSUPPORTED, "coefficient vector exceeds the peer mailbox slot");
+        F.p2p = ctx->p2p;
+        F.p2p.seq = ++ctx->p2p_seq;
+    } else if (ctx->comm.comm && red) {
         F.phases = red;
         prof_begin(ctx, PROF_LB_FIELD);
     lb_field_kernel<<<1, kFieldThreads, smem, ctx->stream>>>(F);

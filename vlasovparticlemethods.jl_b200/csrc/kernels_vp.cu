@@ -210,6 +210,7 @@ struct FieldDev {
     int nh, K, ES;
     double invh, escale, wscale;
     int phases, w_slot, km_slot;
+    P2PDev p2p;
 };
 
 __global__ void __launch_bounds__(kFieldThreads) vp_field_kernel(const FieldDev F)
@@ -249,6 +250,11 @@ __global__ void __launch_bounds__(kFieldThreads) vp_field_kernel(const FieldDev 
                 F.rhs[i] = s;
             }
         __syncthreads();
+        // multi-GPU: sum rhs | K | M over the ranks through NVLink peer memory, inside this kernel
+        if (F.p2p.seq) {
+            if (F.has_dep) p2p_allreduce(F.p2p, F.rhs, nh + 2);
+            else p2p_allreduce(F.p2p, F.rhs + nh, 2);
+        }
     }
 
     if (F.phases & FIELD_SOLVE) {
@@ -430,8 +436,14 @@ int launch_vp_field(vpm_ctx* ctx, vpm_xspace* xs, int phases, int nparts, int ha
     if (smem > ctx->smem_optin) return fail(VPM_ERR_UNSUPPORTED, "x-space too large for the single-CTA field kernel");
     if (smem > 48 * 1024) VPM_CUDA(cudaFuncSetAttribute(vp_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
-    // multi-GPU: reduce locally, all-reduce rhs|K|M, then solve
-    if (ctx->comm.comm && (phases & FIELD_REDUCE) && (has_dep || has_kin)) {
+    F.p2p = P2PDev{};
+    if (ctx->p2p.nranks > 1 && (phases & FIELD_REDUCE) && (has_dep || has_kin)) {
+        if ((size_t)xs->nh + 2 > (size_t)kP2PCap) return fail(VPM_ERR_UNSUPPORTED, "coefficient vector exceeds the peer mailbox slot");
+        F.p2p = ctx->p2p;
+        F.p2p.seq = ++ctx->p2p_seq;
+    }
+    // NCCL path: reduce locally, all-reduce rhs|K|M, then solve
+    else if (ctx->comm.comm && (phases & FIELD_REDUCE) && (has_dep || has_kin)) {
         F.phases = FIELD_REDUCE;
         F.w_slot = F.km_slot = -1;
         prof_begin(ctx, PROF_VP_FIELD);

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/vpm_b200.h"
+#include "p2p.cuh"
 
 namespace vpm {
 
@@ -57,6 +58,11 @@ struct vpm_ctx {
     double* staging = nullptr; // AoS <-> SoA staging
     size_t staging_cap = 0;    // doubles
     vpm::Comm comm;
+    // fused peer-memory all-reduce (p2p.cuh): preferred over NCCL when attached
+    vpm::P2PDev p2p{};
+    vpm::P2PMailbox* p2p_local = nullptr;
+    void* p2p_opened[vpm::kP2PMaxRanks] = {};
+    unsigned long long p2p_seq = 0;
     uint64_t launches = 0;     // kernels launched by this library (bench "gpu_launches")
     // optional per-launch CUDA-event timing (vpm_profile): pairs of events on the launching stream
     bool profile = false;
