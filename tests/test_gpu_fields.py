@@ -70,3 +70,20 @@ def test_legacy_field_functors(vpm, oracle):
     f4 = vpm.ScaledPoissonField(pot, 2.0)
     e4 = f4(np.zeros(n), x, w, 0.0)
     assert nrm(e4, e1 / 4) < 1e-15 and abs(f4.energy() - f1.energy() / 4) < 1e-15
+
+
+def test_plain_c_driver_runs():
+    """The ABI is usable from plain C without Python or torch (examples/vp_bump_on_tail.c)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "vp_bump_on_tail")
+    subprocess.check_call(["gcc", "-O2", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "vp_bump_on_tail.c"),
+                           "-o", exe, "-L" + os.path.join(root, "vlasovparticlemethods.jl_b200", "lib"), "-lvpm_b200",
+                           "-Wl,-rpath," + os.path.join(root, "vlasovparticlemethods.jl_b200", "lib"), "-lm"])
+    out = subprocess.run([exe, "2000000", "100"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    last = out.stdout.strip().splitlines()[-1]
+    assert "particle-steps/s" in last
+    drift = float(last.split("energy drift")[1])
+    assert drift < 5e-3
