@@ -40,17 +40,14 @@ constexpr int kRedW = 8;  // doubles per CTA row of scalar partial sums
 template <int K>
 __device__ __forceinline__ bool v_locate(const LbDev& P, double q, int& ci, double& u)
 {
-    const bool inside = (q >= P.lo) && (q <= P.hi);
+    const bool inside = (q >= P.lo) && (q <= P.hi);  // NaN -> outside
     const double t = (q - P.lo) * P.invh;
-    split_floor(inside ? t : 0.0, ci, u);
-    if (ci > P.ncell - 1) {  // q == hi belongs to the last cell
+    split_floor(t, ci, u);
+    if (ci > P.ncell - 1) {  // q == hi belongs to the last cell (u = 1); garbage for outside particles
         ci = P.ncell - 1;
         u = t - (double)ci;
     }
-    if (ci < 0) {
-        ci = 0;
-        u = 0.0;
-    }
+    ci = max(ci, 0);         // outside particles: any valid cell, their f, f' are masked and nothing is deposited
     return inside;
 }
 
@@ -59,16 +56,24 @@ struct HistCfg {
     static constexpr int copies = HM == 0 ? kBlock : (HM == 1 ? kBlock / 32 : 1);
 };
 
-template <int K, int HM>
-__device__ __forceinline__ void v_deposit(const LbDev& P, double* __restrict__ s_hist, double q, double w)
-{
+// Deposit in two halves so that the pair loop can finish the arithmetic of both particles before the
+// (ordered) shared-memory read-modify-writes: prepare = locate + basis * weight, commit = K RMWs.
+template <int K>
+struct LbDep {
     int ci;
+    bool on;
+    double wb[K];
+};
+
+template <int K>
+__device__ __forceinline__ void v_deposit_prepare(const LbDev& P, double q, double w, LbDep<K>& d)
+{
     double u, b[K];
-    if (!v_locate<K>(P, q, ci, u)) return;  // out-of-domain particles deposit nothing
-    if (ci >= K - 1 && ci <= P.ncell - K) {
+    d.on = v_locate<K>(P, q, d.ci, u);  // out-of-domain particles deposit nothing
+    if (d.ci >= K - 1 && d.ci <= P.ncell - K) {
         basis_uniform<K>(u, b);
     } else {  // the K-1 cells at either end feel the repeated knots: per-cell table
-        const double* pc = P.pieces + (size_t)ci * K * K;
+        const double* pc = P.pieces + (size_t)d.ci * K * K;
 #pragma unroll
         for (int j = 0; j < K; j++) {
             double r = __ldg(pc + j * K + K - 1);
@@ -77,12 +82,20 @@ __device__ __forceinline__ void v_deposit(const LbDev& P, double* __restrict__ s
             b[j] = r;
         }
     }
+#pragma unroll
+    for (int j = 0; j < K; j++) d.wb[j] = b[j] * w;
+}
+
+template <int K, int HM>
+__device__ __forceinline__ void v_deposit_commit(double* __restrict__ s_hist, const LbDep<K>& d)
+{
+    if (!d.on) return;
     constexpr int HS = HistCfg<HM>::copies;
-    double* hcell = s_hist + ci * HS;
+    double* hcell = s_hist + d.ci * HS;
 #pragma unroll
     for (int j = 0; j < K; j++) {
-        if (HM == 0) hcell[j * HS] = fma(b[j], w, hcell[j * HS]);
-        else atomicAdd(hcell + j * HS, b[j] * w);
+        if (HM == 0) hcell[j * HS] += d.wb[j];
+        else atomicAdd(hcell + j * HS, d.wb[j]);
     }
 }
 
@@ -108,14 +121,15 @@ struct LbItem {
     double q, w, v0, acc, d;
 };
 
-template <int K, int MODE, int HM>
+template <int K, int MODE>
 __device__ __forceinline__ void lb_particle(const LbDev& P, const int mode_rt, const double* __restrict__ s_tab,
-                                            double* __restrict__ s_hist, LbItem& it, double& o1, double& o2,
+                                            LbDep<K>& dep, LbItem& it, double& o1, double& o2,
                                             double (&sums)[5], const double A1, const double A2)
 {
     const int mode = MODE >= 0 ? MODE : mode_rt;
+    dep.on = false;
     if (mode == LB_DEPOSIT_ONLY) {
-        v_deposit<K, HM>(P, s_hist, it.q, it.w);
+        v_deposit_prepare<K>(P, it.q, it.w, dep);
         if (P.diag) {
             sums[0] += it.q;
             sums[1] = fma(it.q, it.q, sums[1]);
@@ -164,7 +178,7 @@ __device__ __forceinline__ void lb_particle(const LbDev& P, const int mode_rt, c
         }
     }
     it.q = qn;
-    v_deposit<K, HM>(P, s_hist, qn, it.w);
+    v_deposit_prepare<K>(P, qn, it.w, dep);
 }
 
 template <int MODE>
@@ -183,7 +197,7 @@ struct LbIo {
 };
 
 template <int K, int MODE, int VEC, int HM>
-__global__ void __launch_bounds__(kBlock) lb_pass_kernel(const LbDev P)
+__global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT) ? 4 : 2) lb_pass_kernel(const LbDev P)
 {
     extern __shared__ double smem[];
     constexpr int TS = 2 * K - 1;
@@ -247,8 +261,13 @@ __global__ void __launch_bounds__(kBlock) lb_pass_kernel(const LbDev P)
             }
             LbItem i0{qa.x, wa.x, va.x, aa.x, da.x}, i1{qa.y, wa.y, va.y, aa.y, da.y};
             double2 o1 = z2, o2 = z2;
-            lb_particle<K, MODE, HM>(P, mode, s_tab, s_hist, i0, o1.x, o2.x, sums, A1, A2);
-            lb_particle<K, MODE, HM>(P, mode, s_tab, s_hist, i1, o1.y, o2.y, sums, A1, A2);
+            LbDep<K> d0, d1;
+            lb_particle<K, MODE>(P, mode, s_tab, d0, i0, o1.x, o2.x, sums, A1, A2);
+            lb_particle<K, MODE>(P, mode, s_tab, d1, i1, o1.y, o2.y, sums, A1, A2);
+            if (dep) {
+                v_deposit_commit<K, HM>(s_hist, d0);
+                v_deposit_commit<K, HM>(s_hist, d1);
+            }
             if (wr_q) st_stream2(P.qout + 2 * i, make_double2(i0.q, i1.q));
             if (wr_acc) st_stream2(P.acc + 2 * i, make_double2(i0.acc, i1.acc));
             if (wr_d) st_stream2(P.d + 2 * i, make_double2(i0.d, i1.d));
@@ -265,7 +284,9 @@ __global__ void __launch_bounds__(kBlock) lb_pass_kernel(const LbDev P)
         for (long long i = i0; i < P.n; i += stride) {
             LbItem it{P.q[i], rd_w ? P.w[i] : 0.0, rd_v0 ? P.v0[i] : 0.0, rd_acc ? P.acc[i] : 0.0, rd_d ? P.d[i] : 0.0};
             double o1 = 0.0, o2 = 0.0;
-            lb_particle<K, MODE, HM>(P, mode, s_tab, s_hist, it, o1, o2, sums, A1, A2);
+            LbDep<K> d0;
+            lb_particle<K, MODE>(P, mode, s_tab, d0, it, o1, o2, sums, A1, A2);
+            if (dep) v_deposit_commit<K, HM>(s_hist, d0);
             if (wr_q) P.qout[i] = it.q;
             if (wr_acc) P.acc[i] = it.acc;
             if (wr_d) P.d[i] = it.d;
@@ -325,9 +346,7 @@ __global__ void __launch_bounds__(kFieldThreads) lb_field_kernel(const LbFieldDe
 
     if (F.phases & LBF_REDUCE) {
         for (int b = warp; b < F.nbfull; b += nwarps) {
-            double s = 0.0;
-            for (int p = lane; p < F.nparts; p += 32) s += F.partials[(size_t)p * F.nbfull + b];
-            s = warp_sum(s);
+            const double s = warp_sum(strided_sum(F.partials + b, (size_t)F.nbfull, F.nparts, lane));
             if (lane == 0) s_full[b] = s;
         }
         __syncthreads();
@@ -338,9 +357,7 @@ __global__ void __launch_bounds__(kFieldThreads) lb_field_kernel(const LbFieldDe
     if (F.phases & LBF_SCALRED) {
         // scalar partial sums (moments: 5, diagnostics: 2) -> rhs[nv..nv+nred)
         if (warp < F.nred) {
-            double s = 0.0;
-            for (int p = lane; p < F.nparts; p += 32) s += F.red_partials[(size_t)p * kRedW + warp];
-            s = warp_sum(s);
+            const double s = warp_sum(strided_sum(F.red_partials + warp, (size_t)kRedW, F.nparts, lane));
             if (lane == 0) F.rhs[nv + warp] = s;
         }
         __syncthreads();

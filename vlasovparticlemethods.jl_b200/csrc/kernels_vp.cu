@@ -229,16 +229,12 @@ __global__ void __launch_bounds__(kFieldThreads) vp_field_kernel(const FieldDev 
         // fixed-order reduction of the per-CTA partial rows: lane-strided partial sums + xor tree
         if (F.has_dep) {
             for (int b = warp; b < F.nb; b += nwarps) {
-                double s = 0.0;
-                for (int p = lane; p < F.nparts; p += 32) s += F.partials[(size_t)p * F.nbp + b];
-                s = warp_sum(s);
+                const double s = warp_sum(strided_sum(F.partials + b, (size_t)F.nbp, F.nparts, lane));
                 if (lane == 0) s_ru[b] = s;
             }
         }
         if (F.has_kin && warp < 2) {
-            double s = 0.0;
-            for (int p = lane; p < F.nparts; p += 32) s += F.kin_partials[2 * p + warp];
-            s = warp_sum(s);
+            const double s = warp_sum(strided_sum(F.kin_partials + warp, 2, F.nparts, lane));
             if (lane == 0) F.rhs[nh + warp] = s;
         }
         __syncthreads();

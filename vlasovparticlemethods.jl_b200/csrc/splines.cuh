@@ -90,6 +90,23 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// s = a[lane*stride] + a[(lane+32)*stride] + ... in exactly that (sequential) order, with eight loads in
+// flight per lane so the single-CTA field kernels are not a chain of L2 round trips
+__device__ __forceinline__ double strided_sum(const double* __restrict__ a, size_t stride, int n, int lane)
+{
+    double s = 0.0;
+    int p = lane;
+    for (; p + 224 < n; p += 256) {
+        double t[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) t[k] = a[(size_t)(p + 32 * k) * stride];
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += t[k];
+    }
+    for (; p < n; p += 32) s += a[(size_t)p * stride];
+    return s;
+}
+
 __device__ __forceinline__ double2 ld_stream2(const double* p) { return __ldcs(reinterpret_cast<const double2*>(p)); }
 __device__ __forceinline__ void st_stream2(double* p, double2 v) { __stcs(reinterpret_cast<double2*>(p), v); }
 
