@@ -179,6 +179,17 @@ int vpm_lb_rk438_steps(vpm_vspace* vs, vpm_particles* p, double nu, double dt, i
 int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double dt, int nsteps, int conservative);
 int vpm_vspace_get(vpm_vspace* vs, double* rhs_host, double* coef_host);
 
+/* ---- host-side operator construction (no GPU needed; what the spaces upload at creation) ----------- */
+/* galerkin_matrix of the periodic basis: first rows (circulant) of the mass and stiffness matrices and of
+ * the zero-mean pseudo-inverse of the stiffness matrix; each output n_basis doubles, any may be NULL */
+int vpm_galerkin_periodic(double lo, double hi, int order, int n_basis, double* mass_row, double* stiff_row, double* pinv_row);
+/* galerkin_matrix(basis) and its banded Cholesky factor for the clamped (Dirichlet) basis
+ * (src/distributions/spline_distribution.jl:10-11): M is size x size row-major, chol_band is size x order
+ * with chol_band[i*order + k] = L(i, i-k); either may be NULL.  Returns the basis size in *size. */
+int vpm_galerkin_clamped(double lo, double hi, int nknots, int order, int dirichlet, int* size, double* M, double* chol_band);
+/* checks the invariant-divisor index wrap used by the kernels against % for divisor d; 0 = ok */
+int vpm_selftest_wrap(int d);
+
 /* ---- multi-GPU: one process per GPU, particle slabs, coefficient vectors all-reduced ---- */
 /* NCCL is dlopen'ed (libnccl.so.2; inside a torch process this resolves to torch's bundled NCCL).
  * unique_id: 128 bytes, produced on rank 0 and broadcast by the host (e.g. torch.distributed). */

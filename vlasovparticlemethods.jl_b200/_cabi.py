@@ -72,6 +72,9 @@ SIGNATURES = {
     "vpm_lb_rk438_steps": (_i32, [_vp, _vp, _f64, _f64, _i32, _i32, _vp]),
     "vpm_lb_rk438_steps_async": (_i32, [_vp, _vp, _f64, _f64, _i32, _i32]),
     "vpm_vspace_get": (_i32, [_vp, _vp, _vp]),
+    "vpm_galerkin_periodic": (_i32, [_f64, _f64, _i32, _i32, _vp, _vp, _vp]),
+    "vpm_galerkin_clamped": (_i32, [_f64, _f64, _i32, _i32, _i32, C.POINTER(_i32), _vp, _vp]),
+    "vpm_selftest_wrap": (_i32, [_i32]),
     "vpm_comm_unique_id": (_i32, [_vp]),
     "vpm_comm_init": (_i32, [_vp, _i32, _i32, _vp]),
     "vpm_comm_destroy": (_i32, [_vp]),

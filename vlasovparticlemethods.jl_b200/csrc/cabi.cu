@@ -959,6 +959,68 @@ int vpm_vspace_get(vpm_vspace* vs, double* rhs_host, double* coef_host)
     return VPM_OK;
 }
 
+/* ---------------------------------------------------------------- host-side operators */
+
+int vpm_galerkin_periodic(double lo, double hi, int order, int n_basis, double* mass_row, double* stiff_row, double* pinv_row)
+{
+    VPM_REQUIRE(order >= 2 && order <= kMaxOrder && n_basis >= 1 && hi > lo, "vpm_galerkin_periodic: bad arguments");
+    std::vector<double> ms, ss, mrow, srow, pinv;
+    periodic_stencils(order, (hi - lo) / n_basis, ms, ss);
+    circulant_first_row(ms, order, n_basis, mrow);
+    circulant_first_row(ss, order, n_basis, srow);
+    if (mass_row) std::memcpy(mass_row, mrow.data(), sizeof(double) * n_basis);
+    if (stiff_row) std::memcpy(stiff_row, srow.data(), sizeof(double) * n_basis);
+    if (pinv_row) {
+        circulant_pinv(srow, true, pinv);
+        std::memcpy(pinv_row, pinv.data(), sizeof(double) * n_basis);
+    }
+    return VPM_OK;
+}
+
+int vpm_galerkin_clamped(double lo, double hi, int nknots, int order, int dirichlet, int* size, double* M, double* chol_band)
+{
+    VPM_REQUIRE(order >= 2 && order <= kMaxOrder && nknots >= 2 && hi > lo && size, "vpm_galerkin_clamped: bad arguments");
+    const int nv = nknots + order - 2 - (dirichlet ? 2 : 0);
+    VPM_REQUIRE(nv >= 1, "vpm_galerkin_clamped: empty basis");
+    *size = nv;
+    if (!M && !chol_band) return VPM_OK;
+    std::vector<double> pieces, mass, chol;
+    clamped_piece_table(lo, hi, nknots, order, pieces);
+    clamped_mass(pieces, nknots - 1, order, (hi - lo) / (nknots - 1), dirichlet, mass);
+    if (M) std::memcpy(M, mass.data(), sizeof(double) * mass.size());
+    if (chol_band) {
+        if (banded_cholesky(mass, nv, order, chol) != 0) return fail(VPM_ERR_INVALID, "mass matrix is not positive definite");
+        std::memcpy(chol_band, chol.data(), sizeof(double) * chol.size());
+    }
+    return VPM_OK;
+}
+
+int vpm_selftest_wrap(int d)
+{
+    VPM_REQUIRE(d >= 1 && d <= (1 << 20), "vpm_selftest_wrap: divisor out of range");
+    const FastMod fm = make_fastmod(d);
+    auto wrap = [&](int ci) -> int {
+        if (fm.d <= 1u) return 0;
+        const uint32_t n = (uint32_t)(ci + fm.bias);
+        const uint32_t q = (uint32_t)(((uint64_t)n * fm.magic) >> 32) >> fm.shift;
+        return (int)(n - q * fm.d);
+    };
+    auto ref = [&](long long ci) -> int { long long r = ci % d; return (int)(r < 0 ? r + d : r); };
+    const int lim = 1 << 30;
+    for (long long ci = -3LL * d - 5; ci <= 3LL * d + 5; ci++)
+        if (wrap((int)ci) != ref(ci)) return fail(VPM_ERR_INVALID, "wrap mismatch near zero");
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    for (int it = 0; it < 2000000; it++) {
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        const int span = lim - d;   // valid index range of the kernels: |ci| <= 2^30 - d
+        const int ci = (int)((s >> 33) % (2ull * span + 1)) - span;
+        if (wrap(ci) != ref(ci)) return fail(VPM_ERR_INVALID, "wrap mismatch at " + std::to_string(ci));
+    }
+    for (int ci : {lim - d, -(lim - d), lim - 1 - d, -(lim - 1) + d})
+        if (wrap(ci) != ref(ci)) return fail(VPM_ERR_INVALID, "wrap mismatch at the range end");
+    return VPM_OK;
+}
+
 /* ---------------------------------------------------------------- multi-GPU */
 
 int vpm_comm_unique_id(void* unique_id_128)

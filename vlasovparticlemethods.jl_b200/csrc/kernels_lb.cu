@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(kFieldThreads) lb_field_kernel(const LbFieldDe
     extern __shared__ double sm[];
     double* s_full = sm;                 // nbfull
     double* s_y = s_full + F.nbfull;     // nv
+    double* s_chol = s_y + F.nv;         // nv * K
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kFieldThreads / 32;
     const int K = F.K, nv = F.nv;
 
@@ -370,18 +371,24 @@ __global__ void __launch_bounds__(kFieldThreads) lb_field_kernel(const LbFieldDe
     }
     if (F.phases & LBF_SOLVE) {
         // ldiv!(coefficients, cholesky(M), rhs): banded forward / backward substitution
+        // factor staged in shared memory (diagonal as reciprocals) so the sequential sweeps of thread 0 are
+        // chains of shared-memory loads, not L2 round trips
         for (int i = tid; i < nv; i += kFieldThreads) s_y[i] = F.rhs[i];
+        for (int i = tid; i < nv * K; i += kFieldThreads) {
+            const double c = F.chol[i];
+            s_chol[i] = (i % K == 0) ? 1.0 / c : c;
+        }
         __syncthreads();
         if (tid == 0) {
             for (int i = 0; i < nv; i++) {
                 double s = s_y[i];
-                for (int k = 1; k < K && k <= i; k++) s -= F.chol[(size_t)i * K + k] * s_y[i - k];
-                s_y[i] = s / F.chol[(size_t)i * K];
+                for (int k = 1; k < K && k <= i; k++) s -= s_chol[i * K + k] * s_y[i - k];
+                s_y[i] = s * s_chol[i * K];
             }
             for (int i = nv - 1; i >= 0; i--) {
                 double s = s_y[i];
-                for (int k = 1; k < K && i + k < nv; k++) s -= F.chol[(size_t)(i + k) * K + k] * s_y[i + k];
-                s_y[i] = s / F.chol[(size_t)i * K];
+                for (int k = 1; k < K && i + k < nv; k++) s -= s_chol[(i + k) * K + k] * s_y[i + k];
+                s_y[i] = s * s_chol[i * K];
             }
         }
         __syncthreads();
@@ -514,7 +521,7 @@ int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nr
     F.chol = vs->chol; F.pieces = vs->pieces;
     F.nv = vs->nv; F.nbfull = vs->nbfull; F.ncell = vs->ncell; F.K = vs->K; F.off = vs->dirichlet ? 1 : 0;
     F.invh = vs->invh;
-    const size_t smem = sizeof(double) * ((size_t)vs->nbfull + vs->nv);
+    const size_t smem = sizeof(double) * ((size_t)vs->nbfull + vs->nv + (size_t)vs->nv * vs->K);
     if (smem > ctx->smem_optin) return fail(VPM_ERR_UNSUPPORTED, "v-space too large for the single-CTA field kernel");
     if (smem > 48 * 1024) VPM_CUDA(cudaFuncSetAttribute(lb_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 

@@ -220,10 +220,20 @@ __global__ void __launch_bounds__(kFieldThreads) vp_field_kernel(const FieldDev 
     double* s_b = s_ru + F.nb + 2;   // nh
     double* s_phi = s_b + F.nh;      // nh
     double* s_d = s_phi + F.nh;      // nh
+    double* s_ginv = s_d + F.nh;     // nh
+    double* s_stiff = s_ginv + F.nh; // 2K-1
+    double* s_dpiece = s_stiff + 2 * F.K - 1;  // (K-1)^2
     __shared__ double s_scal[4];
     __shared__ double s_w[kFieldThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kFieldThreads / 32;
     const int nh = F.nh, K = F.K;
+    // constant operators into shared memory up front: their L2 latency overlaps the partial-row loads
+    if (F.phases & FIELD_SOLVE)
+        for (int i = tid; i < nh; i += kFieldThreads) s_ginv[i] = F.ginv[i];
+    if (F.phases & (FIELD_SOLVE | FIELD_TABLE)) {
+        for (int i = tid; i < 2 * K - 1; i += kFieldThreads) s_stiff[i] = F.stiff[i];
+        for (int i = tid; i < (K - 1) * (K - 1); i += kFieldThreads) s_dpiece[i] = F.dpiece[i];
+    }
 
     if (F.phases & FIELD_REDUCE) {
         // fixed-order reduction of the per-CTA partial rows: lane-strided partial sums + xor tree
@@ -270,7 +280,7 @@ __global__ void __launch_bounds__(kFieldThreads) vp_field_kernel(const FieldDev 
             for (int j = 0; j < nh; j++) {
                 int d = i - j;
                 if (d < 0) d += nh;
-                s = fma(F.ginv[d], s_b[j] - mean, s);
+                s = fma(s_ginv[d], s_b[j] - mean, s);
             }
             s_phi[i] = s;
             F.phi[i] = s;
@@ -284,7 +294,7 @@ __global__ void __launch_bounds__(kFieldThreads) vp_field_kernel(const FieldDev 
                 for (int d = -(K - 1); d <= K - 1; d++) {
                     int j = (i + d) % nh;
                     if (j < 0) j += nh;
-                    r = fma(F.stiff[d + K - 1], s_phi[j], r);
+                    r = fma(s_stiff[d + K - 1], s_phi[j], r);
                 }
                 s = fma(s_phi[i], r, s);
             }
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(kFieldThreads) vp_field_kernel(const FieldDev 
             for (int j = 0; j < K1; j++) {
                 int i = (c - K + 2 + j) % nh;
                 if (i < 0) i += nh;
-                s = fma(s_d[i], F.dpiece[j * K1 + m], s);
+                s = fma(s_d[i], s_dpiece[j * K1 + m], s);
             }
             F.etab[c * F.ES + m] = F.escale * s;
         }
@@ -428,7 +438,7 @@ int launch_vp_field(vpm_ctx* ctx, vpm_xspace* xs, int phases, int nparts, int ha
     F.nh = xs->nh; F.K = xs->K; F.ES = (xs->K - 1) | 1;
     F.invh = xs->invh; F.escale = escale; F.wscale = wscale;
     F.w_slot = w_slot; F.km_slot = km_slot;
-    const size_t smem = sizeof(double) * ((size_t)nb + 2 + 3 * (size_t)xs->nh);
+    const size_t smem = sizeof(double) * ((size_t)nb + 2 + 4 * (size_t)xs->nh + 2 * xs->K - 1 + (size_t)(xs->K - 1) * (xs->K - 1));
     if (smem > ctx->smem_optin) return fail(VPM_ERR_UNSUPPORTED, "x-space too large for the single-CTA field kernel");
     if (smem > 48 * 1024) VPM_CUDA(cudaFuncSetAttribute(vp_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
