@@ -191,7 +191,10 @@ int vpm_galerkin_clamped(double lo, double hi, int nknots, int order, int dirich
 int vpm_selftest_wrap(int d);
 
 /* ---- multi-GPU: one process per GPU, particle slabs, coefficient vectors all-reduced ---- */
-/* NCCL is dlopen'ed (libnccl.so.2; inside a torch process this resolves to torch's bundled NCCL).
+/* With a communicator (NCCL or peer-memory) attached, every deposit / moment / diagnostic reduction returns
+ * the sum over all ranks, so fields and coefficients are identical on every rank; all ranks must make the
+ * same sequence of calls (SPMD).  Solves and gathers on given coefficients stay local.
+ * NCCL is dlopen'ed (libnccl.so.2; inside a torch process this resolves to torch's bundled NCCL).
  * unique_id: 128 bytes, produced on rank 0 and broadcast by the host (e.g. torch.distributed). */
 int vpm_comm_unique_id(void* unique_id_128);
 int vpm_comm_init(vpm_ctx* ctx, int nranks, int rank, const void* unique_id_128);
