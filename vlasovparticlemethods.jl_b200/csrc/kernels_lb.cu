@@ -235,28 +235,7 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
     const bool wr_o1 = Io::wr_o1 && (mode == LB_RHS_OUT || mode == LB_EVAL) && P.out != nullptr;
     const bool wr_o2 = Io::wr_o2 && mode == LB_EVAL && P.out2 != nullptr;
 
-    if (VEC == 2 && MODE == LB_MOMENTS) {
-        // read-only pass (8 B/particle): four independent 16-byte loads in flight per thread, eight particles
-        // of arithmetic per trip; lanes past the end get an out-of-domain sentinel (f = f' = 0, adds zeros)
-        const long long nvec = P.n >> 1;
-        const double outside = P.hi + (P.hi - P.lo);
-        for (long long i = gtid; i < nvec; i += 4 * stride) {
-            double2 qq[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const long long idx = i + k * stride;
-                qq[k] = idx < nvec ? ld_stream2(P.q + 2 * idx) : make_double2(outside, outside);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                LbDep<K> dd;
-                double o1, o2;
-                LbItem a{qq[k].x, 0.0, 0.0, 0.0, 0.0}, b{qq[k].y, 0.0, 0.0, 0.0, 0.0};
-                lb_particle<K, MODE>(P, mode, s_tab, dd, a, o1, o2, sums, A1, A2);
-                lb_particle<K, MODE>(P, mode, s_tab, dd, b, o1, o2, sums, A1, A2);
-            }
-        }
-    } else if (VEC == 2) {
+    if (VEC == 2) {
         const long long nvec = P.n >> 1;
         const double2 z2 = make_double2(0, 0);
         long long i = gtid;
