@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="vp", choices=["vp", "lb", "clb"])
+    ap.add_argument("--n-basis", type=int, default=16, help="x-space basis size (headline config: 16)")
+    ap.add_argument("--order", type=int, default=4, help="spline order (headline config: 4 = cubic)")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: fused peer-memory all-reduce in the field kernel (default) or NCCL")
     return ap.parse_args()
@@ -126,7 +128,9 @@ def run_reference(args):
 
 
 def main():
+    global NH, ORDER
     args = parse()
+    NH, ORDER = args.n_basis, args.order
     if args.impl == "reference":
         return run_reference(args)
 
