@@ -275,6 +275,22 @@ def main():
         e2e = {"value": ntotal * args.e2e_steps / float(t_e2e.item()), "unit": "particle-steps/s",
                "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n, "steps": args.e2e_steps,
                "api": "vpm_vp_strang_step_host (pinned 2 x N integrator state in/out per step; weights resident)"}
+        # for context: what a run!(integrator) user gets — initial state uploaded once from pinned memory, K steps
+        # on the device with (W,K,M) read back for every step, final state downloaded once
+        kk = min(args.steps, 100)
+        diag = np.zeros((kk + 1, 3))
+        barrier()
+        t0 = time.perf_counter()
+        vpm.check(lib.vpm_particles_upload_aos(d._h, cur, 2))
+        vpm.check(lib.vpm_vp_strang_steps(pot._h, d._h, DT, CHI, kk, 0, 1, diag.ctypes.data))
+        vpm.check(lib.vpm_particles_download_aos(d._h, nxt, 2))
+        barrier()
+        t_run = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_run, op=dist.ReduceOp.MAX)
+        e2e["run_api"] = {"value": ntotal * kk / float(t_run.item()), "unit": "particle-steps/s", "steps": kk,
+                          "h2d_bytes_total": 16 * n, "d2h_bytes_total": 16 * n + 24 * (kk + 1),
+                          "api": "upload_aos + vpm_vp_strang_steps(diag_mode=1) + download_aos (state resident between steps)"}
         lib.vpm_host_free(zin)
         lib.vpm_host_free(zout)
 

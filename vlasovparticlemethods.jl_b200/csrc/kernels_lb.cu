@@ -445,7 +445,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
     const size_t base = sizeof(double) * (5 * (kBlock / 32) + ((vs->ncell * TS + 1) & ~1));
     int hm = 0;
     if (dep) {
-        if (base + sizeof(double) * (size_t)vs->nbfull * kBlock > ctx->smem_optin / 2) hm = 1;
+        if (base + sizeof(double) * (size_t)vs->nbfull * kBlock > ctx->smem_optin) hm = 1;  // shared-memory CAS atomics are ~5x slower
         if (hm == 1 && base + sizeof(double) * (size_t)vs->nbfull * (kBlock / 32) > ctx->smem_optin / 2) hm = 2;
     }
     if (const char* e = getenv("VPM_TUNE_HM")) {  // test hook: force a privatisation level
@@ -476,6 +476,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
         case LB_EVAL: kern = lb_pass_kernel<K, LB_EVAL, 2, 0>; break;
     }
     VPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int occ = 0;
     VPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem));
     if (occ < 1) return fail(VPM_ERR_UNSUPPORTED, "lb pass kernel does not fit on an SM");

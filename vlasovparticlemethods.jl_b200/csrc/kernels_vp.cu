@@ -353,10 +353,11 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
 
     const bool dep = p.flags & VP_DEPOSIT;
     const size_t base = sizeof(double) * (2 * (kBlock / 32) + ((xs->nh * ES + 1) & ~1));
-    // per-thread copies while at least two CTAs fit on an SM, then per-warp, then per-CTA copies with atomics
+    // per-thread copies whenever one CTA of them fits (even 1 CTA/SM beats shared-memory CAS atomics), else per-warp,
+    // else per-CTA copies with atomics
     int hm = 0;
     if (dep) {
-        if (base + sizeof(double) * (size_t)nb * kBlock > ctx->smem_optin / 2) hm = 1;
+        if (base + sizeof(double) * (size_t)nb * kBlock > ctx->smem_optin) hm = 1;  // shared-memory CAS atomics are ~5x slower
         if (hm == 1 && base + sizeof(double) * (size_t)nb * (kBlock / 32) > ctx->smem_optin / 2) hm = 2;
     }
     if (const char* e = getenv("VPM_TUNE_HM")) {  // test hook: force a privatisation level
@@ -389,6 +390,7 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     else kern = vp_pass_kernel<K, -1, 1, 3, 0>;
 
     VPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int occ = 0;
     VPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem));
     if (occ < 1) return fail(VPM_ERR_UNSUPPORTED, "vp pass kernel does not fit on an SM");
