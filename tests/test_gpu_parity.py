@@ -293,7 +293,7 @@ def test_errors_are_reported(vpm):
 
 
 # ------------------------------------------------------------------------------------- large grids
-@pytest.mark.parametrize("hm", ["1", "2"])
+@pytest.mark.parametrize("hm", ["1", "2", "3"])
 def test_histogram_fallback_modes(vpm, oracle, hm, monkeypatch):
     """Grids too large for per-thread histogram copies fall back to per-warp / per-CTA copies with
     shared-memory atomics; VPM_TUNE_HM forces those code paths on a small grid."""

@@ -57,7 +57,7 @@ struct HistCfg {
 template <int K, int FLAGS, int HM>
 __device__ __forceinline__ void vp_particle(const VpDev& P, const int flags_rt, const double* __restrict__ s_etab,
                                             double* __restrict__ s_hist, double& x, double& v, const double w,
-                                            double& ksum, double& msum)
+                                            double& ksum, double& msum, int* dep_c = nullptr, double* dep_u = nullptr)
 {
     constexpr int ES = VpCfg<K>::ES;
     const int flags = FLAGS >= 0 ? FLAGS : flags_rt;
@@ -84,6 +84,11 @@ __device__ __forceinline__ void vp_particle(const VpDev& P, const int flags_rt, 
         int ci;
         double u, b[K];
         split_floor((x - P.lo) * P.invh, ci, u);
+        if (HM == 3) {  // tile-sorted deposit: hand the cell and local coordinate back to the caller
+            *dep_c = wrap_index(ci, P.fm);
+            *dep_u = u;
+            return;
+        }
         basis_uniform<K>(u, b);
         // bins are unwrapped: cell c feeds bins c..c+K-1 (function c-K+1+j lives in bin c+j, folded
         // mod nh by the field kernel) -> one address computation, K immediate-offset RMWs
@@ -176,6 +181,148 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
             for (int t = lane; t < HS; t += 32) s += s_hbase[b * HS + t];
             s = warp_sum(s);
             if (lane == 0) P.partials[(size_t)blockIdx.x * P.nbp + b] = s;
+        }
+    }
+    if (flags & VP_DIAG) {
+        ksum = warp_sum(ksum);
+        msum = warp_sum(msum);
+        if (lane == 0) {
+            s_red[2 * warp] = ksum;
+            s_red[2 * warp + 1] = msum;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double k = 0.0, m = 0.0;
+            for (int wi = 0; wi < kBlock / 32; wi++) {
+                k += s_red[2 * wi];
+                m += s_red[2 * wi + 1];
+            }
+            P.kin_partials[2 * blockIdx.x] = k;
+            P.kin_partials[2 * blockIdx.x + 1] = m;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Large grids (n_basis + K - 1 > ~110 bins): per-thread histogram copies no longer fit and shared-memory fp64
+// atomics are CAS loops (64 cycles per warp instruction).  This variant bins each tile of particles by cell
+// inside shared memory (counting sort on native 32-bit shared atomics), then reduces every cell's segment
+// with exactly one owning thread -- a segmented reduction over cell-binned particles with no fp64 atomics.
+// Per-cell accumulators acc[c][j] (the K basis functions of cell c) are folded into bins at the end.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTilePPT = 4;                       // particles per thread per tile
+constexpr int kTile = kBlock * kTilePPT;
+
+template <int K>
+__global__ void __launch_bounds__(kBlock, 1) vp_pass_tiled_kernel(const VpDev P)
+{
+    extern __shared__ double smem[];
+    constexpr int ES = VpCfg<K>::ES;
+    const int flags = P.flags, nh = P.nh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* s_red = smem;                                   // 2 * warps
+    double* s_etab = smem + 2 * (kBlock / 32);              // nh * ES
+    double* s_acc = s_etab + ((nh * ES + 1) & ~1);          // nh * K
+    double* s_u = s_acc + (size_t)nh * K;                   // kTile
+    double* s_w = s_u + kTile;                              // kTile
+    int* s_cnt = reinterpret_cast<int*>(s_w + kTile);       // nh
+    int* s_off = s_cnt + nh;                                // nh + 1
+    __shared__ int s_wsum[kBlock / 32];
+
+    if (flags & VP_KICK1)
+        for (int i = tid; i < nh * ES; i += kBlock) s_etab[i] = P.etab[i];
+    for (int i = tid; i < nh * K; i += kBlock) s_acc[i] = 0.0;
+    for (int i = tid; i < nh; i += kBlock) s_cnt[i] = 0;
+    __syncthreads();
+
+    double ksum = 0.0, msum = 0.0;
+    const bool need_v = flags & (VP_PRE | VP_KICK1 | VP_POST1 | VP_POST2 | VP_DIAG);
+    const bool need_w = flags & (VP_DIAG | VP_DEPOSIT);
+    const bool dep = flags & VP_DEPOSIT;
+    const int chunk = (nh + kBlock - 1) / kBlock;           // cells scanned per thread
+
+    for (long long base = (long long)blockIdx.x * kTile; base < P.n; base += (long long)gridDim.x * kTile) {
+        int pc[kTilePPT], pr[kTilePPT];
+        double pu[kTilePPT], pw[kTilePPT];
+        // A: push the particles, take a ticket in their cell
+#pragma unroll
+        for (int k = 0; k < kTilePPT; k++) {
+            const long long i = base + (long long)k * kBlock + tid;
+            pc[k] = -1;
+            if (i < P.n) {
+                double x = P.x_in[i], v = need_v ? P.v_in[i] : 0.0;
+                pw[k] = need_w ? P.w[i] : 0.0;
+                vp_particle<K, -1, 3>(P, flags, s_etab, nullptr, x, v, pw[k], ksum, msum, &pc[k], &pu[k]);
+                if (flags & VP_WRITE_X) P.x_out[i] = x;
+                if (flags & VP_WRITE_V) P.v_out[i] = v;
+                if (dep) pr[k] = atomicAdd(&s_cnt[pc[k]], 1);
+                else pc[k] = -1;
+            }
+        }
+        if (!dep) continue;
+        __syncthreads();
+        // B: exclusive scan of the counts (chunk consecutive cells per thread, warp scan, cross-warp fix-up)
+        int local = 0;
+        for (int c = tid * chunk; c < min(nh, (tid + 1) * chunk); c++) local += s_cnt[c];
+        int incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int wi = 0; wi < warp; wi++) wbase += s_wsum[wi];
+        int run = wbase + incl - local;
+        for (int c = tid * chunk; c < min(nh, (tid + 1) * chunk); c++) {
+            s_off[c] = run;
+            run += s_cnt[c];
+        }
+        if (tid == kBlock - 1) s_off[nh] = run;
+        __syncthreads();
+        // C: scatter (u, w) into cell order
+#pragma unroll
+        for (int k = 0; k < kTilePPT; k++)
+            if (pc[k] >= 0) {
+                const int pos = s_off[pc[k]] + pr[k];
+                s_u[pos] = pu[k];
+                s_w[pos] = pw[k];
+            }
+        __syncthreads();
+        // D: every cell's segment is reduced by its single owner thread; reset the counters
+        for (int c = tid; c < nh; c += kBlock) {
+            const int beg = s_off[c], end = beg + s_cnt[c];
+            s_cnt[c] = 0;
+            if (end > beg) {
+                double acc[K];
+#pragma unroll
+                for (int j = 0; j < K; j++) acc[j] = 0.0;
+                for (int q = beg; q < end; q++) {
+                    double b[K];
+                    basis_uniform<K>(s_u[q], b);
+                    const double w = s_w[q];
+#pragma unroll
+                    for (int j = 0; j < K; j++) acc[j] = fma(w, b[j], acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < K; j++) s_acc[c * K + j] += acc[j];
+            }
+        }
+        __syncthreads();
+    }
+
+    if (dep) {
+        // bin b = c + j collects function j of cell c (unwrapped bins, folded by the field kernel)
+        const int nb = nh + K - 1;
+        for (int b = tid; b < nb; b += kBlock) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                const int c = b - j;
+                if (c >= 0 && c < nh) s += s_acc[c * K + j];
+            }
+            P.partials[(size_t)blockIdx.x * P.nbp + b] = s;
         }
     }
     if (flags & VP_DIAG) {
@@ -366,6 +513,14 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     }
     const size_t copies = hm == 0 ? kBlock : (hm == 1 ? kBlock / 32 : 1);
     size_t smem = base + (dep ? sizeof(double) * (size_t)nb * copies : 0);
+    // grids beyond the per-thread copies: tile-sorted segmented reduction (no fp64 atomics)
+    const size_t smem_tiled = base + sizeof(double) * ((size_t)xs->nh * K + 2 * (size_t)kTile) + sizeof(int) * (2 * (size_t)xs->nh + 2);
+    bool tiled = dep && hm != 0 && smem_tiled <= ctx->smem_optin;
+    if (const char* e = getenv("VPM_TUNE_HM")) {
+        if (atoi(e) == 3 && dep && smem_tiled <= ctx->smem_optin) tiled = true;
+        else if (atoi(e) != 3 && atoi(e) > 0) tiled = false;
+    }
+    if (tiled) smem = smem_tiled;
     if (smem > ctx->smem_optin)
         return fail(VPM_ERR_UNSUPPORTED, "x-space too large: the field table and one histogram copy must fit in shared memory");
 
@@ -380,7 +535,8 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
         return (v >= 2 && v <= 4) ? v : 3;
     }();
     void (*kern)(const VpDev) = nullptr;
-    if (hm == 1) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 1> : vp_pass_kernel<K, -1, 1, 3, 1>;
+    if (tiled) kern = vp_pass_tiled_kernel<K>;
+    else if (hm == 1) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 1> : vp_pass_kernel<K, -1, 1, 3, 1>;
     else if (hm == 2) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 2> : vp_pass_kernel<K, -1, 1, 3, 2>;
     else if (vec && p.flags == kMainFlags) {
         kern = tune_minb == 2 ? vp_pass_kernel<K, kMainFlags, 2, 2, 0>
@@ -393,7 +549,7 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     int occ = 0;
     VPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem));
     if (occ < 1) return fail(VPM_ERR_UNSUPPORTED, "vp pass kernel does not fit on an SM");
-    long long want = (p.n / (vec ? 2 : 1) + kBlock - 1) / kBlock;
+    long long want = tiled ? (p.n + kTile - 1) / kTile : (p.n / (vec ? 2 : 1) + kBlock - 1) / kBlock;
     if (want < 1) want = 1;
     long long grid = (long long)ctx->sm_count * occ;
     if (grid > want) grid = want;
