@@ -210,12 +210,10 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
 // with exactly one owning thread -- a segmented reduction over cell-binned particles with no fp64 atomics.
 // Per-cell accumulators acc[c][j] (the K basis functions of cell c) are folded into bins at the end.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTilePPT = 4;                       // particles per thread per tile
-constexpr int kTile = kBlock * kTilePPT;
-
-template <int K>
-__global__ void __launch_bounds__(kBlock, 1) vp_pass_tiled_kernel(const VpDev P)
+template <int K, int kTilePPT, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) vp_pass_tiled_kernel(const VpDev P)
 {
+    constexpr int kTile = kBlock * kTilePPT;
     extern __shared__ double smem[];
     constexpr int ES = VpCfg<K>::ES;
     const int flags = P.flags, nh = P.nh;
@@ -514,6 +512,11 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     const size_t copies = hm == 0 ? kBlock : (hm == 1 ? kBlock / 32 : 1);
     size_t smem = base + (dep ? sizeof(double) * (size_t)nb * copies : 0);
     // grids beyond the per-thread copies: tile-sorted segmented reduction (no fp64 atomics)
+    static const int tune_tile = [] {
+        const char* e = getenv("VPM_TUNE_TILE");
+        return e ? atoi(e) : 0;
+    }();
+    const int kTile = kBlock * (tune_tile == 1 ? 8 : 4);
     const size_t smem_tiled = base + sizeof(double) * ((size_t)xs->nh * K + 2 * (size_t)kTile) + sizeof(int) * (2 * (size_t)xs->nh + 2);
     bool tiled = dep && hm != 0 && smem_tiled <= ctx->smem_optin;
     if (const char* e = getenv("VPM_TUNE_HM")) {
@@ -535,7 +538,7 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
         return (v >= 2 && v <= 4) ? v : 3;
     }();
     void (*kern)(const VpDev) = nullptr;
-    if (tiled) kern = vp_pass_tiled_kernel<K>;
+    if (tiled) kern = tune_tile == 1 ? vp_pass_tiled_kernel<K, 8, 2> : (tune_tile == 2 ? vp_pass_tiled_kernel<K, 4, 2> : vp_pass_tiled_kernel<K, 4, 3>);
     else if (hm == 1) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 1> : vp_pass_kernel<K, -1, 1, 3, 1>;
     else if (hm == 2) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 2> : vp_pass_kernel<K, -1, 1, 3, 2>;
     else if (vec && p.flags == kMainFlags) {
