@@ -53,9 +53,7 @@ __device__ __forceinline__ bool v_locate(const LbDev& P, double q, int& ci, doub
 
 template <int HM>
 struct HistCfg {
-    // 0: one copy per thread; 4: one copy per lane pair (the even lane applies both lanes' updates, which halves
-    // the shared-memory footprint and doubles the resident warps); 1: per warp, 2: per CTA (CAS atomics)
-    static constexpr int copies = HM == 0 ? kBlock : (HM == 4 ? kBlock / 2 : (HM == 1 ? kBlock / 32 : 1));
+    static constexpr int copies = HM == 0 ? kBlock : (HM == 1 ? kBlock / 32 : 1);
 };
 
 // Deposit in two halves so that the pair loop can finish the arithmetic of both particles before the
@@ -96,29 +94,8 @@ __device__ __forceinline__ void v_deposit_commit(double* __restrict__ s_hist, co
     double* hcell = s_hist + d.ci * HS;
 #pragma unroll
     for (int j = 0; j < K; j++) {
-        if (HM == 0 || HM == 4) hcell[j * HS] += d.wb[j];
+        if (HM == 0) hcell[j * HS] += d.wb[j];
         else atomicAdd(hcell + j * HS, d.wb[j]);
-    }
-}
-
-// Commit one particle per lane.  HM == 4: lanes 2i and 2i+1 share a histogram copy; the odd lane hands its
-// update to the even lane by shuffle and the even lane applies both (plain read-modify-writes, no atomics).
-// Must be called by all 32 lanes of the warp.
-template <int K, int HM>
-__device__ __forceinline__ void v_deposit_commit_warp(double* __restrict__ s_hist, const LbDep<K>& d, int lane)
-{
-    if (HM != 4) {
-        v_deposit_commit<K, HM>(s_hist, d);
-        return;
-    }
-    LbDep<K> p;
-    p.ci = __shfl_xor_sync(0xffffffffu, d.ci, 1);
-    p.on = __shfl_xor_sync(0xffffffffu, (int)d.on, 1) != 0;
-#pragma unroll
-    for (int j = 0; j < K; j++) p.wb[j] = __shfl_xor_sync(0xffffffffu, d.wb[j], 1);
-    if ((lane & 1) == 0) {
-        v_deposit_commit<K, HM>(s_hist, d);
-        v_deposit_commit<K, HM>(s_hist, p);
     }
 }
 
@@ -220,8 +197,7 @@ struct LbIo {
 };
 
 template <int K, int MODE, int VEC, int HM>
-__global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT) ? 4 : (HM == 4 ? 3 : 2))
-lb_pass_kernel(const LbDev P)
+__global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT) ? 4 : 2) lb_pass_kernel(const LbDev P)
 {
     extern __shared__ double smem[];
     constexpr int TS = 2 * K - 1;
@@ -235,7 +211,7 @@ lb_pass_kernel(const LbDev P)
     double* s_tab = smem + 5 * (kBlock / 32);    // ncell * TS
     constexpr int HS = HistCfg<HM>::copies;
     double* s_hbase = s_tab + ((P.ncell * TS + 1) & ~1);
-    double* s_hist = s_hbase + (HM == 0 ? tid : (HM == 4 ? (tid >> 1) : (HM == 1 ? (tid >> 5) : 0)));
+    double* s_hist = s_hbase + (HM == 0 ? tid : (HM == 1 ? (tid >> 5) : 0));
 
     if (ev)
         for (int i = tid; i < P.ncell * TS; i += kBlock) s_tab[i] = P.ftab[i];
@@ -272,8 +248,7 @@ lb_pass_kernel(const LbDev P)
             if (rd_acc) aa = ld_stream2(P.acc + 2 * i);
             if (rd_d) da = ld_stream2(P.d + 2 * i);
         }
-        // HM == 4 shuffles inside the commit: keep the warp together until its last lane is done
-        while (HM == 4 ? __any_sync(0xffffffffu, have) : have) {
+        while (have) {
             const long long inext = i + stride;
             const bool hn = inext < nvec;
             double2 qn = z2, wn = z2, vn = z2, an = z2, dn = z2;
@@ -287,23 +262,17 @@ lb_pass_kernel(const LbDev P)
             LbItem i0{qa.x, wa.x, va.x, aa.x, da.x}, i1{qa.y, wa.y, va.y, aa.y, da.y};
             double2 o1 = z2, o2 = z2;
             LbDep<K> d0, d1;
-            d0.on = d1.on = false;
-            d0.ci = d1.ci = 0;
-            if (HM != 4 || have) {
-                lb_particle<K, MODE>(P, mode, s_tab, d0, i0, o1.x, o2.x, sums, A1, A2);
-                lb_particle<K, MODE>(P, mode, s_tab, d1, i1, o1.y, o2.y, sums, A1, A2);
-            }
+            lb_particle<K, MODE>(P, mode, s_tab, d0, i0, o1.x, o2.x, sums, A1, A2);
+            lb_particle<K, MODE>(P, mode, s_tab, d1, i1, o1.y, o2.y, sums, A1, A2);
             if (dep) {
-                v_deposit_commit_warp<K, HM>(s_hist, d0, lane);
-                v_deposit_commit_warp<K, HM>(s_hist, d1, lane);
+                v_deposit_commit<K, HM>(s_hist, d0);
+                v_deposit_commit<K, HM>(s_hist, d1);
             }
-            if (HM != 4 || have) {
-                if (wr_q) st_stream2(P.qout + 2 * i, make_double2(i0.q, i1.q));
-                if (wr_acc) st_stream2(P.acc + 2 * i, make_double2(i0.acc, i1.acc));
-                if (wr_d) st_stream2(P.d + 2 * i, make_double2(i0.d, i1.d));
-                if (wr_o1) st_stream2(P.out + 2 * i, o1);
-                if (wr_o2) st_stream2(P.out2 + 2 * i, o2);
-            }
+            if (wr_q) st_stream2(P.qout + 2 * i, make_double2(i0.q, i1.q));
+            if (wr_acc) st_stream2(P.acc + 2 * i, make_double2(i0.acc, i1.acc));
+            if (wr_d) st_stream2(P.d + 2 * i, make_double2(i0.d, i1.d));
+            if (wr_o1) st_stream2(P.out + 2 * i, o1);
+            if (wr_o2) st_stream2(P.out2 + 2 * i, o2);
             qa = qn; wa = wn; va = vn; aa = an; da = dn;
             i = inext;
             have = hn;
@@ -312,23 +281,17 @@ lb_pass_kernel(const LbDev P)
     // scalar path: whole array when VEC == 1, odd tail otherwise
     {
         long long i0 = VEC == 2 ? ((P.n & ~1LL) + gtid) : gtid;
-        for (long long i = i0; HM == 4 ? __any_sync(0xffffffffu, i < P.n) : (i < P.n); i += stride) {
-            const bool act = i < P.n;
-            LbItem it{0.0, 0.0, 0.0, 0.0, 0.0};
-            if (act) it = LbItem{P.q[i], rd_w ? P.w[i] : 0.0, rd_v0 ? P.v0[i] : 0.0, rd_acc ? P.acc[i] : 0.0, rd_d ? P.d[i] : 0.0};
+        for (long long i = i0; i < P.n; i += stride) {
+            LbItem it{P.q[i], rd_w ? P.w[i] : 0.0, rd_v0 ? P.v0[i] : 0.0, rd_acc ? P.acc[i] : 0.0, rd_d ? P.d[i] : 0.0};
             double o1 = 0.0, o2 = 0.0;
             LbDep<K> d0;
-            d0.on = false;
-            d0.ci = 0;
-            if (act) lb_particle<K, MODE>(P, mode, s_tab, d0, it, o1, o2, sums, A1, A2);
-            if (dep) v_deposit_commit_warp<K, HM>(s_hist, d0, lane);
-            if (act) {
-                if (wr_q) P.qout[i] = it.q;
-                if (wr_acc) P.acc[i] = it.acc;
-                if (wr_d) P.d[i] = it.d;
-                if (wr_o1) P.out[i] = o1;
-                if (wr_o2) P.out2[i] = o2;
-            }
+            lb_particle<K, MODE>(P, mode, s_tab, d0, it, o1, o2, sums, A1, A2);
+            if (dep) v_deposit_commit<K, HM>(s_hist, d0);
+            if (wr_q) P.qout[i] = it.q;
+            if (wr_acc) P.acc[i] = it.acc;
+            if (wr_d) P.d[i] = it.d;
+            if (wr_o1) P.out[i] = o1;
+            if (wr_o2) P.out2[i] = o2;
         }
     }
 
@@ -466,12 +429,6 @@ __global__ void __launch_bounds__(kFieldThreads) lb_field_kernel(const LbFieldDe
     }
 }
 
-static bool vec_ok(const LbPass& p)
-{
-    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    return al(p.q) && al(p.w) && al(p.v0) && al(p.acc) && al(p.d) && al(p.qout) && al(p.out) && al(p.out2);
-}
-
 template <int K>
 int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* grid_out)
 {
@@ -495,30 +452,18 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
         const int f = atoi(e);
         if (f > hm && f <= 2 && dep) hm = f;
     }
-    // pair-shared copies (HM 4) for the stage / deposit passes: half the shared memory, one more resident CTA
-    static const int tune_pair = [] {
-        const char* e = getenv("VPM_TUNE_LBPAIR");
-        return e ? atoi(e) : 1;
-    }();
-    if (hm == 0 && dep && vec_ok(p) && tune_pair) hm = 4;
-    const size_t copies = hm == 0 ? kBlock : (hm == 4 ? kBlock / 2 : (hm == 1 ? kBlock / 32 : 1));
+    const size_t copies = hm == 0 ? kBlock : (hm == 1 ? kBlock / 32 : 1);
     const size_t smem = base + (dep ? sizeof(double) * (size_t)vs->nbfull * copies : 0);
     if (smem > ctx->smem_optin)
         return fail(VPM_ERR_UNSUPPORTED, "v-space too large: the f/f' table and one histogram copy must fit in shared memory");
 
-    const bool vec = vec_ok(p);
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const bool vec = al(p.q) && al(p.w) && al(p.v0) && al(p.acc) && al(p.d) && al(p.qout) && al(p.out) && al(p.out2);
 
     void (*kern)(const LbDev) = nullptr;
     if (p.mode < LB_DEPOSIT_ONLY || p.mode > LB_EVAL) return fail(VPM_ERR_INVALID, "bad LB pass mode");
     if (hm == 1) kern = vec ? lb_pass_kernel<K, -1, 2, 1> : lb_pass_kernel<K, -1, 1, 1>;
     else if (hm == 2) kern = vec ? lb_pass_kernel<K, -1, 2, 2> : lb_pass_kernel<K, -1, 1, 2>;
-    else if (hm == 4) switch (p.mode) {
-        case LB_DEPOSIT_ONLY: kern = lb_pass_kernel<K, LB_DEPOSIT_ONLY, 2, 4>; break;
-        case LB_STAGE1: kern = lb_pass_kernel<K, LB_STAGE1, 2, 4>; break;
-        case LB_STAGE2: kern = lb_pass_kernel<K, LB_STAGE2, 2, 4>; break;
-        case LB_STAGE3: kern = lb_pass_kernel<K, LB_STAGE3, 2, 4>; break;
-        default: kern = lb_pass_kernel<K, LB_STAGE4, 2, 4>; break;
-    }
     else if (!vec) kern = lb_pass_kernel<K, -1, 1, 0>;
     else switch (p.mode) {
         case LB_DEPOSIT_ONLY: kern = lb_pass_kernel<K, LB_DEPOSIT_ONLY, 2, 0>; break;
