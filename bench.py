@@ -253,6 +253,26 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.workload)
 
+    # ---- context only (NOT the headline): uniform-weight fast path, 32 B per particle-step -------------------
+    # every reference sampler produces equal weights (w = L/N), so the steppers can skip the w[] stream when the
+    # caller declares it; `value` above always streams w[] (40 B), as the reference's layout does.
+    uniform = None
+    if args.workload == "vp" and world == 1:
+        d.set_uniform_weight(L / ntotal)
+        run_steps(3)
+        barrier()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ku = min(args.steps, 50)
+        u0.record(stream)
+        run_steps(ku)
+        u1.record(stream)
+        barrier()
+        ums = u0.elapsed_time(u1) / ku
+        uniform = {"value": n / (ums * 1e-3), "unit": "particle-steps/s", "ms_per_step": ums,
+                   "bytes_per_particle_step": 32, "GBps": 32 * n / (ums * 1e-3) / 1e9,
+                   "api": "vpm_particles_set_uniform_weight + vpm_vp_strang_steps"}
+        vpm.initialize_(d, vpm.BumpOnTail(kappa=KAPPA), offset=rank * n, ntotal=ntotal)   # back to per-particle weights
+
     # ---- e2e: the host-array drop-in step (z = 2 x N host matrix in, out), PCIe copies inside the timing ----
     e2e = None
     if args.workload == "vp" and not args.no_e2e:
@@ -322,6 +342,7 @@ def main():
                          "launches_timed": pass_cnt, "field_kernel_share": field_ms / max(pass_ms + field_ms, 1e-30),
                          "frac_of_8TBs_nominal": achieved / 8000.0},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "uniform_weight_variant": uniform,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

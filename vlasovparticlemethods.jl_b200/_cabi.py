@@ -42,6 +42,7 @@ SIGNATURES = {
     "vpm_particles_download_aos": (_i32, [_vp, _vp, _i32]),
     "vpm_particles_upload_soa": (_i32, [_vp, _vp, _vp, _vp]),
     "vpm_particles_download_soa": (_i32, [_vp, _vp, _vp, _vp]),
+    "vpm_particles_set_uniform_weight": (_i32, [_vp, _f64]),
     "vpm_sample_bump_on_tail": (_i32, [_vp, _i64, _i64, _u64, _f64, _f64, _f64, _f64, _f64]),
     "vpm_sample_maxwellian": (_i32, [_vp, _i64, _i64, _u64, _f64, _f64, _f64, _i32, _f64]),
     "vpm_xspace_create": (_i32, [_vp, _f64, _f64, _i32, _i32, C.POINTER(_vp)]),

@@ -258,6 +258,11 @@ class ParticleDistribution(DistributionFunction):
         check(_lib().vpm_particles_download_soa(self._h, _hp(x), _hp(v), _hp(w)))
         return x, v, w
 
+    def set_uniform_weight(self, w):
+        """all particles carry weight w (as every reference sampler produces): the steppers skip the w stream"""
+        check(_lib().vpm_particles_set_uniform_weight(self._h, float(w)))
+        return self
+
     def upload_aos(self, z):
         """z: (ld, N) Julia column-major matrix == C-order (N, ld) array; rows x, v[, w]."""
         z = np.asarray(z, dtype=np.float64)

@@ -339,6 +339,7 @@ int vpm_particles_upload_aos(vpm_particles* p, const double* z, int ld)
         VPM_CUDA(cudaMemcpyAsync(ctx->staging, z + o * ld, sizeof(double) * m * ld, cudaMemcpyHostToDevice, ctx->stream));
         VPM_CHECK(launch_aos_to_soa(ctx, ctx->staging, ld, m, p->x + o, p->v + o, ld == 3 ? p->w + o : nullptr));
     }
+    if (ld == 3) p->uw = false;
     VPM_CUDA(cudaStreamSynchronize(ctx->stream));
     return VPM_OK;
 }
@@ -367,7 +368,10 @@ int vpm_particles_upload_soa(vpm_particles* p, const double* x, const double* v,
     const size_t bytes = sizeof(double) * (size_t)p->n;
     if (x) VPM_CUDA(cudaMemcpyAsync(p->x, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (v) VPM_CUDA(cudaMemcpyAsync(p->v, v, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    if (w) VPM_CUDA(cudaMemcpyAsync(p->w, w, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (w) {
+        VPM_CUDA(cudaMemcpyAsync(p->w, w, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        p->uw = false;
+    }
     VPM_CUDA(cudaStreamSynchronize(ctx->stream));
     return VPM_OK;
 }
@@ -385,11 +389,22 @@ int vpm_particles_download_soa(vpm_particles* p, double* x, double* v, double* w
     return VPM_OK;
 }
 
+int vpm_particles_set_uniform_weight(vpm_particles* p, double w)
+{
+    VPM_REQUIRE(p && std::isfinite(w), "vpm_particles_set_uniform_weight: bad arguments");
+    VPM_CUDA(cudaSetDevice(p->ctx->device));
+    VPM_CHECK(launch_fill(p->ctx, p->w, p->n, w));
+    p->uw = true;
+    p->wu = w;
+    return VPM_OK;
+}
+
 int vpm_sample_bump_on_tail(vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed, double eps, double kappa,
                             double alpha, double sigma, double v0)
 {
     VPM_REQUIRE(p && ntotal > 0 && kappa > 0, "vpm_sample_bump_on_tail: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
+    p->uw = false;
     return launch_sample_bump_on_tail(p->ctx, p, offset, ntotal, seed, eps, kappa, alpha, sigma, v0);
 }
 
@@ -398,6 +413,7 @@ int vpm_sample_maxwellian(vpm_particles* p, int64_t offset, int64_t ntotal, uint
 {
     VPM_REQUIRE(p && ntotal > 0, "vpm_sample_maxwellian: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
+    p->uw = false;
     return launch_sample_maxwellian(p->ctx, p, offset, ntotal, seed, xlo, xhi, shift, doubled, wnum);
 }
 
@@ -602,7 +618,8 @@ int vpm_xspace_get(vpm_xspace* xs, double* rhs_host, double* phi_host)
 
 // Strang stepping on SoA arrays (x, v evolve; w and the frozen-field deposit positions are inputs)
 static int vp_steps(vpm_xspace* xs, double* x, double* v, const double* w, int64_t n, const double* xdep,
-                    const double* wdep, int64_t ndep, double dt, double chi, int nsteps, int mode, int diag_mode)
+                    const double* wdep, int64_t ndep, double dt, double chi, int nsteps, int mode, int diag_mode,
+                    bool uw = false, double wu = 0.0)
 {
     vpm_ctx* ctx = xs->ctx;
     const double Dt = dt * chi, escale = -1.0 / (chi * chi), wscale = 1.0 / (chi * chi);
@@ -612,11 +629,13 @@ static int vp_steps(vpm_xspace* xs, double* x, double* v, const double* w, int64
 
     VpPass ps{};
     ps.x_in = x; ps.v_in = v; ps.w = w; ps.x_out = x; ps.v_out = v; ps.n = n;
+    ps.use_uw = uw; ps.w_uniform = wu;
 
     if (mode == VPM_VP_FROZEN) {
         // field of model.distribution, fixed for the whole run
         VpPass pd{};
         pd.x_in = xdep; pd.w = wdep; pd.n = ndep; pd.flags = VP_DEPOSIT;
+        pd.use_uw = uw; pd.w_uniform = wu;
         VPM_CHECK(launch_vp_pass(ctx, xs, pd, &grid));
         VPM_CHECK(launch_vp_field(ctx, xs, ALL, grid, 1, 0, escale, wscale, diag_mode ? 0 : -1, -1));
         if (diag_mode) {
@@ -687,7 +706,7 @@ int vpm_vp_strang_steps_async(vpm_xspace* xs, vpm_particles* p, double dt, doubl
         // the deposit positions are the particles' positions at call time; the pass that computes the field
         // runs before any push on the same stream, so no copy is needed
     }
-    return vp_steps(xs, p->x, p->v, p->w, p->n, xdep, p->w, p->n, dt, chi, nsteps, mode, diag_mode);
+    return vp_steps(xs, p->x, p->v, p->w, p->n, xdep, p->w, p->n, dt, chi, nsteps, mode, diag_mode, p->uw, p->wu);
 }
 
 int vpm_vp_strang_steps(vpm_xspace* xs, vpm_particles* p, double dt, double chi, int nsteps, int mode, int diag_mode,
@@ -721,7 +740,7 @@ int vpm_vp_strang_step_host(vpm_xspace* xs, vpm_particles* p, const double* z_in
     double* v = x + npad;
     VPM_CUDA(cudaMemcpyAsync(z, z_in, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
     VPM_CHECK(launch_aos_to_soa(ctx, z, 2, n, x, v, nullptr));
-    VPM_CHECK(vp_steps(xs, x, v, p->w, n, p->x, p->w, n, dt, chi, 1, mode, 0));
+    VPM_CHECK(vp_steps(xs, x, v, p->w, n, p->x, p->w, n, dt, chi, 1, mode, 0, p->uw, p->wu));
     VPM_CHECK(launch_soa_to_aos(ctx, x, v, nullptr, 2, n, z));
     VPM_CUDA(cudaMemcpyAsync(z_out, z, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
     VPM_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -918,6 +937,7 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
     int grid = 0;
     LbPass ps{};
     ps.n = p->n; ps.w = p->w; ps.nu = nu; ps.dt = dt; ps.conservative = conservative;
+    ps.use_uw = p->uw; ps.w_uniform = p->wu;
     ps.acc = p->acc; ps.d = p->d;
     {   // projection of the initial state + step-0 diagnostics
         LbPass p0 = ps;

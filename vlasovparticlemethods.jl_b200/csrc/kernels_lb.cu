@@ -33,6 +33,8 @@ struct LbDev {
     const double* pieces;
     double* partials;
     double* red_partials;
+    double w_uniform;
+    int use_uw;
 };
 
 constexpr int kRedW = 8;  // doubles per CTA row of scalar partial sums
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
     const long long gtid = (long long)blockIdx.x * kBlock + tid;
 
     // runtime-mode variants decide loads/stores from the mode; compile-time modes fold these
-    const bool rd_w = Io::rd_w && dep;
+    const bool rd_w = Io::rd_w && dep && !P.use_uw;
     const bool rd_v0 = Io::rd_v0 && (mode >= LB_STAGE2 && mode <= LB_STAGE4);
     const bool rd_acc = rd_v0;
     const bool rd_d = Io::rd_d && mode == LB_STAGE3;
@@ -240,7 +242,8 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
         const double2 z2 = make_double2(0, 0);
         long long i = gtid;
         bool have = i < nvec;
-        double2 qa = z2, wa = z2, va = z2, aa = z2, da = z2;
+        const double2 wdef = make_double2(P.w_uniform, P.w_uniform);
+        double2 qa = z2, wa = wdef, va = z2, aa = z2, da = z2;
         if (have) {
             qa = ld_stream2(P.q + 2 * i);
             if (rd_w) wa = ld_stream2(P.w + 2 * i);
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
         while (have) {
             const long long inext = i + stride;
             const bool hn = inext < nvec;
-            double2 qn = z2, wn = z2, vn = z2, an = z2, dn = z2;
+            double2 qn = z2, wn = wdef, vn = z2, an = z2, dn = z2;
             if (hn) {
                 qn = ld_stream2(P.q + 2 * inext);
                 if (rd_w) wn = ld_stream2(P.w + 2 * inext);
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
     {
         long long i0 = VEC == 2 ? ((P.n & ~1LL) + gtid) : gtid;
         for (long long i = i0; i < P.n; i += stride) {
-            LbItem it{P.q[i], rd_w ? P.w[i] : 0.0, rd_v0 ? P.v0[i] : 0.0, rd_acc ? P.acc[i] : 0.0, rd_d ? P.d[i] : 0.0};
+            LbItem it{P.q[i], rd_w ? P.w[i] : P.w_uniform, rd_v0 ? P.v0[i] : 0.0, rd_acc ? P.acc[i] : 0.0, rd_d ? P.d[i] : 0.0};
             double o1 = 0.0, o2 = 0.0;
             LbDep<K> d0;
             lb_particle<K, MODE>(P, mode, s_tab, d0, it, o1, o2, sums, A1, A2);
@@ -439,6 +442,8 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
     P.n = p.n; P.nu = p.nu; P.dt = p.dt; P.conservative = p.conservative; P.diag = p.diag;
     P.lo = vs->lo; P.hi = vs->hi; P.invh = vs->invh; P.ncell = vs->ncell; P.nbfull = vs->nbfull;
     P.ftab = vs->ftab; P.scal = vs->scal; P.pieces = vs->pieces;
+    P.use_uw = p.use_uw;
+    P.w_uniform = p.use_uw ? p.w_uniform : 0.0;
 
     const bool stage = p.mode >= LB_STAGE1 && p.mode <= LB_STAGE4;
     const bool dep = p.mode == LB_DEPOSIT_ONLY || stage;

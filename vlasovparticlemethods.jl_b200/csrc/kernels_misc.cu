@@ -119,6 +119,12 @@ __global__ void sample_maxwellian_kernel(long long n, long long offset, long lon
     }
 }
 
+__global__ void fill_kernel(double* __restrict__ a, long long n, double value)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] = value;
+}
+
 unsigned grid_for(vpm_ctx* ctx, long long n, int block)
 {
     long long g = (n + block - 1) / block;
@@ -129,6 +135,14 @@ unsigned grid_for(vpm_ctx* ctx, long long n, int block)
 }
 
 }  // namespace
+
+int launch_fill(vpm_ctx* ctx, double* a, int64_t n, double value)
+{
+    fill_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(a, n, value);
+    ctx->launches++;
+    VPM_CUDA(cudaGetLastError());
+    return VPM_OK;
+}
 
 int launch_aos_to_soa(vpm_ctx* ctx, const double* z, int ld, int64_t n, double* x, double* v, double* w)
 {

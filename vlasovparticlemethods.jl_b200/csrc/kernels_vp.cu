@@ -37,6 +37,8 @@ struct VpDev {
     double* partials;
     double* kin_partials;
     int nbp;
+    double w_uniform;
+    int use_uw;
 };
 
 template <int K>
@@ -125,14 +127,15 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
 
     double ksum = 0.0, msum = 0.0;
     const bool need_v = flags & (VP_PRE | VP_KICK1 | VP_POST1 | VP_POST2 | VP_DIAG);
-    const bool need_w = flags & (VP_DIAG | VP_DEPOSIT);
+    const bool need_w = (flags & (VP_DIAG | VP_DEPOSIT)) && !P.use_uw;
     const long long stride = (long long)gridDim.x * kBlock;
     const long long gtid = (long long)blockIdx.x * kBlock + tid;
 
     if (VEC == 2) {
         const long long nvec = P.n >> 1;
         long long i = gtid;
-        double2 xa = make_double2(0, 0), va = xa, wa = xa;
+        const double2 wdef = make_double2(P.w_uniform, P.w_uniform);
+        double2 xa = make_double2(0, 0), va = xa, wa = wdef;
         bool have = i < nvec;
         if (have) {
             xa = ld_stream2(P.x_in + 2 * i);
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
         while (have) {
             const long long inext = i + stride;
             const bool hn = inext < nvec;
-            double2 xn = make_double2(0, 0), vn = xn, wn = xn;
+            double2 xn = make_double2(0, 0), vn = xn, wn = wdef;
             if (hn) {
                 xn = ld_stream2(P.x_in + 2 * inext);
                 if (need_v) vn = ld_stream2(P.v_in + 2 * inext);
@@ -158,14 +161,14 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
         }
         if ((P.n & 1) && gtid == 0) {  // odd tail
             const long long t = P.n - 1;
-            double x = P.x_in[t], v = need_v ? P.v_in[t] : 0.0, w = need_w ? P.w[t] : 0.0;
+            double x = P.x_in[t], v = need_v ? P.v_in[t] : 0.0, w = need_w ? P.w[t] : P.w_uniform;
             vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, x, v, w, ksum, msum);
             if (flags & VP_WRITE_X) P.x_out[t] = x;
             if (flags & VP_WRITE_V) P.v_out[t] = v;
         }
     } else {
         for (long long i = gtid; i < P.n; i += stride) {
-            double x = P.x_in[i], v = need_v ? P.v_in[i] : 0.0, w = need_w ? P.w[i] : 0.0;
+            double x = P.x_in[i], v = need_v ? P.v_in[i] : 0.0, w = need_w ? P.w[i] : P.w_uniform;
             vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, x, v, w, ksum, msum);
             if (flags & VP_WRITE_X) P.x_out[i] = x;
             if (flags & VP_WRITE_V) P.v_out[i] = v;
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_tiled_kernel(const VpDev
 
     double ksum = 0.0, msum = 0.0;
     const bool need_v = flags & (VP_PRE | VP_KICK1 | VP_POST1 | VP_POST2 | VP_DIAG);
-    const bool need_w = flags & (VP_DIAG | VP_DEPOSIT);
+    const bool need_w = (flags & (VP_DIAG | VP_DEPOSIT)) && !P.use_uw;
     const bool dep = flags & VP_DEPOSIT;
     const int chunk = (nh + kBlock - 1) / kBlock;           // cells scanned per thread
 
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_tiled_kernel(const VpDev
             pc[k] = -1;
             if (i < P.n) {
                 double x = P.x_in[i], v = need_v ? P.v_in[i] : 0.0;
-                pw[k] = need_w ? P.w[i] : 0.0;
+                pw[k] = need_w ? P.w[i] : P.w_uniform;
                 vp_particle<K, -1, 3>(P, flags, s_etab, nullptr, x, v, pw[k], ksum, msum, &pc[k], &pu[k]);
                 if (flags & VP_WRITE_X) P.x_out[i] = x;
                 if (flags & VP_WRITE_V) P.v_out[i] = v;
@@ -493,6 +496,8 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     P.tau_pre = p.tau_pre; P.tau_kick = p.tau_kick; P.tau_post1 = p.tau_post1; P.tau_post2 = p.tau_post2;
     P.lo = xs->lo; P.invh = xs->invh; P.nh = xs->nh; P.fm = xs->fm;
     P.etab = xs->etab;
+    P.use_uw = p.use_uw;
+    P.w_uniform = p.use_uw ? p.w_uniform : 0.0;
     const int nb = xs->nh + K - 1;
     P.nbp = nb;
 

@@ -76,6 +76,9 @@ struct vpm_particles {
     double *x = nullptr, *v = nullptr, *w = nullptr;
     // RK438 scratch (allocated on first LB use)
     double *q = nullptr, *acc = nullptr, *d = nullptr;
+    // uniform-weight fast path (vpm_particles_set_uniform_weight): the steppers skip the w[] stream
+    bool uw = false;
+    double wu = 0.0;
 };
 
 struct vpm_xspace {
@@ -142,6 +145,8 @@ struct VpPass {
     int64_t n;
     int flags;
     double tau_pre, tau_kick, tau_post1, tau_post2;
+    double w_uniform;   // use_uw: every particle has this weight and w[] is not read (32 B/particle-step)
+    int use_uw;
 };
 
 // returns the number of CTAs launched (= number of partial rows) via *grid_out
@@ -175,6 +180,8 @@ struct LbPass {
     double nu, dt;
     int conservative;
     int diag;   // stage 4: accumulate sum v, sum v^2
+    double w_uniform;
+    int use_uw;
 };
 
 int launch_lb_pass(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* grid_out);
@@ -185,6 +192,7 @@ enum LbFieldPhase : int { LBF_REDUCE = 1, LBF_SOLVE = 2, LBF_TABLE = 4, LBF_COEF
 int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nred, int diag_slot);
 
 // ---------------- misc kernels (kernels_misc.cu) ----------------
+int launch_fill(vpm_ctx* ctx, double* a, int64_t n, double value);
 int launch_aos_to_soa(vpm_ctx* ctx, const double* z, int ld, int64_t n, double* x, double* v, double* w);
 int launch_soa_to_aos(vpm_ctx* ctx, const double* x, const double* v, const double* w, int ld, int64_t n, double* z);
 int launch_sample_bump_on_tail(vpm_ctx* ctx, vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed,
