@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <new>
 
 #include "vpm_internal.h"
@@ -33,6 +34,27 @@ static int grow(double** buf, size_t* cap, size_t doubles, cudaStream_t stream)
     cudaError_t e = cudaMalloc((void**)buf, want * sizeof(double));
     if (e != cudaSuccess) return fail(VPM_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     *cap = want;
+    return VPM_OK;
+}
+
+int kernel_occupancy(vpm_ctx* ctx, const void* kern, int block, size_t smem, int* occ)
+{
+    struct Key {
+        int dev;
+        const void* k;
+        size_t smem;
+        bool operator<(const Key& o) const { return dev != o.dev ? dev < o.dev : (k != o.k ? k < o.k : smem < o.smem); }
+    };
+    static std::map<Key, int> cache;
+    const Key key{ctx->device, kern, smem};
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *occ = it->second;
+        return VPM_OK;
+    }
+    VPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, block, smem));
+    cache[key] = *occ;
     return VPM_OK;
 }
 

@@ -480,9 +480,11 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
         case LB_MOMENTS: kern = lb_pass_kernel<K, LB_MOMENTS, 2, 0>; break;
         case LB_EVAL: kern = lb_pass_kernel<K, LB_EVAL, 2, 0>; break;
     }
-    VPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    VPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem));
+    {
+        const int rc_occ = kernel_occupancy(ctx, (const void*)kern, kBlock, smem, &occ);
+        if (rc_occ) return rc_occ;
+    }
     if (occ < 1) return fail(VPM_ERR_UNSUPPORTED, "lb pass kernel does not fit on an SM");
     long long want = (p.n / (vec ? 2 : 1) + kBlock - 1) / kBlock;
     if (want < 1) want = 1;

@@ -553,9 +553,11 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     else if (vec) kern = vp_pass_kernel<K, -1, 2, 3, 0>;
     else kern = vp_pass_kernel<K, -1, 1, 3, 0>;
 
-    VPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    VPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem));
+    {
+        const int rc_occ = kernel_occupancy(ctx, (const void*)kern, kBlock, smem, &occ);
+        if (rc_occ) return rc_occ;
+    }
     if (occ < 1) return fail(VPM_ERR_UNSUPPORTED, "vp pass kernel does not fit on an SM");
     long long want = tiled ? (p.n + kTile - 1) / kTile : (p.n / (vec ? 2 : 1) + kBlock - 1) / kBlock;
     if (want < 1) want = 1;

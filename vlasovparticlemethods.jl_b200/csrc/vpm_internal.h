@@ -118,6 +118,9 @@ struct vpm_vspace {
 
 namespace vpm {
 
+// cudaFuncSetAttribute(max dynamic smem) + occupancy query, memoised per (device, kernel, smem): the pair costs
+// several microseconds of host time per launch, which dominates the step for small particle counts
+int kernel_occupancy(vpm_ctx* ctx, const void* kern, int block, size_t smem, int* occ);
 int ensure_partials(vpm_ctx* ctx, size_t doubles);
 int ensure_red(vpm_ctx* ctx, size_t doubles);
 int ensure_staging(vpm_ctx* ctx, size_t doubles);
