@@ -45,14 +45,19 @@ int kernel_occupancy(vpm_ctx* ctx, const void* kern, int block, size_t smem, int
         size_t smem;
         bool operator<(const Key& o) const { return dev != o.dev ? dev < o.dev : (k != o.k ? k < o.k : smem < o.smem); }
     };
-    static std::map<Key, int> cache;
+    static std::map<Key, int> cache;                           // occupancy per (device, kernel, smem)
+    static std::map<std::pair<int, const void*>, size_t> attr;  // largest dynamic-smem attribute set so far
+    size_t& cur = attr[{ctx->device, kern}];
+    if (smem > cur) {  // the attribute is per kernel: only ever raise it
+        VPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
     const Key key{ctx->device, kern, smem};
     auto it = cache.find(key);
     if (it != cache.end()) {
         *occ = it->second;
         return VPM_OK;
     }
-    VPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, block, smem));
     cache[key] = *occ;
     return VPM_OK;
