@@ -105,6 +105,21 @@ function Base.getproperty(p::DevicePotential, s::Symbol)
     getfield(p, s)
 end
 
+# every reference sampler gives equal weights: declaring it lets the steppers skip the w[] stream
+set_uniform_weight!(d::DeviceParticleDistribution, w::Real) =
+    (check(ccall((:vpm_particles_set_uniform_weight, libvpm), Cint, (Ptr{Cvoid}, Float64), d.h, w)); d)
+
+# ---------------------------------------------------------------------------------- multi-GPU (one process per GPU)
+# Fused peer-memory all-reduce of the coefficient vector inside the field kernels (NVLink).  `allgather` is any
+# host-side all-gather of 64-byte blobs in rank order (e.g. MPI.Allgather); NCCL (`vpm_comm_init`) is the fallback.
+function attach_peers!(ctx::Context, nranks::Integer, rank::Integer, allgather::Function)
+    h = Vector{UInt8}(undef, 64)
+    check(ccall((:vpm_p2p_prepare, libvpm), Cint, (Ptr{Cvoid}, Ptr{UInt8}), ctx.h, h))
+    all = allgather(h)::Vector{UInt8}                       # 64 * nranks bytes
+    check(ccall((:vpm_p2p_attach, libvpm), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx.h, nranks, rank, all))
+    ctx
+end
+
 # ---------------------------------------------------------------------------------- seam functions
 function ptrs(d::DeviceParticleDistribution)
     x = Ref{Ptr{Float64}}(); v = Ref{Ptr{Float64}}(); w = Ref{Ptr{Float64}}()
