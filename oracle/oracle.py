@@ -78,6 +78,7 @@ def lib():
             "vpo_uniform": (f64, [u64, u64, u32]),
             "vpo_norminv": (f64, [f64]),
             "vpo_sample_bump_on_tail": (None, [i64, i64, i64, u64, f64, f64, f64, f64, f64, _D, _D, _D]),
+            "vpo_sample_normal": (f64, [i64, i64, i64, u64, f64, f64, f64, _D, _D, _D]),
             "vpo_sample_maxwellian": (None, [i64, i64, i64, u64, f64, f64, f64, i32, f64, _D, _D, _D]),
         }
         for name, (res, args) in sig.items():
@@ -271,6 +272,13 @@ def sample_bump_on_tail(N, offset=0, Ntotal=None, seed=0x5EED0001, eps=0.03, kap
     x, v, w = np.zeros(N), np.zeros(N), np.zeros(N)
     lib().vpo_sample_bump_on_tail(N, offset, Ntotal, seed, eps, kappa, alpha, sigma, v0, _dp(x), _dp(v), _dp(w))
     return x, v, w
+
+
+def sample_normal(N, offset=0, Ntotal=None, seed=0x5EED0001, xlo=0.0, xhi=1.0, xmax=0.0):
+    Ntotal = N if Ntotal is None else Ntotal
+    x, v, w = np.zeros(N), np.zeros(N), np.zeros(N)
+    used = lib().vpo_sample_normal(N, offset, Ntotal, seed, xlo, xhi, xmax, _dp(x), _dp(v), _dp(w))
+    return x, v, w, used
 
 
 def sample_maxwellian(N, offset=0, Ntotal=None, seed=0x5EED0001, xlo=0.0, xhi=1.0, shift=0.0, doubled=False, wnum=1.0):

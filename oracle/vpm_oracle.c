@@ -768,6 +768,28 @@ VPO_API void vpo_sample_bump_on_tail(int64_t N, int64_t offset, int64_t Ntotal, 
     }
 }
 
+/* NormalDistribution: src/examples/normal.jl:10-36 (x0, v ~ N(0,1); x0 mapped by the sample maximum) */
+VPO_API double vpo_sample_normal(int64_t N, int64_t offset, int64_t Ntotal, uint64_t seed, double xlo, double xhi,
+                                 double xmax, double *x, double *v, double *w)
+{
+    double m = 0.0;
+    for (int64_t p = 0; p < N; p++) {
+        uint64_t gi = (uint64_t)(offset + p);
+        x[p] = vpo_norminv(vpo_uniform(seed, gi, 0));
+        v[p] = vpo_norminv(vpo_uniform(seed, gi, 1));
+        w[p] = 1.0 / (double)Ntotal;
+        if (fabs(x[p]) > m) m = fabs(x[p]);
+    }
+    if (!(xmax > 0.0)) xmax = ceil(m);
+    for (int64_t p = 0; p < N; p++) {
+        double t = x[p] + xmax;
+        t = t / (2.0 * xmax);
+        t = t * (xhi - xlo);
+        x[p] = t + xlo;
+    }
+    return xmax;
+}
+
 /* Maxwellian mixture in v, uniform x on [xlo,xhi):
  *   nshift=0: v~N(0,1)   (NormalDistribution v-part, src/examples/normal.jl:16)
  *   DoubleMaxwellian: first floor(Ntotal/2) particles +shift, rest -shift (doublemaxwellian.jl:17-29)

@@ -1,0 +1,55 @@
+"""Device-side NormalDistribution sampler (src/examples/normal.jl:10-36) against its CPU twin, and the
+config-1 script (scripts/vlasov_poisson.jl as shipped: 1e4 particles, 16 knots, order 3, frozen-field Strang)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vpm():
+    import vpm_b200
+    vpm_b200.default_context()
+    return vpm_b200
+
+
+def test_normal_distribution_sampler(vpm, oracle):
+    n = 10000
+    d = vpm.ParticleDistribution(1, 1, n)
+    vpm.initialize_(d, vpm.NormalDistribution((0.0, 1.0)))
+    xo, vo, wo, xmax = oracle.sample_normal(n)
+    x, v, w = d.get()
+    assert d.xmax == xmax and xmax == np.ceil(xmax) and 3 <= xmax <= 6
+    np.testing.assert_allclose(x, xo, rtol=1e-13, atol=1e-14)
+    np.testing.assert_allclose(v, vo, rtol=1e-13, atol=1e-14)
+    np.testing.assert_array_equal(w, wo)
+    assert x.min() >= 0.0 and x.max() <= 1.0 and abs(x.mean() - 0.5) < 0.01
+    # a slab of a larger ensemble with an agreed xmax (multi-rank usage)
+    d2 = vpm.ParticleDistribution(1, 1, 1000)
+    vpm.initialize_(d2, vpm.NormalDistribution((-2.0, 3.0)), offset=5000, ntotal=n, xmax=5.0)
+    xo2, vo2, wo2, _ = oracle.sample_normal(1000, offset=5000, Ntotal=n, xlo=-2.0, xhi=3.0, xmax=5.0)
+    np.testing.assert_allclose(d2.get("x"), xo2, rtol=1e-13, atol=1e-14)
+
+
+def test_config1_vlasov_poisson_script(vpm, oracle):
+    """scripts/vlasov_poisson.jl:6-30 with its shipped parameters, both field modes, against the oracle."""
+    npart, nknot, order, tstep, tspan, domain = 10000, 16, 3, 0.1, (0.0, 20.0), (0.0, 1.0)
+    dist = vpm.initialize_(vpm.ParticleDistribution(1, 1, npart), vpm.NormalDistribution(domain))
+    x0, v0, w0 = dist.get()
+    potential = vpm.Potential(vpm.PeriodicBasisBSplineKit(domain, order, nknot))
+    model = vpm.VlasovPoisson(dist, potential)
+    integrator = vpm.SplittingMethod(model, tspan, tstep)          # field="frozen": as shipped
+    vpm.run_(integrator)
+    xs = oracle.XSpace(domain[0], domain[1], order, nknot)
+    xo, vo, _ = xs.strang_frozen(x0, v0, x0, w0, tstep, 200)
+    x1, v1, _ = dist.get()
+    nrm = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert nrm(x1, xo) < 1e-12 and nrm(v1, vo) < 1e-12
+    # the physical (self-consistent) variant of the same configuration
+    dist2 = vpm.ParticleDistribution(1, 1, npart).set(x0, v0, w0)
+    integ2 = vpm.SplittingMethod(vpm.VlasovPoisson(dist2, potential), tspan, tstep, field="selfconsistent")
+    vpm.run_(integ2, diag_mode=1)
+    xo2, vo2, do2, _ = xs.strang_selfconsistent(x0, v0, w0, tstep, 200)
+    x2, v2, _ = dist2.get()
+    assert nrm(x2, xo2) < 1e-10 and nrm(v2, vo2) < 1e-10       # 200 steps of a chaotic N-body system
+    np.testing.assert_allclose(integ2.diagnostics[:, 1:], do2[:, 1:], rtol=1e-9)

@@ -750,12 +750,12 @@ class DoubleMaxwellian:
         self.domain, self.shift = domain, shift
 
 
-def initialize_(dist, params, seed=DEFAULT_SEED, offset=0, ntotal=None):
+def initialize_(dist, params, seed=DEFAULT_SEED, offset=0, ntotal=None, xmax=None):
     """initialize!(dist, example): device-side, counter-based in the global particle index so a slab
     [offset, offset+npart) of an ntotal-particle ensemble is reproducible on any rank.
 
-    NormalDistribution maps x through a data-dependent affine transform (normal.jl:19-21, needs the sample
-    maximum), so it is drawn on the host with numpy's seeded generator and uploaded (config 1 is 1e4 particles).
+    NormalDistribution maps x through a data-dependent affine transform (normal.jl:19-21): xmax = ceil(max |x0|)
+    is reduced on the device over this rank's particles unless `xmax` is given (multi-rank runs pass one value).
     """
     n = dist.npart
     ntotal = n if ntotal is None else int(ntotal)
@@ -769,12 +769,10 @@ def initialize_(dist, params, seed=DEFAULT_SEED, offset=0, ntotal=None):
         check(_lib().vpm_sample_maxwellian(dist._h, int(offset), ntotal, int(seed), params.domain[0], params.domain[1],
                                             0.0, 0, 1.0))
     elif isinstance(params, NormalDistribution):
-        rng = np.random.default_rng(seed)
-        x0, v0 = rng.standard_normal(n), rng.standard_normal(n)
-        xmax = math.ceil(np.abs(x0).max())
-        x0 = (x0 + xmax) / (2 * xmax)
-        x0 = x0 * (params.domain[1] - params.domain[0]) + params.domain[0]
-        dist.set(x0, v0, np.full(n, 1.0 / n))
+        used = C.c_double()
+        check(_lib().vpm_sample_normal(dist._h, int(offset), ntotal, int(seed), params.domain[0], params.domain[1],
+                                       float(xmax or 0.0), C.byref(used)))
+        dist.xmax = used.value
     else:
         raise TypeError(f"no initialize_ method for {type(params).__name__}")
     return dist

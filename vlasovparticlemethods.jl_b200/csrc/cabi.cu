@@ -435,6 +435,15 @@ int vpm_sample_bump_on_tail(vpm_particles* p, int64_t offset, int64_t ntotal, ui
     return launch_sample_bump_on_tail(p->ctx, p, offset, ntotal, seed, eps, kappa, alpha, sigma, v0);
 }
 
+int vpm_sample_normal(vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed, double xlo, double xhi, double xmax,
+                      double* xmax_used)
+{
+    VPM_REQUIRE(p && ntotal > 0 && xhi > xlo, "vpm_sample_normal: bad arguments");
+    VPM_CUDA(cudaSetDevice(p->ctx->device));
+    p->uw = false;
+    return launch_sample_normal(p->ctx, p, offset, ntotal, seed, xlo, xhi, xmax, xmax_used);
+}
+
 int vpm_sample_maxwellian(vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed, double xlo, double xhi,
                           double shift, int doubled, double wnum)
 {
@@ -537,12 +546,8 @@ int vpm_poisson_solve(vpm_xspace* xs, const double* rhs_host, double* phi_host)
     vpm_ctx* ctx = xs->ctx;
     VPM_CUDA(cudaSetDevice(ctx->device));
     if (rhs_host) VPM_CHECK(h2d(ctx, xs->rhs, rhs_host, xs->nh));
-    // solve only: the rhs is taken as given (already global), so bypass the all-reduce split
-    vpm::Comm saved = ctx->comm;
-    ctx->comm.comm = nullptr;
-    int rc = launch_vp_field(ctx, xs, FIELD_SOLVE | FIELD_TABLE, 0, 0, 0, -1.0, 1.0, -1, -1);
-    ctx->comm = saved;
-    VPM_CHECK(rc);
+    // solve only: the rhs is taken as given (already global); without the REDUCE phase nothing is communicated
+    VPM_CHECK(launch_vp_field(ctx, xs, FIELD_SOLVE | FIELD_TABLE, 0, 0, 0, -1.0, 1.0, -1, -1));
     if (phi_host) VPM_CHECK(d2h(ctx, phi_host, xs->phi, xs->nh));
     return VPM_OK;
 }
@@ -578,16 +583,12 @@ int vpm_gather_x(vpm_xspace* xs, const double* coef_host, const double* x_dev, i
 int vpm_field_energy(vpm_xspace* xs, const double* phi_host, double* energy)
 {
     VPM_REQUIRE(xs && phi_host && energy, "vpm_field_energy: NULL argument");
-    // nh x (2K-1) flops of host arithmetic on host data: dot(phi, S, phi)/2
-    const int nh = xs->nh, K = xs->K;
-    long double e = 0;
-    for (int i = 0; i < nh; i++) {
-        long double r = 0;
-        for (int d = -(K - 1); d <= K - 1; d++) r += (long double)xs->stiff_stencil[d + K - 1] * phi_host[((i + d) % nh + nh) % nh];
-        e += (long double)phi_host[i] * r;
-    }
-    *energy = (double)(0.5L * e);
-    return VPM_OK;
+    vpm_ctx* ctx = xs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    VPM_CHECK(ensure_red(ctx, (size_t)xs->nh + 2));
+    VPM_CHECK(h2d(ctx, ctx->red, phi_host, xs->nh));
+    VPM_CHECK(launch_x_energy(ctx, xs, ctx->red, ctx->red + xs->nh));
+    return d2h(ctx, energy, ctx->red + xs->nh, 1);
 }
 
 int vpm_push_drift(vpm_xspace* xs, vpm_particles* p, double tau)
@@ -607,11 +608,7 @@ int vpm_push_kick(vpm_xspace* xs, vpm_particles* p, const double* phi_host, doub
     vpm_ctx* ctx = xs->ctx;
     VPM_CUDA(cudaSetDevice(ctx->device));
     if (phi_host) VPM_CHECK(h2d(ctx, xs->phi, phi_host, xs->nh));
-    vpm::Comm saved = ctx->comm;
-    ctx->comm.comm = nullptr;
-    int rc = launch_vp_field(ctx, xs, FIELD_TABLE, 0, 0, 0, -scale, 1.0, -1, -1);
-    ctx->comm = saved;
-    VPM_CHECK(rc);
+    VPM_CHECK(launch_vp_field(ctx, xs, FIELD_TABLE, 0, 0, 0, -scale, 1.0, -1, -1));
     VpPass ps{};
     ps.x_in = p->x; ps.v_in = p->v; ps.w = p->w; ps.v_out = p->v; ps.n = p->n;
     ps.flags = VP_KICK1 | VP_WRITE_V;
@@ -848,11 +845,8 @@ int vpm_deposit_v(vpm_vspace* vs, const double* v_dev, const double* w_dev, int6
 
 static int lb_field_local(vpm_ctx* ctx, vpm_vspace* vs, int phases)
 {
-    vpm::Comm saved = ctx->comm;
-    ctx->comm.comm = nullptr;
-    int rc = launch_lb_field(ctx, vs, phases, 0, 0, -1);
-    ctx->comm = saved;
-    return rc;
+    // phases without REDUCE / SCALRED never communicate
+    return launch_lb_field(ctx, vs, phases & ~(LBF_REDUCE | LBF_SCALRED), 0, 0, -1);
 }
 
 int vpm_mass_solve_v(vpm_vspace* vs, const double* rhs_host, double* coef_host)

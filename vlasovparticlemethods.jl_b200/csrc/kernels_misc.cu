@@ -3,6 +3,8 @@
 //                integrator's 2 x N state (src/models/vlasov_poisson.jl:81)
 //   samplers:    BumpOnTail (src/examples/bumpontail.jl:43-75), NormalDistribution v-part
 //                (src/examples/normal.jl:16), DoubleMaxwellian (src/examples/doublemaxwellian.jl:15-35)
+#include <cmath>
+
 #include "vpm_internal.h"
 
 namespace vpm {
@@ -125,6 +127,42 @@ __global__ void fill_kernel(double* __restrict__ a, long long n, double value)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] = value;
 }
 
+// NormalDistribution (src/examples/normal.jl:10-36), pass 1: x0, v ~ N(0,1), w = 1/N, per-CTA max |x0|
+__global__ void sample_normal_kernel(long long n, long long offset, long long ntotal, uint64_t seed, double* __restrict__ x,
+                                     double* __restrict__ v, double* __restrict__ w, double* __restrict__ cta_max)
+{
+    __shared__ double s_m[8];
+    double m = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t gi = (uint64_t)(offset + i);
+        const double x0 = norminv(uniform01(seed, gi, 0));
+        x[i] = x0;
+        v[i] = norminv(uniform01(seed, gi, 1));
+        w[i] = 1.0 / (double)ntotal;
+        m = fmax(m, fabs(x0));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); k++) m = fmax(m, s_m[k]);
+        cta_max[blockIdx.x] = m;
+    }
+}
+
+// pass 2 (normal.jl:19-25): x0 += xmax; x0 /= 2 xmax; x0 *= hi - lo; x0 += lo
+__global__ void normal_affine_kernel(long long n, double xmax, double xlo, double xhi, double* __restrict__ x)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double t = x[i] + xmax;
+        t = t / (2.0 * xmax);
+        t = t * (xhi - xlo);
+        x[i] = t + xlo;
+    }
+}
+
 unsigned grid_for(vpm_ctx* ctx, long long n, int block)
 {
     long long g = (n + block - 1) / block;
@@ -167,6 +205,31 @@ int launch_sample_bump_on_tail(vpm_ctx* ctx, vpm_particles* p, int64_t offset, i
                                                                       p->x, p->v, p->w);
     ctx->launches++;
     VPM_CUDA(cudaGetLastError());
+    return VPM_OK;
+}
+
+int launch_sample_normal(vpm_ctx* ctx, vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed, double xlo, double xhi,
+                         double xmax, double* xmax_used)
+{
+    const unsigned grid = grid_for(ctx, p->n, 256);
+    int rc = ensure_red(ctx, grid);
+    if (rc) return rc;
+    sample_normal_kernel<<<grid, 256, 0, ctx->stream>>>(p->n, offset, ntotal, seed, p->x, p->v, p->w, ctx->red);
+    ctx->launches++;
+    VPM_CUDA(cudaGetLastError());
+    if (!(xmax > 0.0)) {  // ceil(maximum(abs.(x0))) over this rank's particles (normal.jl:19)
+        std::vector<double> part(grid);
+        VPM_CUDA(cudaMemcpyAsync(part.data(), ctx->red, sizeof(double) * grid, cudaMemcpyDeviceToHost, ctx->stream));
+        VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+        double m = 0.0;
+        for (double q : part) m = q > m ? q : m;
+        xmax = std::ceil(m);
+        if (!(xmax > 0.0)) xmax = 1.0;
+    }
+    normal_affine_kernel<<<grid, 256, 0, ctx->stream>>>(p->n, xmax, xlo, xhi, p->x);
+    ctx->launches++;
+    VPM_CUDA(cudaGetLastError());
+    if (xmax_used) *xmax_used = xmax;
     return VPM_OK;
 }
 

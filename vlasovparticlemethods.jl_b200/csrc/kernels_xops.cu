@@ -62,7 +62,40 @@ __global__ void circulant_apply_kernel(const double* __restrict__ col, const dou
     }
 }
 
+// dot(phi, S, phi) / 2 with the circulant stiffness stencil: energy(::PoissonField), src/electric_field.jl:47
+__global__ void x_energy_kernel(const double* __restrict__ phi, const double* __restrict__ stiff, int nh, int K,
+                                double* __restrict__ out)
+{
+    __shared__ double s_part[8];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nh; i += blockDim.x) {
+        double r = 0.0;
+        for (int d = -(K - 1); d <= K - 1; d++) {
+            int j = (i + d) % nh;
+            if (j < 0) j += nh;
+            r = fma(stiff[d + K - 1], phi[j], r);
+        }
+        s = fma(phi[i], r, s);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_part[w];
+        out[0] = 0.5 * t;
+    }
+}
+
 }  // namespace
+
+int launch_x_energy(vpm_ctx* ctx, const vpm_xspace* xs, const double* phi_dev, double* out_dev)
+{
+    x_energy_kernel<<<1, 256, 0, ctx->stream>>>(phi_dev, xs->stiff, xs->nh, xs->K, out_dev);
+    ctx->launches++;
+    VPM_CUDA(cudaGetLastError());
+    return VPM_OK;
+}
 
 // builds the table into tab_dev (row stride = *ncoef | 1); piece tables for order K live in ctx->red scratch
 int launch_x_table(vpm_ctx* ctx, vpm_xspace* xs, const double* coef_dev, int deriv, double* tab_dev, int* ncoef)

@@ -164,6 +164,7 @@ int launch_vp_field(vpm_ctx* ctx, vpm_xspace* xs, int phases, int nparts, int ha
 // generic per-cell polynomial gather: out[i] = sum_m tab[cell(x_i)][m] u^m  (periodic x-space)
 int launch_x_table(vpm_ctx* ctx, vpm_xspace* xs, const double* coef_dev, int deriv, double* tab_dev, int* ncoef);
 int launch_x_gather(vpm_ctx* ctx, const vpm_xspace* xs, const double* tab_dev, int ncoef, const double* x, int64_t n, double* out);
+int launch_x_energy(vpm_ctx* ctx, const vpm_xspace* xs, const double* phi_dev, double* out_dev);
 int launch_circulant_apply(vpm_ctx* ctx, const double* col_dev, const double* in_dev, double* out_dev, int n);
 
 // ---------------- Lenard-Bernstein passes (kernels_lb.cu) ----------------
@@ -198,6 +199,8 @@ int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nr
 int launch_fill(vpm_ctx* ctx, double* a, int64_t n, double value);
 int launch_aos_to_soa(vpm_ctx* ctx, const double* z, int ld, int64_t n, double* x, double* v, double* w);
 int launch_soa_to_aos(vpm_ctx* ctx, const double* x, const double* v, const double* w, int ld, int64_t n, double* z);
+int launch_sample_normal(vpm_ctx* ctx, vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed, double xlo, double xhi,
+                         double xmax, double* xmax_used);
 int launch_sample_bump_on_tail(vpm_ctx* ctx, vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed,
                                double eps, double kappa, double alpha, double sigma, double v0);
 int launch_sample_maxwellian(vpm_ctx* ctx, vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed,
