@@ -207,6 +207,140 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Bulk-async (TMA engine) streaming variant of the fused main pass: one elected thread issues 1-D
+// cp.async.bulk copies of whole x/v/w tiles into a two-stage shared-memory ring and the data's arrival is
+// tracked by mbarriers, so the bytes in flight no longer depend on registers or resident warps.
+// Selected with VPM_TUNE_TMA=1 (measured against the register-prefetch kernel in DESIGN.md).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+constexpr int kTmaStages = 2;
+constexpr int kTmaTile = 2 * kBlock;  // particles per tile: one double2 per thread and array
+
+template <int K, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) vp_pass_tma_kernel(const VpDev P)
+{
+    extern __shared__ __align__(16) double smem[];
+    constexpr int ES = VpCfg<K>::ES;
+    constexpr int FLAGS = kMainFlags;
+    const int tid = threadIdx.x;
+    const int nb = P.nh + K - 1;
+    double* s_red = smem;
+    double* s_etab = smem + 2 * (kBlock / 32);
+    double* s_hbase = s_etab + ((P.nh * ES + 1) & ~1);
+    double* s_hist = s_hbase + tid;
+    double* s_stage = s_hbase + (size_t)nb * kBlock;                 // kTmaStages x {x, v, w} x kTmaTile
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + (size_t)kTmaStages * 3 * kTmaTile);
+
+    for (int i = tid; i < P.nh * ES; i += kBlock) s_etab[i] = P.etab[i];
+    for (int i = tid; i < nb * kBlock; i += kBlock) s_hbase[i] = 0.0;
+    if (tid == 0) {
+        for (int s = 0; s < kTmaStages; s++) mbar_init(&s_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long ntiles = P.n / kTmaTile;
+    auto issue = [&](int s, long long g) {
+        double* dst = s_stage + (size_t)s * 3 * kTmaTile;
+        const bool uw = P.use_uw;
+        mbar_expect_tx(&s_bar[s], (uint32_t)((uw ? 2 : 3) * kTmaTile * sizeof(double)));
+        bulk_g2s(dst, P.x_in + g * kTmaTile, kTmaTile * sizeof(double), &s_bar[s]);
+        bulk_g2s(dst + kTmaTile, P.v_in + g * kTmaTile, kTmaTile * sizeof(double), &s_bar[s]);
+        if (!uw) bulk_g2s(dst + 2 * kTmaTile, P.w + g * kTmaTile, kTmaTile * sizeof(double), &s_bar[s]);
+    };
+    if (tid == 0)
+        for (int s = 0; s < kTmaStages; s++) {
+            const long long g = blockIdx.x + (long long)s * gridDim.x;
+            if (g < ntiles) issue(s, g);
+        }
+
+    double ksum = 0.0, msum = 0.0;
+    const double2 wdef = make_double2(P.w_uniform, P.w_uniform);
+    for (long long it = 0;; it++) {
+        const long long g = blockIdx.x + it * gridDim.x;
+        if (g >= ntiles) break;
+        const int s = (int)(it % kTmaStages);
+        mbar_wait(&s_bar[s], (uint32_t)((it / kTmaStages) & 1));
+        const double* src = s_stage + (size_t)s * 3 * kTmaTile;
+        double2 xa = *reinterpret_cast<const double2*>(src + 2 * tid);
+        double2 va = *reinterpret_cast<const double2*>(src + kTmaTile + 2 * tid);
+        double2 wa = P.use_uw ? wdef : *reinterpret_cast<const double2*>(src + 2 * kTmaTile + 2 * tid);
+        vp_particle<K, FLAGS, 0>(P, FLAGS, s_etab, s_hist, xa.x, va.x, wa.x, ksum, msum);
+        vp_particle<K, FLAGS, 0>(P, FLAGS, s_etab, s_hist, xa.y, va.y, wa.y, ksum, msum);
+        const long long i = g * kTmaTile + 2 * tid;
+        st_stream2(P.x_out + i, xa);
+        st_stream2(P.v_out + i, va);
+        __syncthreads();  // every thread has read stage s: hand it back to the copy engine
+        if (tid == 0) {
+            const long long gn = g + (long long)kTmaStages * gridDim.x;
+            if (gn < ntiles) issue(s, gn);
+        }
+    }
+    // remainder (< one tile): plain loads, spread over the grid
+    for (long long i = ntiles * kTmaTile + (long long)blockIdx.x * kBlock + tid; i < P.n; i += (long long)gridDim.x * kBlock) {
+        double x = P.x_in[i], v = P.v_in[i], w = P.use_uw ? P.w_uniform : P.w[i];
+        vp_particle<K, FLAGS, 0>(P, FLAGS, s_etab, s_hist, x, v, w, ksum, msum);
+        P.x_out[i] = x;
+        P.v_out[i] = v;
+    }
+
+    const int lane = tid & 31, warp = tid >> 5;
+    __syncthreads();
+    for (int b = warp; b < nb; b += kBlock / 32) {
+        double sum = 0.0;
+#pragma unroll
+        for (int t = lane; t < kBlock; t += 32) sum += s_hbase[b * kBlock + t];
+        sum = warp_sum(sum);
+        if (lane == 0) P.partials[(size_t)blockIdx.x * P.nbp + b] = sum;
+    }
+    ksum = warp_sum(ksum);
+    msum = warp_sum(msum);
+    if (lane == 0) {
+        s_red[2 * warp] = ksum;
+        s_red[2 * warp + 1] = msum;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double k = 0.0, m = 0.0;
+        for (int wi = 0; wi < kBlock / 32; wi++) {
+            k += s_red[2 * wi];
+            m += s_red[2 * wi + 1];
+        }
+        P.kin_partials[2 * blockIdx.x] = k;
+        P.kin_partials[2 * blockIdx.x + 1] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Large grids (n_basis + K - 1 > ~110 bins): per-thread histogram copies no longer fit and shared-memory fp64
 // atomics are CAS loops (64 cycles per warp instruction).  This variant bins each tile of particles by cell
 // inside shared memory (counting sort on native 32-bit shared atomics), then reduces every cell's segment
@@ -543,7 +677,15 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
         return (v >= 2 && v <= 4) ? v : 3;
     }();
     void (*kern)(const VpDev) = nullptr;
-    if (tiled) kern = tune_tile == 1 ? vp_pass_tiled_kernel<K, 8, 2> : (tune_tile == 2 ? vp_pass_tiled_kernel<K, 4, 2> : vp_pass_tiled_kernel<K, 4, 3>);
+    static const int tune_tma = [] {
+        const char* e = getenv("VPM_TUNE_TMA");
+        return e ? atoi(e) : 0;
+    }();
+    const bool tma = tune_tma && !tiled && hm == 0 && vec && p.flags == kMainFlags;
+    if (tma) {
+        smem += sizeof(double) * (size_t)kTmaStages * 3 * kTmaTile + sizeof(uint64_t) * kTmaStages;
+        kern = tune_tma == 2 ? vp_pass_tma_kernel<K, 2> : vp_pass_tma_kernel<K, 3>;
+    } else if (tiled) kern = tune_tile == 1 ? vp_pass_tiled_kernel<K, 8, 2> : (tune_tile == 2 ? vp_pass_tiled_kernel<K, 4, 2> : vp_pass_tiled_kernel<K, 4, 3>);
     else if (hm == 1) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 1> : vp_pass_kernel<K, -1, 1, 3, 1>;
     else if (hm == 2) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 2> : vp_pass_kernel<K, -1, 1, 3, 2>;
     else if (vec && p.flags == kMainFlags) {
@@ -559,7 +701,7 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
         if (rc_occ) return rc_occ;
     }
     if (occ < 1) return fail(VPM_ERR_UNSUPPORTED, "vp pass kernel does not fit on an SM");
-    long long want = tiled ? (p.n + kTile - 1) / kTile : (p.n / (vec ? 2 : 1) + kBlock - 1) / kBlock;
+    long long want = tiled ? (p.n + kTile - 1) / kTile : (tma ? (p.n + kTmaTile - 1) / kTmaTile : (p.n / (vec ? 2 : 1) + kBlock - 1) / kBlock);
     if (want < 1) want = 1;
     long long grid = (long long)ctx->sm_count * occ;
     if (grid > want) grid = want;
