@@ -242,10 +242,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "memory");
 }
 
-constexpr int kTmaStages = 2;
 constexpr int kTmaTile = 2 * kBlock;  // particles per tile: one double2 per thread and array
 
-template <int K, int MINB>
+template <int K, int MINB, int kTmaStages>
 __global__ void __launch_bounds__(kBlock, MINB) vp_pass_tma_kernel(const VpDev P)
 {
     extern __shared__ __align__(16) double smem[];
@@ -683,8 +682,9 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     }();
     const bool tma = tune_tma && !tiled && hm == 0 && vec && p.flags == kMainFlags;
     if (tma) {
-        smem += sizeof(double) * (size_t)kTmaStages * 3 * kTmaTile + sizeof(uint64_t) * kTmaStages;
-        kern = tune_tma == 2 ? vp_pass_tma_kernel<K, 2> : vp_pass_tma_kernel<K, 3>;
+        const int stages = tune_tma == 2 ? 3 : (tune_tma == 3 ? 4 : 2);
+        smem += sizeof(double) * (size_t)stages * 3 * kTmaTile + sizeof(uint64_t) * stages;
+        kern = tune_tma == 2 ? vp_pass_tma_kernel<K, 2, 3> : (tune_tma == 3 ? vp_pass_tma_kernel<K, 2, 4> : vp_pass_tma_kernel<K, 3, 2>);
     } else if (tiled) kern = tune_tile == 1 ? vp_pass_tiled_kernel<K, 8, 2> : (tune_tile == 2 ? vp_pass_tiled_kernel<K, 4, 2> : vp_pass_tiled_kernel<K, 4, 3>);
     else if (hm == 1) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 1> : vp_pass_kernel<K, -1, 1, 3, 1>;
     else if (hm == 2) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 2> : vp_pass_kernel<K, -1, 1, 3, 2>;
