@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
 // Bulk-async (TMA engine) streaming variant of the fused main pass: one elected thread issues 1-D
 // cp.async.bulk copies of whole x/v/w tiles into a two-stage shared-memory ring and the data's arrival is
 // tracked by mbarriers, so the bytes in flight no longer depend on registers or resident warps.
-// Selected with VPM_TUNE_TMA=1 (measured against the register-prefetch kernel in DESIGN.md).
+// Default for the fused main pass (0.608 vs 0.635 ms per 1e8 particles against the register-prefetch kernel,
+// DESIGN.md 4.1); VPM_TUNE_TMA=0 selects the latter.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
@@ -677,8 +678,8 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     }();
     void (*kern)(const VpDev) = nullptr;
     static const int tune_tma = [] {
-        const char* e = getenv("VPM_TUNE_TMA");
-        return e ? atoi(e) : 0;
+        const char* e = getenv("VPM_TUNE_TMA");  // 0: register-prefetch kernel, 1 (default): 2-stage bulk-async ring
+        return e ? atoi(e) : 1;
     }();
     const bool tma = tune_tma && !tiled && hm == 0 && vec && p.flags == kMainFlags;
     if (tma) {
