@@ -337,7 +337,8 @@ def main():
                        "parallelism": f"particle slabs x{world}, coefficient all-reduce per field update ({comm_used})" if world > 1 else "single GPU",
                        "passes_in_timed_region": passes_per_call(args.steps)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "vp_pass_kernel" if args.workload == "vp" else "lb_pass_kernel",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": ("vp_pass_tma_kernel (fused kick+drift+deposit; prologue/epilogue passes use vp_pass_kernel)"
+                                    if os.environ.get("VPM_TUNE_TMA", "1") != "0" else "vp_pass_kernel") if args.workload == "vp" else "lb_pass_kernel",
                          "bytes_per_launch": bytes_per_launch, "avg_launch_ms": pass_ms / max(pass_cnt, 1),
                          "launches_timed": pass_cnt, "field_kernel_share": field_ms / max(pass_ms + field_ms, 1e-30),
                          "frac_of_8TBs_nominal": achieved / 8000.0},
