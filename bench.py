@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--workload", default="vp", choices=["vp", "lb", "clb"])
     ap.add_argument("--n-basis", type=int, default=16, help="x-space basis size (headline config: 16)")
     ap.add_argument("--order", type=int, default=4, help="spline order (headline config: 4 = cubic)")
+    ap.add_argument("--field", default="selfconsistent", choices=["selfconsistent", "frozen"],
+                    help="vp: self-consistent Strang loop (headline) or the frozen field of the shipped SplittingMethod")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: fused peer-memory all-reduce in the field kernel (default) or NCCL")
     return ap.parse_args()
@@ -191,8 +193,8 @@ def main():
         pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), ORDER, NH), ctx)
 
         def run_steps(k):
-            vpm.check(lib.vpm_vp_strang_steps_async(pot._h, d._h, DT, CHI, int(k), 0, 0))
-        kind_pass, bytes_unit, wl = 0, BYTES_PER_STEP, "vp_bump_on_tail_strang_selfconsistent"
+            vpm.check(lib.vpm_vp_strang_steps_async(pot._h, d._h, DT, CHI, int(k), 1 if args.field == "frozen" else 0, 0))
+        kind_pass, bytes_unit, wl = 0, BYTES_PER_STEP, "vp_bump_on_tail_strang_" + args.field
         passes_per_call = lambda k: k + 1
     else:
         cons = args.workload == "clb"

@@ -245,14 +245,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 
 constexpr int kTmaTile = 2 * kBlock;  // particles per tile: one double2 per thread and array
 
-template <int K, int MINB, int kTmaStages>
+template <int K, int FLAGS, int MINB, int kTmaStages>
 __global__ void __launch_bounds__(kBlock, MINB) vp_pass_tma_kernel(const VpDev P)
 {
     extern __shared__ __align__(16) double smem[];
     constexpr int ES = VpCfg<K>::ES;
-    constexpr int FLAGS = kMainFlags;
+    constexpr bool DEP = (FLAGS & VP_DEPOSIT) != 0;
     const int tid = threadIdx.x;
-    const int nb = P.nh + K - 1;
+    const int nb = DEP ? P.nh + K - 1 : 0;
     double* s_red = smem;
     double* s_etab = smem + 2 * (kBlock / 32);
     double* s_hbase = s_etab + ((P.nh * ES + 1) & ~1);
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_tma_kernel(const VpDev P
 
     const int lane = tid & 31, warp = tid >> 5;
     __syncthreads();
-    for (int b = warp; b < nb; b += kBlock / 32) {
+    for (int b = warp; b < nb; b += kBlock / 32) {  // nb == 0 without a deposit
         double sum = 0.0;
 #pragma unroll
         for (int t = lane; t < kBlock; t += 32) sum += s_hbase[b * kBlock + t];
@@ -681,11 +681,15 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
         const char* e = getenv("VPM_TUNE_TMA");  // 0: register-prefetch kernel, 1 (default): 2-stage bulk-async ring
         return e ? atoi(e) : 1;
     }();
-    const bool tma = tune_tma && !tiled && hm == 0 && vec && p.flags == kMainFlags;
-    if (tma) {
+    const bool tma = tune_tma && !tiled && hm == 0 && vec && (p.flags == kMainFlags || p.flags == kFrozenFlags);
+    if (tma && p.flags == kFrozenFlags) {  // no histograms: a deeper ring fits
+        smem += sizeof(double) * (size_t)4 * 3 * kTmaTile + sizeof(uint64_t) * 4;
+        kern = vp_pass_tma_kernel<K, kFrozenFlags, 3, 4>;
+    } else if (tma) {
         const int stages = tune_tma == 2 ? 3 : (tune_tma == 3 ? 4 : 2);
         smem += sizeof(double) * (size_t)stages * 3 * kTmaTile + sizeof(uint64_t) * stages;
-        kern = tune_tma == 2 ? vp_pass_tma_kernel<K, 2, 3> : (tune_tma == 3 ? vp_pass_tma_kernel<K, 2, 4> : vp_pass_tma_kernel<K, 3, 2>);
+        kern = tune_tma == 2 ? vp_pass_tma_kernel<K, kMainFlags, 2, 3>
+             : (tune_tma == 3 ? vp_pass_tma_kernel<K, kMainFlags, 2, 4> : vp_pass_tma_kernel<K, kMainFlags, 3, 2>);
     } else if (tiled) kern = tune_tile == 1 ? vp_pass_tiled_kernel<K, 8, 2> : (tune_tile == 2 ? vp_pass_tiled_kernel<K, 4, 2> : vp_pass_tiled_kernel<K, 4, 3>);
     else if (hm == 1) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 1> : vp_pass_kernel<K, -1, 1, 3, 1>;
     else if (hm == 2) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 2> : vp_pass_kernel<K, -1, 1, 3, 2>;
