@@ -52,8 +52,10 @@ def test_fuzz_vlasov_poisson(vpm, oracle, seed):
             assert (np.abs(m.diagnostics - do) / scale).max() < 1e-9, tag
 
 
+@pytest.mark.parametrize("ring", ["-1", "0"])   # TMA ring passes (default) / register-prefetch passes
 @pytest.mark.parametrize("seed", range(8))
-def test_fuzz_lenard_bernstein(vpm, oracle, seed):
+def test_fuzz_lenard_bernstein(vpm, oracle, seed, ring, monkeypatch):
+    monkeypatch.setenv("VPM_TUNE_LBTMA", ring)
     rng = np.random.default_rng(2000 + seed)
     K = int(rng.integers(3, 7))
     nk = int(rng.choice([8, 12, 21, 41, 64, 150]))

@@ -205,8 +205,10 @@ def test_large_properties(vpm):
 
 
 # ------------------------------------------------------------------------------------- v-space / LB
+@pytest.mark.parametrize("ring", ["-1", "0"])   # TMA ring passes (default) / register-prefetch passes
 @pytest.mark.parametrize("name", ["lb_k4_n41", "lb_k5_n12"])
-def test_lb_golden(vpm, name):
+def test_lb_golden(vpm, name, ring, monkeypatch):
+    monkeypatch.setenv("VPM_TUNE_LBTMA", ring)
     g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     K, nk, dt, ns, nu = int(g["K"]), int(g["nknots"]), float(g["dt"]), int(g["nsteps"]), float(g["nu"])
     v, w = g["v"], g["w"]

@@ -61,7 +61,8 @@ def test_lb_uniform_weight(vpm, oracle):
         gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d, vpm.CollisionEntropy(sd)), (0.0, 0.03), 0.01)
         vpm.run_(gi)
         res.append((d.get("v"), gi.diagnostics))
-    np.testing.assert_array_equal(res[0][0], res[1][0])
-    np.testing.assert_array_equal(res[0][1], res[1][1])
+    # the w[] stream changes which pass variants fit (ring vs register prefetch), hence the summation order
+    assert nrm(res[0][0], res[1][0]) < 1e-13
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-12)
     vo, do = oracle.VSpace(-10.0, 10.0, 41, 4).rk438(v, w, 1.0, 0.01, 3, conservative=True)
     assert nrm(res[1][0], vo) < 1e-11

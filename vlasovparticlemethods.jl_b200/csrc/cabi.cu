@@ -192,6 +192,8 @@ int vpm_ctx_create(int device, void* stream, vpm_ctx** out)
     VPM_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
+    c->smem_sm = prop.sharedMemPerMultiprocessor;
+    c->smem_reserved = prop.reservedSharedMemPerBlock;
     *out = c;
     return VPM_OK;
 }
@@ -338,7 +340,7 @@ int vpm_particles_destroy(vpm_particles* p)
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     cudaFree(p->x); cudaFree(p->v); cudaFree(p->w);
-    cudaFree(p->q); cudaFree(p->acc); cudaFree(p->d);
+    cudaFree(p->q); cudaFree(p->ka); cudaFree(p->kb);
     delete p;
     return VPM_OK;
 }
@@ -938,10 +940,10 @@ static int alloc_scratch(vpm_particles* p)
 {
     if (p->q) return VPM_OK;
     const size_t bytes = sizeof(double) * (size_t)(p->n > 0 ? p->n + (p->n & 1) : 2);
-    cudaError_t e1 = cudaMalloc((void**)&p->q, bytes), e2 = cudaMalloc((void**)&p->acc, bytes), e3 = cudaMalloc((void**)&p->d, bytes);
+    cudaError_t e1 = cudaMalloc((void**)&p->q, bytes), e2 = cudaMalloc((void**)&p->ka, bytes), e3 = cudaMalloc((void**)&p->kb, bytes);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-        cudaFree(p->q); cudaFree(p->acc); cudaFree(p->d);
-        p->q = p->acc = p->d = nullptr;
+        cudaFree(p->q); cudaFree(p->ka); cudaFree(p->kb);
+        p->q = p->ka = p->kb = nullptr;
         return fail(VPM_ERR_NOMEM, "cudaMalloc of RK438 stage arrays failed");
     }
     return VPM_OK;
@@ -959,7 +961,7 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
     LbPass ps{};
     ps.n = p->n; ps.w = p->w; ps.nu = nu; ps.dt = dt; ps.conservative = conservative;
     ps.use_uw = p->uw; ps.w_uniform = p->wu;
-    ps.acc = p->acc; ps.d = p->d;
+    ps.ka = p->ka; ps.kb = p->kb;
     {   // projection of the initial state + step-0 diagnostics
         LbPass p0 = ps;
         p0.mode = LB_DEPOSIT_ONLY; p0.q = p->v; p0.diag = 1;
@@ -968,12 +970,14 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
     }
     for (int it = 1; it <= nsteps; it++) {
         for (int s = 1; s <= 4; s++) {
+            // stage input in memory: v (s = 1), q4 (s = 4); q2, q3 only for the conservative model's moments
+            // pass -- the stage passes themselves recompute them from v and the stored derivatives
             const double* q = s == 1 ? p->v : p->q;
             if (conservative) VPM_CHECK(lb_prepare_clb(ctx, vs, q, p->n));
             LbPass st = ps;
             st.mode = LB_STAGE1 + (s - 1);
             st.q = q; st.v0 = p->v;
-            st.qout = s == 4 ? p->v : p->q;
+            st.qout = s == 4 ? p->v : ((s == 3 || conservative) ? p->q : nullptr);
             st.diag = s == 4;
             VPM_CHECK(launch_lb_pass(ctx, vs, st, &grid));
             if (s == 4) VPM_CHECK(launch_lb_field(ctx, vs, PROJ | LBF_SCALRED | LBF_DIAG, grid, 2, it));

@@ -8,11 +8,20 @@
 //   RK438 stage algebra                        src/models/lenard_bernstein.jl:79 (GeometricIntegrators tableau)
 //
 // One streaming pass per Runge-Kutta stage: evaluate f_s, f_s' at the stage input from the per-cell
-// polynomial table, form the stage derivative, do the stage algebra in registers, write the next
-// stage input and deposit it for the next projection (private shared-memory histograms, no atomics).
+// polynomial table, form the stage derivative k_s, do the stage algebra in registers and deposit the next
+// stage input for the next projection (private shared-memory histograms, no atomics).
+//
+// Stage vectors are kept in "k form": a pass stores only its derivative k_s (8 B) and the next pass
+// RECOMPUTES its stage input q_s = v + dt sum_j a_sj k_j from v and the stored k's with the same fma
+// sequence (rk_q2/rk_q3/rk_q4 below), instead of storing both q_s and a running accumulator:
+//   stage 1: read v, w        write k1            (24 B)      stage 3: read v, k1, k2, w   write q4, acc (48 B)
+//   stage 2: read v, k1, w    write k2            (32 B)      stage 4: read q4, v, acc, w  write v       (40 B)
+// = 144 B per RK438 particle-step (the accumulate-and-store form needed 184 B).  The conservative model
+// also needs q_2, q_3 in memory for its moments pass (qout != nullptr in stages 1, 2: +8 B each).
 #include <cstdlib>
 
 #include "splines.cuh"
+#include "tma.cuh"
 #include "vpm_internal.h"
 
 namespace vpm {
@@ -22,7 +31,7 @@ namespace {
 struct LbDev {
     int mode;
     const double *q, *w, *v0;
-    double *acc, *d, *qout, *out, *out2;
+    double *ka, *kb, *qout, *out, *out2;
     long long n;
     double nu, dt;
     int conservative, diag;
@@ -35,22 +44,32 @@ struct LbDev {
     double* red_partials;
     double w_uniform;
     int use_uw;
+    int stages;   // ring depth of lb_pass_tma_kernel
 };
 
 constexpr int kRedW = 8;  // doubles per CTA row of scalar partial sums
 
+// Cell index and local coordinate of q on the clamped grid.  Fast path (0 <= t < ncell, t = (q - lo) / h): one
+// round-toward-zero fma against 2^52 leaves floor(t) in the low mantissa word, so ci and u = t - ci cost four
+// fp64 instructions and no conversions or selects.  Everything else -- q == hi (last cell, u = 1), particles
+// outside the domain, NaN -- is detected from the bit pattern of the sum and takes the rare slow path;
+// outside particles are sent to the GHOST cell ncell, whose f / f' table row is zero (Spline evaluation is
+// zero outside the knots) and which deposits nothing.
 template <int K>
 __device__ __forceinline__ bool v_locate(const LbDev& P, double q, int& ci, double& u)
 {
-    const bool inside = (q >= P.lo) && (q <= P.hi);  // NaN -> outside
-    const double t = (q - P.lo) * P.invh;
-    split_floor(t, ci, u);
-    if (ci > P.ncell - 1) {  // q == hi belongs to the last cell (u = 1); garbage for outside particles
-        ci = P.ncell - 1;
-        u = t - (double)ci;
+    const double M = 4503599627370496.0;  // 2^52
+    const double t0 = q - P.lo;
+    const double tm = __fma_rz(t0, P.invh, M);
+    ci = __double2loint(tm);
+    u = fma(t0, P.invh, -(tm - M));
+    if (__double2hiint(tm) != 0x43300000 || (unsigned)ci >= (unsigned)P.ncell) {
+        const bool inside = (q >= P.lo) && (q <= P.hi);  // NaN -> outside
+        ci = inside ? P.ncell - 1 : P.ncell;
+        u = inside ? fma(t0, P.invh, -(double)(P.ncell - 1)) : 0.0;
+        return inside;
     }
-    ci = max(ci, 0);         // outside particles: any valid cell, their f, f' are masked and nothing is deposited
-    return inside;
+    return true;
 }
 
 template <int HM>
@@ -59,33 +78,33 @@ struct HistCfg {
 };
 
 // Deposit in two halves so that the pair loop can finish the arithmetic of both particles before the
-// (ordered) shared-memory read-modify-writes: prepare = locate + basis * weight, commit = K RMWs.
+// (ordered) shared-memory read-modify-writes: prepare = locate + basis, commit = K fused multiply-add RMWs.
 template <int K>
 struct LbDep {
     int ci;
     bool on;
-    double wb[K];
+    double w;
+    double b[K];
 };
 
 template <int K>
 __device__ __forceinline__ void v_deposit_prepare(const LbDev& P, double q, double w, LbDep<K>& d)
 {
-    double u, b[K];
+    double u;
+    d.w = w;
     d.on = v_locate<K>(P, q, d.ci, u);  // out-of-domain particles deposit nothing
     if (d.ci >= K - 1 && d.ci <= P.ncell - K) {
-        basis_uniform<K>(u, b);
-    } else {  // the K-1 cells at either end feel the repeated knots: per-cell table
+        basis_uniform<K>(u, d.b);
+    } else if (d.on) {  // the K-1 cells at either end feel the repeated knots: per-cell table
         const double* pc = P.pieces + (size_t)d.ci * K * K;
 #pragma unroll
         for (int j = 0; j < K; j++) {
             double r = __ldg(pc + j * K + K - 1);
 #pragma unroll
             for (int m = K - 2; m >= 0; m--) r = fma(r, u, __ldg(pc + j * K + m));
-            b[j] = r;
+            d.b[j] = r;
         }
     }
-#pragma unroll
-    for (int j = 0; j < K; j++) d.wb[j] = b[j] * w;
 }
 
 template <int K, int HM>
@@ -96,8 +115,8 @@ __device__ __forceinline__ void v_deposit_commit(double* __restrict__ s_hist, co
     double* hcell = s_hist + d.ci * HS;
 #pragma unroll
     for (int j = 0; j < K; j++) {
-        if (HM == 0) hcell[j * HS] += d.wb[j];
-        else atomicAdd(hcell + j * HS, d.wb[j]);
+        if (HM == 0) hcell[j * HS] = fma(d.b[j], d.w, hcell[j * HS]);
+        else atomicAdd(hcell + j * HS, d.b[j] * d.w);
     }
 }
 
@@ -107,7 +126,7 @@ __device__ __forceinline__ void v_eval(const LbDev& P, const double* __restrict_
     constexpr int TS = 2 * K - 1;
     int ci;
     double u;
-    const bool inside = v_locate<K>(P, q, ci, u);
+    v_locate<K>(P, q, ci, u);   // outside particles read the zero row of the ghost cell
     const double* e = s_tab + ci * TS;
     double a = e[K - 1];
 #pragma unroll
@@ -115,13 +134,19 @@ __device__ __forceinline__ void v_eval(const LbDev& P, const double* __restrict_
     double g = e[2 * K - 2];
 #pragma unroll
     for (int m = K - 3; m >= 0; m--) g = fma(g, u, e[K + m]);
-    f = inside ? a : 0.0;   // Spline evaluation is zero outside the knots
-    df = inside ? g : 0.0;
+    f = a;
+    df = g;
 }
 
 struct LbItem {
-    double q, w, v0, acc, d;
+    double q, w, v0, a, b;   // a, b: the stored stage derivatives (k1 | acc, k2)
 };
+
+// RK438 stage inputs (GeometricIntegrators tableau: a21 = 1/3; a31 = -1/3, a32 = 1; a41 = 1, a42 = -1, a43 = 1).
+// Explicit fma sequences: the pass that deposits q_s and the pass that evaluates k_s at q_s must agree bitwise.
+__device__ __forceinline__ double rk_q2(double v0, double k1, double dt) { return fma(dt, k1 * (1.0 / 3.0), v0); }
+__device__ __forceinline__ double rk_q3(double v0, double k1, double k2, double dt) { return fma(dt, fma(-k1, 1.0 / 3.0, k2), v0); }
+__device__ __forceinline__ double rk_q4(double v0, double k1, double k2, double k3, double dt) { return fma(dt, (k1 - k2) + k3, v0); }
 
 template <int K, int MODE>
 __device__ __forceinline__ void lb_particle(const LbDev& P, const int mode_rt, const double* __restrict__ s_tab,
@@ -138,8 +163,13 @@ __device__ __forceinline__ void lb_particle(const LbDev& P, const int mode_rt, c
         }
         return;
     }
+    // the stage input: stages 2 and 3 recompute it from v0 and the stored derivatives
+    double qe = it.q;
+    if (mode == LB_STAGE1) it.v0 = it.q;
+    if (mode == LB_STAGE2) qe = rk_q2(it.v0, it.a, P.dt);
+    if (mode == LB_STAGE3) qe = rk_q3(it.v0, it.a, it.b, P.dt);
     double f, df;
-    v_eval<K>(P, s_tab, it.q, f, df);
+    v_eval<K>(P, s_tab, qe, f, df);
     if (mode == LB_EVAL) {
         o1 = f;
         o2 = df;
@@ -147,33 +177,30 @@ __device__ __forceinline__ void lb_particle(const LbDev& P, const int mode_rt, c
     }
     if (mode == LB_MOMENTS) {
         sums[0] += f;
-        sums[1] = fma(it.q, f, sums[1]);
-        sums[2] = fma(it.q * it.q, f, sums[2]);
+        sums[1] = fma(qe, f, sums[1]);
+        sums[2] = fma(qe * qe, f, sums[2]);
         sums[3] += df;
-        sums[4] = fma(it.q, df, sums[4]);
+        sums[4] = fma(qe, df, sums[4]);
         return;
     }
     // LB: vdot = -nu (f' + v f)    CLB: vdot = -nu (f' + (A1 + A2 v) f)
-    const double k = -P.nu * (df + (P.conservative ? (A1 + A2 * it.q) : it.q) * f);
+    const double k = -P.nu * fma(fma(A2, qe, A1), f, df);   // A1 = 0, A2 = 1 for the plain model
     if (mode == LB_RHS_OUT) {
         o1 = k;
         return;
     }
-    const double third = 1.0 / 3.0;
     double qn;
     if (mode == LB_STAGE1) {          // q2 = v0 + dt (k1/3)
-        qn = it.q + P.dt * (k * third);
-        it.acc = k;
+        qn = rk_q2(it.v0, k, P.dt);
+        it.a = k;
     } else if (mode == LB_STAGE2) {   // q3 = v0 + dt (-k1/3 + k2)
-        const double k1 = it.acc;
-        qn = it.v0 + P.dt * (-k1 * third + k);
-        it.d = k1 - k;
-        it.acc = k1 + 3.0 * k;
-    } else if (mode == LB_STAGE3) {   // q4 = v0 + dt (k1 - k2 + k3)
-        qn = it.v0 + P.dt * (it.d + k);
-        it.acc = it.acc + 3.0 * k;
+        qn = rk_q3(it.v0, it.a, k, P.dt);
+        it.b = k;
+    } else if (mode == LB_STAGE3) {   // q4 = v0 + dt (k1 - k2 + k3);  acc = k1 + 3 k2 + 3 k3
+        qn = rk_q4(it.v0, it.a, it.b, k, P.dt);
+        it.a = fma(3.0, k, fma(3.0, it.b, it.a));
     } else {                          // v1 = v0 + dt (k1 + 3 k2 + 3 k3 + k4)/8
-        qn = it.v0 + P.dt * ((it.acc + k) * 0.125);
+        qn = fma(P.dt, (it.a + k) * 0.125, it.v0);
         if (P.diag) {
             sums[0] += qn;
             sums[1] = fma(qn, qn, sums[1]);
@@ -188,116 +215,23 @@ struct LbIo {
     static constexpr bool rt = MODE < 0;
     static constexpr bool stage = MODE >= LB_STAGE1 && MODE <= LB_STAGE4;
     static constexpr bool dep = rt || MODE == LB_DEPOSIT_ONLY || stage;
+    static constexpr bool rd_q = rt || !(MODE == LB_STAGE2 || MODE == LB_STAGE3);
     static constexpr bool rd_w = dep;
     static constexpr bool rd_v0 = rt || MODE == LB_STAGE2 || MODE == LB_STAGE3 || MODE == LB_STAGE4;
-    static constexpr bool rd_d = rt || MODE == LB_STAGE3;
+    static constexpr bool rd_b = rt || MODE == LB_STAGE3;
     static constexpr bool wr_q = rt || stage;
-    static constexpr bool wr_acc = rt || MODE == LB_STAGE1 || MODE == LB_STAGE2 || MODE == LB_STAGE3;
-    static constexpr bool wr_d = rt || MODE == LB_STAGE2;
+    static constexpr bool wr_a = rt || MODE == LB_STAGE1 || MODE == LB_STAGE3;
+    static constexpr bool wr_b = rt || MODE == LB_STAGE2;
     static constexpr bool wr_o1 = rt || MODE == LB_RHS_OUT || MODE == LB_EVAL;
     static constexpr bool wr_o2 = rt || MODE == LB_EVAL;
 };
 
-template <int K, int MODE, int VEC, int HM>
-__global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT) ? 4 : 2) lb_pass_kernel(const LbDev P)
+// Fixed-order reduction of the CTA's private histograms into one partial row, and of the scalar sums.
+template <int HS>
+__device__ __forceinline__ void lb_epilogue(const LbDev& P, const int mode, const bool dep, const double* __restrict__ s_hbase,
+                                            double* __restrict__ s_red, double (&sums)[5])
 {
-    extern __shared__ double smem[];
-    constexpr int TS = 2 * K - 1;
-    using Io = LbIo<MODE>;
-    const int mode = MODE >= 0 ? MODE : P.mode;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool stage = mode >= LB_STAGE1 && mode <= LB_STAGE4;
-    const bool dep = mode == LB_DEPOSIT_ONLY || stage;
-    const bool ev = mode != LB_DEPOSIT_ONLY;
-    double* s_red = smem;                        // 5 * warps
-    double* s_tab = smem + 5 * (kBlock / 32);    // ncell * TS
-    constexpr int HS = HistCfg<HM>::copies;
-    double* s_hbase = s_tab + ((P.ncell * TS + 1) & ~1);
-    double* s_hist = s_hbase + (HM == 0 ? tid : (HM == 1 ? (tid >> 5) : 0));
-
-    if (ev)
-        for (int i = tid; i < P.ncell * TS; i += kBlock) s_tab[i] = P.ftab[i];
-    if (dep)
-        for (int i = tid; i < P.nbfull * HS; i += kBlock) s_hbase[i] = 0.0;
-    __syncthreads();
-    const double A1 = P.conservative && ev ? P.scal[0] : 0.0, A2 = P.conservative && ev ? P.scal[1] : 1.0;
-
-    double sums[5] = {0, 0, 0, 0, 0};
-    const long long stride = (long long)gridDim.x * kBlock;
-    const long long gtid = (long long)blockIdx.x * kBlock + tid;
-
-    // runtime-mode variants decide loads/stores from the mode; compile-time modes fold these
-    const bool rd_w = Io::rd_w && dep && !P.use_uw;
-    const bool rd_v0 = Io::rd_v0 && (mode >= LB_STAGE2 && mode <= LB_STAGE4);
-    const bool rd_acc = rd_v0;
-    const bool rd_d = Io::rd_d && mode == LB_STAGE3;
-    const bool wr_q = Io::wr_q && stage;
-    const bool wr_acc = Io::wr_acc && (mode >= LB_STAGE1 && mode <= LB_STAGE3);
-    const bool wr_d = Io::wr_d && mode == LB_STAGE2;
-    const bool wr_o1 = Io::wr_o1 && (mode == LB_RHS_OUT || mode == LB_EVAL) && P.out != nullptr;
-    const bool wr_o2 = Io::wr_o2 && mode == LB_EVAL && P.out2 != nullptr;
-
-    if (VEC == 2) {
-        const long long nvec = P.n >> 1;
-        const double2 z2 = make_double2(0, 0);
-        long long i = gtid;
-        bool have = i < nvec;
-        const double2 wdef = make_double2(P.w_uniform, P.w_uniform);
-        double2 qa = z2, wa = wdef, va = z2, aa = z2, da = z2;
-        if (have) {
-            qa = ld_stream2(P.q + 2 * i);
-            if (rd_w) wa = ld_stream2(P.w + 2 * i);
-            if (rd_v0) va = ld_stream2(P.v0 + 2 * i);
-            if (rd_acc) aa = ld_stream2(P.acc + 2 * i);
-            if (rd_d) da = ld_stream2(P.d + 2 * i);
-        }
-        while (have) {
-            const long long inext = i + stride;
-            const bool hn = inext < nvec;
-            double2 qn = z2, wn = wdef, vn = z2, an = z2, dn = z2;
-            if (hn) {
-                qn = ld_stream2(P.q + 2 * inext);
-                if (rd_w) wn = ld_stream2(P.w + 2 * inext);
-                if (rd_v0) vn = ld_stream2(P.v0 + 2 * inext);
-                if (rd_acc) an = ld_stream2(P.acc + 2 * inext);
-                if (rd_d) dn = ld_stream2(P.d + 2 * inext);
-            }
-            LbItem i0{qa.x, wa.x, va.x, aa.x, da.x}, i1{qa.y, wa.y, va.y, aa.y, da.y};
-            double2 o1 = z2, o2 = z2;
-            LbDep<K> d0, d1;
-            lb_particle<K, MODE>(P, mode, s_tab, d0, i0, o1.x, o2.x, sums, A1, A2);
-            lb_particle<K, MODE>(P, mode, s_tab, d1, i1, o1.y, o2.y, sums, A1, A2);
-            if (dep) {
-                v_deposit_commit<K, HM>(s_hist, d0);
-                v_deposit_commit<K, HM>(s_hist, d1);
-            }
-            if (wr_q) st_stream2(P.qout + 2 * i, make_double2(i0.q, i1.q));
-            if (wr_acc) st_stream2(P.acc + 2 * i, make_double2(i0.acc, i1.acc));
-            if (wr_d) st_stream2(P.d + 2 * i, make_double2(i0.d, i1.d));
-            if (wr_o1) st_stream2(P.out + 2 * i, o1);
-            if (wr_o2) st_stream2(P.out2 + 2 * i, o2);
-            qa = qn; wa = wn; va = vn; aa = an; da = dn;
-            i = inext;
-            have = hn;
-        }
-    }
-    // scalar path: whole array when VEC == 1, odd tail otherwise
-    {
-        long long i0 = VEC == 2 ? ((P.n & ~1LL) + gtid) : gtid;
-        for (long long i = i0; i < P.n; i += stride) {
-            LbItem it{P.q[i], rd_w ? P.w[i] : P.w_uniform, rd_v0 ? P.v0[i] : 0.0, rd_acc ? P.acc[i] : 0.0, rd_d ? P.d[i] : 0.0};
-            double o1 = 0.0, o2 = 0.0;
-            LbDep<K> d0;
-            lb_particle<K, MODE>(P, mode, s_tab, d0, it, o1, o2, sums, A1, A2);
-            if (dep) v_deposit_commit<K, HM>(s_hist, d0);
-            if (wr_q) P.qout[i] = it.q;
-            if (wr_acc) P.acc[i] = it.acc;
-            if (wr_d) P.d[i] = it.d;
-            if (wr_o1) P.out[i] = o1;
-            if (wr_o2) P.out2[i] = o2;
-        }
-    }
-
     if (dep) {
         __syncthreads();
         for (int b = warp; b < P.nbfull; b += kBlock / 32) {
@@ -322,6 +256,234 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
             P.red_partials[(size_t)blockIdx.x * kRedW + tid] = s;
         }
     }
+}
+
+template <int K, int MODE, int VEC, int HM>
+__global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT) ? 4 : 2) lb_pass_kernel(const LbDev P)
+{
+    extern __shared__ double smem[];
+    constexpr int TS = 2 * K - 1;
+    using Io = LbIo<MODE>;
+    const int mode = MODE >= 0 ? MODE : P.mode;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool stage = mode >= LB_STAGE1 && mode <= LB_STAGE4;
+    const bool dep = mode == LB_DEPOSIT_ONLY || stage;
+    const bool ev = mode != LB_DEPOSIT_ONLY;
+    double* s_red = smem;                        // 5 * warps
+    double* s_tab = smem + 5 * (kBlock / 32);    // ncell * TS
+    constexpr int HS = HistCfg<HM>::copies;
+    double* s_hbase = s_tab + (((P.ncell + 1) * TS + 1) & ~1);
+    double* s_hist = s_hbase + (HM == 0 ? tid : (HM == 1 ? (tid >> 5) : 0));
+
+    if (ev)   // rows 0..ncell-1 from the field kernel, ghost row ncell = 0
+        for (int i = tid; i < (P.ncell + 1) * TS; i += kBlock) s_tab[i] = i < P.ncell * TS ? P.ftab[i] : 0.0;
+    if (dep)
+        for (int i = tid; i < P.nbfull * HS; i += kBlock) s_hbase[i] = 0.0;
+    __syncthreads();
+    const double A1 = P.conservative && ev ? P.scal[0] : 0.0, A2 = P.conservative && ev ? P.scal[1] : 1.0;
+
+    double sums[5] = {0, 0, 0, 0, 0};
+    const long long stride = (long long)gridDim.x * kBlock;
+    const long long gtid = (long long)blockIdx.x * kBlock + tid;
+
+    // runtime-mode variants decide loads/stores from the mode; compile-time modes fold these
+    const bool rd_q = Io::rd_q && !(mode == LB_STAGE2 || mode == LB_STAGE3);
+    const bool rd_w = Io::rd_w && dep && !P.use_uw;
+    const bool rd_v0 = Io::rd_v0 && (mode >= LB_STAGE2 && mode <= LB_STAGE4);
+    const bool rd_a = rd_v0;
+    const bool rd_b = Io::rd_b && mode == LB_STAGE3;
+    const bool wr_q = Io::wr_q && stage && P.qout != nullptr;   // stages 1, 2 store q only for the CLB moments pass
+    const bool wr_a = Io::wr_a && (mode == LB_STAGE1 || mode == LB_STAGE3);
+    const bool wr_b = Io::wr_b && mode == LB_STAGE2;
+    const bool wr_o1 = Io::wr_o1 && (mode == LB_RHS_OUT || mode == LB_EVAL) && P.out != nullptr;
+    const bool wr_o2 = Io::wr_o2 && mode == LB_EVAL && P.out2 != nullptr;
+
+    if (VEC == 2) {
+        const long long nvec = P.n >> 1;
+        const double2 z2 = make_double2(0, 0);
+        long long i = gtid;
+        bool have = i < nvec;
+        const double2 wdef = make_double2(P.w_uniform, P.w_uniform);
+        double2 qa = z2, wa = wdef, va = z2, aa = z2, ba = z2;
+        if (have) {
+            if (rd_q) qa = ld_stream2(P.q + 2 * i);
+            if (rd_w) wa = ld_stream2(P.w + 2 * i);
+            if (rd_v0) va = ld_stream2(P.v0 + 2 * i);
+            if (rd_a) aa = ld_stream2(P.ka + 2 * i);
+            if (rd_b) ba = ld_stream2(P.kb + 2 * i);
+        }
+        while (have) {
+            const long long inext = i + stride;
+            const bool hn = inext < nvec;
+            double2 qn = z2, wn = wdef, vn = z2, an = z2, bn = z2;
+            if (hn) {
+                if (rd_q) qn = ld_stream2(P.q + 2 * inext);
+                if (rd_w) wn = ld_stream2(P.w + 2 * inext);
+                if (rd_v0) vn = ld_stream2(P.v0 + 2 * inext);
+                if (rd_a) an = ld_stream2(P.ka + 2 * inext);
+                if (rd_b) bn = ld_stream2(P.kb + 2 * inext);
+            }
+            LbItem i0{qa.x, wa.x, va.x, aa.x, ba.x}, i1{qa.y, wa.y, va.y, aa.y, ba.y};
+            double2 o1 = z2, o2 = z2;
+            LbDep<K> d0, d1;
+            lb_particle<K, MODE>(P, mode, s_tab, d0, i0, o1.x, o2.x, sums, A1, A2);
+            lb_particle<K, MODE>(P, mode, s_tab, d1, i1, o1.y, o2.y, sums, A1, A2);
+            if (dep) {
+                v_deposit_commit<K, HM>(s_hist, d0);
+                v_deposit_commit<K, HM>(s_hist, d1);
+            }
+            if (wr_q) st_stream2(P.qout + 2 * i, make_double2(i0.q, i1.q));
+            if (wr_a) st_stream2(P.ka + 2 * i, make_double2(i0.a, i1.a));
+            if (wr_b) st_stream2(P.kb + 2 * i, make_double2(i0.b, i1.b));
+            if (wr_o1) st_stream2(P.out + 2 * i, o1);
+            if (wr_o2) st_stream2(P.out2 + 2 * i, o2);
+            qa = qn; wa = wn; va = vn; aa = an; ba = bn;
+            i = inext;
+            have = hn;
+        }
+    }
+    // scalar path: whole array when VEC == 1, odd tail otherwise
+    {
+        long long i0 = VEC == 2 ? ((P.n & ~1LL) + gtid) : gtid;
+        for (long long i = i0; i < P.n; i += stride) {
+            LbItem it{rd_q ? P.q[i] : 0.0, rd_w ? P.w[i] : P.w_uniform, rd_v0 ? P.v0[i] : 0.0, rd_a ? P.ka[i] : 0.0, rd_b ? P.kb[i] : 0.0};
+            double o1 = 0.0, o2 = 0.0;
+            LbDep<K> d0;
+            lb_particle<K, MODE>(P, mode, s_tab, d0, it, o1, o2, sums, A1, A2);
+            if (dep) v_deposit_commit<K, HM>(s_hist, d0);
+            if (wr_q) P.qout[i] = it.q;
+            if (wr_a) P.ka[i] = it.a;
+            if (wr_b) P.kb[i] = it.b;
+            if (wr_o1) P.out[i] = o1;
+            if (wr_o2) P.out2[i] = o2;
+        }
+    }
+
+    lb_epilogue<HS>(P, mode, dep, s_hbase, s_red, sums);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bulk-async (TMA engine) streaming variant for the compile-time modes: every input stream of the pass
+// (q | v0 | ka | kb | w, whichever the mode reads) arrives as a 4 KB tile of 512 particles in a shared-memory
+// ring filled by 1-D cp.async.bulk copies; an mbarrier per stage tracks the bytes.  The register-prefetch
+// kernel above keeps only one trip (16 B per stream and thread) in flight, which caps the one- and
+// two-stream passes (moments, stage 1, deposit) at ~3-4 TB/s by Little's law; the ring keeps
+// stages x streams x 4 KB per CTA in flight without spending registers.  Stage count is a launch parameter
+// (P.stages, chosen by the host to fill the shared memory left beside the histograms at the target
+// occupancy).  Thread t owns particles 512 g + 2 t, 2 t + 1 of its CTA's tiles, so the summation order
+// differs from lb_pass_kernel's (results agree to rounding); every histogram copy and every reduction still
+// has a fixed order, so the result is reproducible run to run.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLbTile = 2 * kBlock;
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT) ? 4 : 2) lb_pass_tma_kernel(const LbDev P)
+{
+    static_assert(MODE >= 0, "the ring variant is specialised per mode");
+    extern __shared__ __align__(16) double smem[];
+    constexpr int TS = 2 * K - 1;
+    using Io = LbIo<MODE>;
+    constexpr bool stage = Io::stage;
+    constexpr bool dep = Io::dep;
+    constexpr bool ev = MODE != LB_DEPOSIT_ONLY;
+    // slot of every stream inside a ring stage (compile-time; the weight stream is last so that the
+    // uniform-weight variant simply drops it)
+    constexpr bool rd_q = Io::rd_q, rd_v0 = Io::rd_v0, rd_a = Io::rd_v0, rd_b = Io::rd_b;
+    constexpr int iq = 0, iv0 = iq + (rd_q ? 1 : 0), ia = iv0 + (rd_v0 ? 1 : 0), ib = ia + (rd_a ? 1 : 0), iw = ib + (rd_b ? 1 : 0);
+    const bool rd_w = Io::rd_w && !P.use_uw;
+    const int ns = iw + (rd_w ? 1 : 0);
+
+    const int tid = threadIdx.x;
+    double* s_red = smem;                        // 5 * warps
+    double* s_tab = smem + 5 * (kBlock / 32);    // ncell * TS
+    double* s_hbase = s_tab + (((P.ncell + 1) * TS + 1) & ~1);
+    double* s_hist = s_hbase + tid;
+    double* s_stage = s_hbase + (dep ? (size_t)P.nbfull * kBlock : 0);      // stages x ns x kLbTile
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + (size_t)P.stages * ns * kLbTile);
+
+    if (ev)   // rows 0..ncell-1 from the field kernel, ghost row ncell = 0
+        for (int i = tid; i < (P.ncell + 1) * TS; i += kBlock) s_tab[i] = i < P.ncell * TS ? P.ftab[i] : 0.0;
+    if (dep)
+        for (int i = tid; i < P.nbfull * kBlock; i += kBlock) s_hbase[i] = 0.0;
+    if (tid == 0) {
+        for (int s = 0; s < P.stages; s++) mbar_init(&s_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const double A1 = P.conservative && ev ? P.scal[0] : 0.0, A2 = P.conservative && ev ? P.scal[1] : 1.0;
+
+    const long long ntiles = P.n / kLbTile;
+    const uint32_t tile_bytes = kLbTile * sizeof(double);
+    auto issue = [&](int s, long long g) {
+        double* dst = s_stage + (size_t)s * ns * kLbTile;
+        const long long off = g * kLbTile;
+        mbar_expect_tx(&s_bar[s], (uint32_t)ns * tile_bytes);
+        if (rd_q) bulk_g2s(dst + iq * kLbTile, P.q + off, tile_bytes, &s_bar[s]);
+        if (rd_v0) bulk_g2s(dst + iv0 * kLbTile, P.v0 + off, tile_bytes, &s_bar[s]);
+        if (rd_a) bulk_g2s(dst + ia * kLbTile, P.ka + off, tile_bytes, &s_bar[s]);
+        if (rd_b) bulk_g2s(dst + ib * kLbTile, P.kb + off, tile_bytes, &s_bar[s]);
+        if (rd_w) bulk_g2s(dst + iw * kLbTile, P.w + off, tile_bytes, &s_bar[s]);
+    };
+    if (tid == 0)
+        for (int s = 0; s < P.stages; s++) {
+            const long long g = blockIdx.x + (long long)s * gridDim.x;
+            if (g < ntiles) issue(s, g);
+        }
+
+    const bool wr_q = Io::wr_q && stage && P.qout != nullptr;
+    const bool wr_o1 = Io::wr_o1 && P.out != nullptr;
+    const bool wr_o2 = Io::wr_o2 && P.out2 != nullptr;
+    double sums[5] = {0, 0, 0, 0, 0};
+    const double2 z2 = make_double2(0, 0), wdef = make_double2(P.w_uniform, P.w_uniform);
+    int s = 0;
+    uint32_t phase = 0;
+    for (long long g = blockIdx.x; g < ntiles; g += gridDim.x) {
+        mbar_wait(&s_bar[s], phase);
+        const double* src = s_stage + (size_t)s * ns * kLbTile + 2 * tid;
+        const double2 qa = rd_q ? *reinterpret_cast<const double2*>(src + iq * kLbTile) : z2;
+        const double2 va = rd_v0 ? *reinterpret_cast<const double2*>(src + iv0 * kLbTile) : z2;
+        const double2 aa = rd_a ? *reinterpret_cast<const double2*>(src + ia * kLbTile) : z2;
+        const double2 ba = rd_b ? *reinterpret_cast<const double2*>(src + ib * kLbTile) : z2;
+        const double2 wa = rd_w ? *reinterpret_cast<const double2*>(src + iw * kLbTile) : wdef;
+        LbItem i0{qa.x, wa.x, va.x, aa.x, ba.x}, i1{qa.y, wa.y, va.y, aa.y, ba.y};
+        double2 o1 = z2, o2 = z2;
+        LbDep<K> d0, d1;
+        lb_particle<K, MODE>(P, MODE, s_tab, d0, i0, o1.x, o2.x, sums, A1, A2);
+        lb_particle<K, MODE>(P, MODE, s_tab, d1, i1, o1.y, o2.y, sums, A1, A2);
+        if (dep) {
+            v_deposit_commit<K, 0>(s_hist, d0);
+            v_deposit_commit<K, 0>(s_hist, d1);
+        }
+        const long long i = g * kLbTile + 2 * tid;
+        if (wr_q) st_stream2(P.qout + i, make_double2(i0.q, i1.q));
+        if (Io::wr_a) st_stream2(P.ka + i, make_double2(i0.a, i1.a));
+        if (Io::wr_b) st_stream2(P.kb + i, make_double2(i0.b, i1.b));
+        if (wr_o1) st_stream2(P.out + i, o1);
+        if (wr_o2) st_stream2(P.out2 + i, o2);
+        __syncthreads();  // every thread has read stage s: hand it back to the copy engine
+        if (tid == 0) {
+            const long long gn = g + (long long)P.stages * gridDim.x;
+            if (gn < ntiles) issue(s, gn);
+        }
+        if (++s == P.stages) {
+            s = 0;
+            phase ^= 1u;
+        }
+    }
+    // remainder (< one tile): plain loads, spread over the grid
+    for (long long i = ntiles * kLbTile + (long long)blockIdx.x * kBlock + tid; i < P.n; i += (long long)gridDim.x * kBlock) {
+        LbItem it{rd_q ? P.q[i] : 0.0, rd_w ? P.w[i] : P.w_uniform, rd_v0 ? P.v0[i] : 0.0, rd_a ? P.ka[i] : 0.0, rd_b ? P.kb[i] : 0.0};
+        double o1 = 0.0, o2 = 0.0;
+        LbDep<K> d0;
+        lb_particle<K, MODE>(P, MODE, s_tab, d0, it, o1, o2, sums, A1, A2);
+        if (dep) v_deposit_commit<K, 0>(s_hist, d0);
+        if (wr_q) P.qout[i] = it.q;
+        if (Io::wr_a) P.ka[i] = it.a;
+        if (Io::wr_b) P.kb[i] = it.b;
+        if (wr_o1) P.out[i] = o1;
+        if (wr_o2) P.out2[i] = o2;
+    }
+    lb_epilogue<kBlock>(P, MODE, dep, s_hbase, s_red, sums);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -438,7 +600,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
     constexpr int TS = 2 * K - 1;
     LbDev P{};
     P.mode = p.mode;
-    P.q = p.q; P.w = p.w; P.v0 = p.v0; P.acc = p.acc; P.d = p.d; P.qout = p.qout; P.out = p.out; P.out2 = p.out2;
+    P.q = p.q; P.w = p.w; P.v0 = p.v0; P.ka = p.ka; P.kb = p.kb; P.qout = p.qout; P.out = p.out; P.out2 = p.out2;
     P.n = p.n; P.nu = p.nu; P.dt = p.dt; P.conservative = p.conservative; P.diag = p.diag;
     P.lo = vs->lo; P.hi = vs->hi; P.invh = vs->invh; P.ncell = vs->ncell; P.nbfull = vs->nbfull;
     P.ftab = vs->ftab; P.scal = vs->scal; P.pieces = vs->pieces;
@@ -447,7 +609,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
 
     const bool stage = p.mode >= LB_STAGE1 && p.mode <= LB_STAGE4;
     const bool dep = p.mode == LB_DEPOSIT_ONLY || stage;
-    const size_t base = sizeof(double) * (5 * (kBlock / 32) + ((vs->ncell * TS + 1) & ~1));
+    const size_t base = sizeof(double) * (5 * (kBlock / 32) + (((vs->ncell + 1) * TS + 1) & ~1));
     int hm = 0;
     if (dep) {
         if (base + sizeof(double) * (size_t)vs->nbfull * kBlock > ctx->smem_optin) hm = 1;  // shared-memory CAS atomics are ~5x slower
@@ -458,16 +620,52 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
         if (f > hm && f <= 2 && dep) hm = f;
     }
     const size_t copies = hm == 0 ? kBlock : (hm == 1 ? kBlock / 32 : 1);
-    const size_t smem = base + (dep ? sizeof(double) * (size_t)vs->nbfull * copies : 0);
-    if (smem > ctx->smem_optin)
+    const size_t smem_reg = base + (dep ? sizeof(double) * (size_t)vs->nbfull * copies : 0);
+    if (smem_reg > ctx->smem_optin)
         return fail(VPM_ERR_UNSUPPORTED, "v-space too large: the f/f' table and one histogram copy must fit in shared memory");
 
     auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    const bool vec = al(p.q) && al(p.w) && al(p.v0) && al(p.acc) && al(p.d) && al(p.qout) && al(p.out) && al(p.out2);
+    const bool vec = al(p.q) && al(p.w) && al(p.v0) && al(p.ka) && al(p.kb) && al(p.qout) && al(p.out) && al(p.out2);
 
     void (*kern)(const LbDev) = nullptr;
     if (p.mode < LB_DEPOSIT_ONLY || p.mode > LB_EVAL) return fail(VPM_ERR_INVALID, "bad LB pass mode");
-    if (hm == 1) kern = vec ? lb_pass_kernel<K, -1, 2, 1> : lb_pass_kernel<K, -1, 1, 1>;
+
+    // TMA ring variant: size the ring to the shared memory left at the kernel's target occupancy
+    // (2 CTAs/SM beside the histograms, 4 CTAs/SM for the gather-only modes); needs >= 2 stages to pay.
+    int tune_tma = -1;   // test / tuning hook. 0: register-prefetch kernel everywhere; bit m+1 set: ring for mode m
+    if (const char* e = getenv("VPM_TUNE_LBTMA")) tune_tma = atoi(e);
+    size_t smem = smem_reg;
+    bool tma = false;
+    if (hm == 0 && vec && p.n >= kLbTile && tune_tma != 0 && (tune_tma < 0 || ((tune_tma >> (p.mode + 1)) & 1))) {
+        const bool st = p.mode >= LB_STAGE1 && p.mode <= LB_STAGE4;
+        int ns = 0;
+        if (!(p.mode == LB_STAGE2 || p.mode == LB_STAGE3)) ns++;                 // q
+        if (p.mode >= LB_STAGE2 && p.mode <= LB_STAGE4) ns += 2;                 // v0, ka
+        if (p.mode == LB_STAGE3) ns++;                                           // kb
+        if ((st || p.mode == LB_DEPOSIT_ONLY) && !p.use_uw) ns++;                // w
+        const int target = dep ? 2 : 4;
+        const size_t per_cta = ctx->smem_sm / target - ctx->smem_reserved;
+        const size_t stage_bytes = (size_t)ns * kLbTile * sizeof(double);
+        const size_t fixed = smem_reg + 8 * sizeof(uint64_t);
+        int stages = per_cta > fixed ? (int)((per_cta - fixed) / stage_bytes) : 0;
+        if (stages > 6) stages = 6;
+        if (stages >= 2) {
+            tma = true;
+            P.stages = stages;
+            smem = smem_reg + (size_t)stages * stage_bytes + (size_t)stages * sizeof(uint64_t);
+        }
+    }
+    if (tma) switch (p.mode) {
+        case LB_DEPOSIT_ONLY: kern = lb_pass_tma_kernel<K, LB_DEPOSIT_ONLY>; break;
+        case LB_STAGE1: kern = lb_pass_tma_kernel<K, LB_STAGE1>; break;
+        case LB_STAGE2: kern = lb_pass_tma_kernel<K, LB_STAGE2>; break;
+        case LB_STAGE3: kern = lb_pass_tma_kernel<K, LB_STAGE3>; break;
+        case LB_STAGE4: kern = lb_pass_tma_kernel<K, LB_STAGE4>; break;
+        case LB_RHS_OUT: kern = lb_pass_tma_kernel<K, LB_RHS_OUT>; break;
+        case LB_MOMENTS: kern = lb_pass_tma_kernel<K, LB_MOMENTS>; break;
+        case LB_EVAL: kern = lb_pass_tma_kernel<K, LB_EVAL>; break;
+    }
+    else if (hm == 1) kern = vec ? lb_pass_kernel<K, -1, 2, 1> : lb_pass_kernel<K, -1, 1, 1>;
     else if (hm == 2) kern = vec ? lb_pass_kernel<K, -1, 2, 2> : lb_pass_kernel<K, -1, 1, 2>;
     else if (!vec) kern = lb_pass_kernel<K, -1, 1, 0>;
     else switch (p.mode) {
@@ -486,7 +684,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
         if (rc_occ) return rc_occ;
     }
     if (occ < 1) return fail(VPM_ERR_UNSUPPORTED, "lb pass kernel does not fit on an SM");
-    long long want = (p.n / (vec ? 2 : 1) + kBlock - 1) / kBlock;
+    long long want = tma ? (p.n + kLbTile - 1) / kLbTile : (p.n / (vec ? 2 : 1) + kBlock - 1) / kBlock;
     if (want < 1) want = 1;
     long long grid = (long long)ctx->sm_count * occ;
     if (grid > want) grid = want;

@@ -49,7 +49,9 @@ struct vpm_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
-    size_t smem_optin = 0;
+    size_t smem_optin = 0;      // largest dynamic shared memory one CTA may opt into
+    size_t smem_sm = 0;         // shared memory of one SM
+    size_t smem_reserved = 1024; // per-CTA reservation the occupancy calculation adds
     // per-CTA partial sums written by the particle passes, reduced in fixed order by the field kernels
     double* partials = nullptr;
     size_t partials_cap = 0;   // doubles
@@ -74,8 +76,8 @@ struct vpm_particles {
     vpm_ctx* ctx = nullptr;
     int64_t n = 0;
     double *x = nullptr, *v = nullptr, *w = nullptr;
-    // RK438 scratch (allocated on first LB use)
-    double *q = nullptr, *acc = nullptr, *d = nullptr;
+    // RK438 scratch (allocated on first LB use): stage input q, stored derivatives ka, kb
+    double *q = nullptr, *ka = nullptr, *kb = nullptr;
     // uniform-weight fast path (vpm_particles_set_uniform_weight): the steppers skip the w[] stream
     bool uw = false;
     double wu = 0.0;
@@ -178,8 +180,9 @@ enum LbMode : int {
 
 struct LbPass {
     int mode;
-    const double *q, *w, *v0;
-    double *acc, *d, *qout, *out, *out2;
+    const double *q, *w, *v0;   // q: pass input (stages 1, 4 and the operator modes); v0: step start (stages 2-4)
+    double *ka, *kb;            // stored stage derivatives: ka = k1 (stage 3 overwrites it with k1+3k2+3k3), kb = k2
+    double *qout, *out, *out2;  // qout: next stage input (stage 3: q4, stage 4: v; stages 1, 2 only if non-null)
     int64_t n;
     double nu, dt;
     int conservative;
