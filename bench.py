@@ -204,8 +204,8 @@ def main():
 
         def run_steps(k):
             vpm.check(lib.vpm_lb_rk438_steps_async(sd._h, d._h, 1.0, 1e-2, int(k), int(cons)))
-        # RK438 particle-step in k form: stage passes 24+32+48+40 B (CLB: +8 B q stores in stages 1, 2 and 4 x 8 B moment passes), DESIGN.md
-        kind_pass, bytes_unit, wl = 2, (144 + (48 if cons else 0)), ("clb" if cons else "lb") + "_rk438_double_maxwellian"
+        # RK438 particle-step in k form: stage passes 24+32+48+32 B (CLB: +8 B q stores in stages 1, 2 and 4 x 8 B moment passes), DESIGN.md
+        kind_pass, bytes_unit, wl = 2, (136 + (48 if cons else 0)), ("clb" if cons else "lb") + "_rk438_double_maxwellian"
         passes_per_call = lambda k: 4 * k * (2 if cons else 1) + 1
 
     # ---- warm-up, then the timed region ----

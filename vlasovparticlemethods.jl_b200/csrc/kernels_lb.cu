@@ -44,32 +44,51 @@ struct LbDev {
     double* red_partials;
     double w_uniform;
     int use_uw;
-    int stages;   // ring depth of lb_pass_tma_kernel
+    int stages;   // ring depth of lb_pass_ring_kernel
+    int w_direct; // ring kernel: the weight stream bypasses the ring (register prefetch) so that a second stage fits
 };
 
 constexpr int kRedW = 8;  // doubles per CTA row of scalar partial sums
 
+// Shared-memory copy of the per-cell table: only the K monomial coefficients of f (the coefficients of f' are
+// m f_m / h and are formed in registers: the passes are co-limited by shared-memory wavefronts, and 4 loaded
+// doubles instead of 7 per evaluation is worth the three extra fp64 multiplies).  Row stride: even, so that a
+// row is read with 16-byte loads, with an odd number of 16-byte units so that the rows of 8 consecutive cells
+// tile all 32 banks (K = 4: 6 doubles).
+template <int K>
+struct TabCfg {
+    static constexpr int TS = 2 * K - 1;                                   // row stride of the global table (f then f')
+    static constexpr int even = (K + 1) & ~1;
+    static constexpr int TSP = ((even / 2) & 1) ? even : even + 2;         // padded shared-memory row stride
+    static constexpr int NV2 = (K + 1) / 2;                                // double2 loads per row
+};
+
 // Cell index and local coordinate of q on the clamped grid.  Fast path (0 <= t < ncell, t = (q - lo) / h): one
 // round-toward-zero fma against 2^52 leaves floor(t) in the low mantissa word, so ci and u = t - ci cost four
 // fp64 instructions and no conversions or selects.  Everything else -- q == hi (last cell, u = 1), particles
-// outside the domain, NaN -- is detected from the bit pattern of the sum and takes the rare slow path;
-// outside particles are sent to the GHOST cell ncell, whose f / f' table row is zero (Spline evaluation is
-// zero outside the knots) and which deposits nothing.
-template <int K>
-__device__ __forceinline__ bool v_locate(const LbDev& P, double q, int& ci, double& u)
+// outside the domain, NaN -- is detected from the bit pattern of the sum (return value true) and fixed by
+// v_locate_fix on a rare, shared slow path; outside particles are sent to the GHOST cell ncell, whose f / f'
+// table row is zero (Spline evaluation is zero outside the knots) and which deposits nothing.
+__device__ __forceinline__ bool v_locate_fast(const LbDev& P, double q, int& ci, double& u)
 {
     const double M = 4503599627370496.0;  // 2^52
     const double t0 = q - P.lo;
     const double tm = __fma_rz(t0, P.invh, M);
     ci = __double2loint(tm);
     u = fma(t0, P.invh, -(tm - M));
-    if (__double2hiint(tm) != 0x43300000 || (unsigned)ci >= (unsigned)P.ncell) {
-        const bool inside = (q >= P.lo) && (q <= P.hi);  // NaN -> outside
-        ci = inside ? P.ncell - 1 : P.ncell;
-        u = inside ? fma(t0, P.invh, -(double)(P.ncell - 1)) : 0.0;
-        return inside;
-    }
-    return true;
+    return __double2hiint(tm) != 0x43300000 || (unsigned)ci >= (unsigned)P.ncell;
+}
+
+// returns whether q lies inside [lo, hi]; leaves (ci, u) of a particle that did not need fixing untouched
+__device__ __forceinline__ bool v_locate_fix(const LbDev& P, double q, int& ci, double& u)
+{
+    int c;
+    double uu;
+    if (!v_locate_fast(P, q, c, uu)) return true;
+    const bool inside = (q >= P.lo) && (q <= P.hi);  // NaN -> outside
+    ci = inside ? P.ncell - 1 : P.ncell;
+    u = inside ? fma(q - P.lo, P.invh, -(double)(P.ncell - 1)) : 0.0;
+    return inside;
 }
 
 template <int HM>
@@ -77,69 +96,8 @@ struct HistCfg {
     static constexpr int copies = HM == 0 ? kBlock : (HM == 1 ? kBlock / 32 : 1);
 };
 
-// Deposit in two halves so that the pair loop can finish the arithmetic of both particles before the
-// (ordered) shared-memory read-modify-writes: prepare = locate + basis, commit = K fused multiply-add RMWs.
-template <int K>
-struct LbDep {
-    int ci;
-    bool on;
-    double w;
-    double b[K];
-};
-
-template <int K>
-__device__ __forceinline__ void v_deposit_prepare(const LbDev& P, double q, double w, LbDep<K>& d)
-{
-    double u;
-    d.w = w;
-    d.on = v_locate<K>(P, q, d.ci, u);  // out-of-domain particles deposit nothing
-    if (d.ci >= K - 1 && d.ci <= P.ncell - K) {
-        basis_uniform<K>(u, d.b);
-    } else if (d.on) {  // the K-1 cells at either end feel the repeated knots: per-cell table
-        const double* pc = P.pieces + (size_t)d.ci * K * K;
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            double r = __ldg(pc + j * K + K - 1);
-#pragma unroll
-            for (int m = K - 2; m >= 0; m--) r = fma(r, u, __ldg(pc + j * K + m));
-            d.b[j] = r;
-        }
-    }
-}
-
-template <int K, int HM>
-__device__ __forceinline__ void v_deposit_commit(double* __restrict__ s_hist, const LbDep<K>& d)
-{
-    if (!d.on) return;
-    constexpr int HS = HistCfg<HM>::copies;
-    double* hcell = s_hist + d.ci * HS;
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-        if (HM == 0) hcell[j * HS] = fma(d.b[j], d.w, hcell[j * HS]);
-        else atomicAdd(hcell + j * HS, d.b[j] * d.w);
-    }
-}
-
-template <int K>
-__device__ __forceinline__ void v_eval(const LbDev& P, const double* __restrict__ s_tab, double q, double& f, double& df)
-{
-    constexpr int TS = 2 * K - 1;
-    int ci;
-    double u;
-    v_locate<K>(P, q, ci, u);   // outside particles read the zero row of the ghost cell
-    const double* e = s_tab + ci * TS;
-    double a = e[K - 1];
-#pragma unroll
-    for (int m = K - 2; m >= 0; m--) a = fma(a, u, e[m]);
-    double g = e[2 * K - 2];
-#pragma unroll
-    for (int m = K - 3; m >= 0; m--) g = fma(g, u, e[K + m]);
-    f = a;
-    df = g;
-}
-
 struct LbItem {
-    double q, w, v0, a, b;   // a, b: the stored stage derivatives (k1 | acc, k2)
+    double q, w, v0, a, b;   // a, b: the stored stage vectors (k1 | v0 + dt (k1+3k2+3k3)/8, k2)
 };
 
 // RK438 stage inputs (GeometricIntegrators tableau: a21 = 1/3; a31 = -1/3, a32 = 1; a41 = 1, a42 = -1, a43 = 1).
@@ -148,66 +106,152 @@ __device__ __forceinline__ double rk_q2(double v0, double k1, double dt) { retur
 __device__ __forceinline__ double rk_q3(double v0, double k1, double k2, double dt) { return fma(dt, fma(-k1, 1.0 / 3.0, k2), v0); }
 __device__ __forceinline__ double rk_q4(double v0, double k1, double k2, double k3, double dt) { return fma(dt, (k1 - k2) + k3, v0); }
 
-template <int K, int MODE>
-__device__ __forceinline__ void lb_particle(const LbDev& P, const int mode_rt, const double* __restrict__ s_tab,
-                                            LbDep<K>& dep, LbItem& it, double& o1, double& o2,
-                                            double (&sums)[5], const double A1, const double A2)
+// One group of NP particles of one thread through a pass.  The work is arranged in PHASES over the whole group
+// (locate all, table rows of all, Horner of all, ..., commit in order) and the rare cases (domain ends,
+// out-of-domain particles, the K-1 cells at either end that feel the repeated knots) are detected for the
+// group as a whole and repaired on one shared slow path, so that the common path is a single straight-line
+// block in which the compiler can interleave the particles' dependent fp64 chains.
+template <int K, int MODE, int HM, int NP>
+__device__ __forceinline__ void lb_group(const LbDev& P, const int mode_rt, const double* __restrict__ s_tab, double* __restrict__ s_hist,
+                                         LbItem (&it)[NP], double (&o1)[NP], double (&o2)[NP], double (&sums)[5], const double A1,
+                                         const double A2)
 {
+    constexpr int TSP = TabCfg<K>::TSP, NV2 = TabCfg<K>::NV2;
+    constexpr int HS = HistCfg<HM>::copies;
     const int mode = MODE >= 0 ? MODE : mode_rt;
-    dep.on = false;
+    int ci[NP];
+    double u[NP], qn[NP];
     if (mode == LB_DEPOSIT_ONLY) {
-        v_deposit_prepare<K>(P, it.q, it.w, dep);
-        if (P.diag) {
-            sums[0] += it.q;
-            sums[1] = fma(it.q, it.q, sums[1]);
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            qn[p] = it[p].q;
+            if (P.diag) {
+                sums[0] += qn[p];
+                sums[1] = fma(qn[p], qn[p], sums[1]);
+            }
         }
-        return;
+    } else {
+        // the stage input: stages 2 and 3 recompute it from v0 and the stored derivatives
+        double qe[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            qe[p] = it[p].q;
+            if (mode == LB_STAGE1) it[p].v0 = it[p].q;
+            if (mode == LB_STAGE2) qe[p] = rk_q2(it[p].v0, it[p].a, P.dt);
+            if (mode == LB_STAGE3) qe[p] = rk_q3(it[p].v0, it[p].a, it[p].b, P.dt);
+        }
+        bool slow = false;
+#pragma unroll
+        for (int p = 0; p < NP; p++) slow |= v_locate_fast(P, qe[p], ci[p], u[p]);
+        if (slow) {
+#pragma unroll
+            for (int p = 0; p < NP; p++) v_locate_fix(P, qe[p], ci[p], u[p]);  // outside -> zero row of the ghost cell
+        }
+        double f[NP], df[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            const double2* e2 = reinterpret_cast<const double2*>(s_tab + ci[p] * TSP);
+            double e[2 * NV2];
+#pragma unroll
+            for (int i = 0; i < NV2; i++) {
+                const double2 t = e2[i];
+                e[2 * i] = t.x;
+                e[2 * i + 1] = t.y;
+            }
+            double a = e[K - 1];
+#pragma unroll
+            for (int m = K - 2; m >= 0; m--) a = fma(a, u[p], e[m]);
+            double g = (double)(K - 1) * e[K - 1];   // f'(u) h = sum_m m f_m u^(m-1)
+#pragma unroll
+            for (int m = K - 2; m >= 1; m--) g = fma(g, u[p], (double)m * e[m]);
+            g *= P.invh;
+            f[p] = a;
+            df[p] = g;
+        }
+        if (mode == LB_EVAL) {
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                o1[p] = f[p];
+                o2[p] = df[p];
+            }
+            return;
+        }
+        if (mode == LB_MOMENTS) {
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                sums[0] += f[p];
+                sums[1] = fma(qe[p], f[p], sums[1]);
+                sums[2] = fma(qe[p] * qe[p], f[p], sums[2]);
+                sums[3] += df[p];
+                sums[4] = fma(qe[p], df[p], sums[4]);
+            }
+            return;
+        }
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            // LB: vdot = -nu (f' + v f)    CLB: vdot = -nu (f' + (A1 + A2 v) f)    (A1 = 0, A2 = 1 for the plain model)
+            const double k = -P.nu * fma(fma(A2, qe[p], A1), f[p], df[p]);
+            if (mode == LB_RHS_OUT) {
+                o1[p] = k;
+            } else if (mode == LB_STAGE1) {   // q2 = v0 + dt (k1/3)
+                qn[p] = rk_q2(it[p].v0, k, P.dt);
+                it[p].a = k;
+            } else if (mode == LB_STAGE2) {   // q3 = v0 + dt (-k1/3 + k2)
+                qn[p] = rk_q3(it[p].v0, it[p].a, k, P.dt);
+                it[p].b = k;
+            } else if (mode == LB_STAGE3) {   // q4 = v0 + dt (k1 - k2 + k3);  a <- v0 + dt (k1 + 3 k2 + 3 k3)/8
+                qn[p] = rk_q4(it[p].v0, it[p].a, it[p].b, k, P.dt);
+                it[p].a = fma(P.dt, fma(3.0, k, fma(3.0, it[p].b, it[p].a)) * 0.125, it[p].v0);
+            } else {                          // v1 = v0 + dt (k1 + 3 k2 + 3 k3 + k4)/8 = a + dt k4/8
+                qn[p] = fma(P.dt, k * 0.125, it[p].a);
+                if (P.diag) {
+                    sums[0] += qn[p];
+                    sums[1] = fma(qn[p], qn[p], sums[1]);
+                }
+            }
+            it[p].q = qn[p];
+        }
+        if (mode == LB_RHS_OUT) return;
     }
-    // the stage input: stages 2 and 3 recompute it from v0 and the stored derivatives
-    double qe = it.q;
-    if (mode == LB_STAGE1) it.v0 = it.q;
-    if (mode == LB_STAGE2) qe = rk_q2(it.v0, it.a, P.dt);
-    if (mode == LB_STAGE3) qe = rk_q3(it.v0, it.a, it.b, P.dt);
-    double f, df;
-    v_eval<K>(P, s_tab, qe, f, df);
-    if (mode == LB_EVAL) {
-        o1 = f;
-        o2 = df;
-        return;
+
+    // deposit w B_j(qn) into this thread's histogram copy
+    bool edge = false;
+#pragma unroll
+    for (int p = 0; p < NP; p++) edge |= v_locate_fast(P, qn[p], ci[p], u[p]);
+    double b[NP][K];
+    bool on[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        basis_uniform<K>(u[p], b[p]);
+        on[p] = true;
+        edge |= (ci[p] < K - 1) | (ci[p] > P.ncell - K);
     }
-    if (mode == LB_MOMENTS) {
-        sums[0] += f;
-        sums[1] = fma(qe, f, sums[1]);
-        sums[2] = fma(qe * qe, f, sums[2]);
-        sums[3] += df;
-        sums[4] = fma(qe, df, sums[4]);
-        return;
-    }
-    // LB: vdot = -nu (f' + v f)    CLB: vdot = -nu (f' + (A1 + A2 v) f)
-    const double k = -P.nu * fma(fma(A2, qe, A1), f, df);   // A1 = 0, A2 = 1 for the plain model
-    if (mode == LB_RHS_OUT) {
-        o1 = k;
-        return;
-    }
-    double qn;
-    if (mode == LB_STAGE1) {          // q2 = v0 + dt (k1/3)
-        qn = rk_q2(it.v0, k, P.dt);
-        it.a = k;
-    } else if (mode == LB_STAGE2) {   // q3 = v0 + dt (-k1/3 + k2)
-        qn = rk_q3(it.v0, it.a, k, P.dt);
-        it.b = k;
-    } else if (mode == LB_STAGE3) {   // q4 = v0 + dt (k1 - k2 + k3);  acc = k1 + 3 k2 + 3 k3
-        qn = rk_q4(it.v0, it.a, it.b, k, P.dt);
-        it.a = fma(3.0, k, fma(3.0, it.b, it.a));
-    } else {                          // v1 = v0 + dt (k1 + 3 k2 + 3 k3 + k4)/8
-        qn = fma(P.dt, (it.a + k) * 0.125, it.v0);
-        if (P.diag) {
-            sums[0] += qn;
-            sums[1] = fma(qn, qn, sums[1]);
+    if (edge) {
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            on[p] = v_locate_fix(P, qn[p], ci[p], u[p]);   // out-of-domain particles deposit nothing
+            if (on[p] && (ci[p] < K - 1 || ci[p] > P.ncell - K)) {  // repeated end knots: per-cell table
+                const double* pc = P.pieces + (size_t)ci[p] * K * K;
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    double r = __ldg(pc + j * K + K - 1);
+#pragma unroll
+                    for (int m = K - 2; m >= 0; m--) r = fma(r, u[p], __ldg(pc + j * K + m));
+                    b[p][j] = r;
+                }
+            }
         }
     }
-    it.q = qn;
-    v_deposit_prepare<K>(P, qn, it.w, dep);
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        if (!on[p]) continue;
+        double* hcell = s_hist + ci[p] * HS;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            if (HM == 0) hcell[j * HS] = fma(b[p][j], it[p].w, hcell[j * HS]);
+            else atomicAdd(hcell + j * HS, b[p][j] * it[p].w);
+        }
+    }
 }
 
 template <int MODE>
@@ -217,7 +261,8 @@ struct LbIo {
     static constexpr bool dep = rt || MODE == LB_DEPOSIT_ONLY || stage;
     static constexpr bool rd_q = rt || !(MODE == LB_STAGE2 || MODE == LB_STAGE3);
     static constexpr bool rd_w = dep;
-    static constexpr bool rd_v0 = rt || MODE == LB_STAGE2 || MODE == LB_STAGE3 || MODE == LB_STAGE4;
+    static constexpr bool rd_v0 = rt || MODE == LB_STAGE2 || MODE == LB_STAGE3;
+    static constexpr bool rd_a = rt || MODE == LB_STAGE2 || MODE == LB_STAGE3 || MODE == LB_STAGE4;
     static constexpr bool rd_b = rt || MODE == LB_STAGE3;
     static constexpr bool wr_q = rt || stage;
     static constexpr bool wr_a = rt || MODE == LB_STAGE1 || MODE == LB_STAGE3;
@@ -226,14 +271,32 @@ struct LbIo {
     static constexpr bool wr_o2 = rt || MODE == LB_EVAL;
 };
 
+template <bool NAMED>
+__device__ __forceinline__ void lb_cta_sync()
+{
+    if (NAMED) asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");   // the kBlock worker threads of a ring CTA
+    else __syncthreads();
+}
+
+// stage the f rows of the table in shared memory with the padded row stride; ghost row ncell = 0
+template <int K>
+__device__ __forceinline__ void lb_stage_table(const LbDev& P, double* __restrict__ s_tab, int tid, int nthreads)
+{
+    constexpr int TS = TabCfg<K>::TS, TSP = TabCfg<K>::TSP;
+    for (int i = tid; i < (P.ncell + 1) * TSP; i += nthreads) {
+        const int r = i / TSP, m = i - r * TSP;
+        s_tab[i] = (r < P.ncell && m < K) ? P.ftab[r * TS + m] : 0.0;
+    }
+}
+
 // Fixed-order reduction of the CTA's private histograms into one partial row, and of the scalar sums.
-template <int HS>
+template <int HS, bool NAMED>
 __device__ __forceinline__ void lb_epilogue(const LbDev& P, const int mode, const bool dep, const double* __restrict__ s_hbase,
                                             double* __restrict__ s_red, double (&sums)[5])
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (dep) {
-        __syncthreads();
+        lb_cta_sync<NAMED>();
         for (int b = warp; b < P.nbfull; b += kBlock / 32) {
             double s = 0.0;
 #pragma unroll
@@ -249,7 +312,7 @@ __device__ __forceinline__ void lb_epilogue(const LbDev& P, const int mode, cons
             const double s = warp_sum(sums[k]);
             if (lane == 0) s_red[5 * warp + k] = s;
         }
-        __syncthreads();
+        lb_cta_sync<NAMED>();
         if (tid < nsum) {
             double s = 0.0;
             for (int wi = 0; wi < kBlock / 32; wi++) s += s_red[5 * wi + tid];
@@ -261,22 +324,20 @@ __device__ __forceinline__ void lb_epilogue(const LbDev& P, const int mode, cons
 template <int K, int MODE, int VEC, int HM>
 __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT) ? 4 : 2) lb_pass_kernel(const LbDev P)
 {
-    extern __shared__ double smem[];
-    constexpr int TS = 2 * K - 1;
+    extern __shared__ __align__(16) double smem[];
     using Io = LbIo<MODE>;
     const int mode = MODE >= 0 ? MODE : P.mode;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const bool stage = mode >= LB_STAGE1 && mode <= LB_STAGE4;
     const bool dep = mode == LB_DEPOSIT_ONLY || stage;
     const bool ev = mode != LB_DEPOSIT_ONLY;
     double* s_red = smem;                        // 5 * warps
-    double* s_tab = smem + 5 * (kBlock / 32);    // ncell * TS
+    double* s_tab = smem + 5 * (kBlock / 32);    // (ncell + 1) * TSP
     constexpr int HS = HistCfg<HM>::copies;
-    double* s_hbase = s_tab + (((P.ncell + 1) * TS + 1) & ~1);
+    double* s_hbase = s_tab + (P.ncell + 1) * TabCfg<K>::TSP;
     double* s_hist = s_hbase + (HM == 0 ? tid : (HM == 1 ? (tid >> 5) : 0));
 
-    if (ev)   // rows 0..ncell-1 from the field kernel, ghost row ncell = 0
-        for (int i = tid; i < (P.ncell + 1) * TS; i += kBlock) s_tab[i] = i < P.ncell * TS ? P.ftab[i] : 0.0;
+    if (ev) lb_stage_table<K>(P, s_tab, tid, kBlock);
     if (dep)
         for (int i = tid; i < P.nbfull * HS; i += kBlock) s_hbase[i] = 0.0;
     __syncthreads();
@@ -289,8 +350,8 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
     // runtime-mode variants decide loads/stores from the mode; compile-time modes fold these
     const bool rd_q = Io::rd_q && !(mode == LB_STAGE2 || mode == LB_STAGE3);
     const bool rd_w = Io::rd_w && dep && !P.use_uw;
-    const bool rd_v0 = Io::rd_v0 && (mode >= LB_STAGE2 && mode <= LB_STAGE4);
-    const bool rd_a = rd_v0;
+    const bool rd_v0 = Io::rd_v0 && (mode == LB_STAGE2 || mode == LB_STAGE3);
+    const bool rd_a = Io::rd_a && (mode >= LB_STAGE2 && mode <= LB_STAGE4);
     const bool rd_b = Io::rd_b && mode == LB_STAGE3;
     const bool wr_q = Io::wr_q && stage && P.qout != nullptr;   // stages 1, 2 store q only for the CLB moments pass
     const bool wr_a = Io::wr_a && (mode == LB_STAGE1 || mode == LB_STAGE3);
@@ -323,20 +384,14 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
                 if (rd_a) an = ld_stream2(P.ka + 2 * inext);
                 if (rd_b) bn = ld_stream2(P.kb + 2 * inext);
             }
-            LbItem i0{qa.x, wa.x, va.x, aa.x, ba.x}, i1{qa.y, wa.y, va.y, aa.y, ba.y};
-            double2 o1 = z2, o2 = z2;
-            LbDep<K> d0, d1;
-            lb_particle<K, MODE>(P, mode, s_tab, d0, i0, o1.x, o2.x, sums, A1, A2);
-            lb_particle<K, MODE>(P, mode, s_tab, d1, i1, o1.y, o2.y, sums, A1, A2);
-            if (dep) {
-                v_deposit_commit<K, HM>(s_hist, d0);
-                v_deposit_commit<K, HM>(s_hist, d1);
-            }
-            if (wr_q) st_stream2(P.qout + 2 * i, make_double2(i0.q, i1.q));
-            if (wr_a) st_stream2(P.ka + 2 * i, make_double2(i0.a, i1.a));
-            if (wr_b) st_stream2(P.kb + 2 * i, make_double2(i0.b, i1.b));
-            if (wr_o1) st_stream2(P.out + 2 * i, o1);
-            if (wr_o2) st_stream2(P.out2 + 2 * i, o2);
+            LbItem it[2] = {{qa.x, wa.x, va.x, aa.x, ba.x}, {qa.y, wa.y, va.y, aa.y, ba.y}};
+            double o1[2] = {0.0, 0.0}, o2[2] = {0.0, 0.0};
+            lb_group<K, MODE, HM, 2>(P, mode, s_tab, s_hist, it, o1, o2, sums, A1, A2);
+            if (wr_q) st_stream2(P.qout + 2 * i, make_double2(it[0].q, it[1].q));
+            if (wr_a) st_stream2(P.ka + 2 * i, make_double2(it[0].a, it[1].a));
+            if (wr_b) st_stream2(P.kb + 2 * i, make_double2(it[0].b, it[1].b));
+            if (wr_o1) st_stream2(P.out + 2 * i, make_double2(o1[0], o1[1]));
+            if (wr_o2) st_stream2(P.out2 + 2 * i, make_double2(o2[0], o2[1]));
             qa = qn; wa = wn; va = vn; aa = an; ba = bn;
             i = inext;
             have = hn;
@@ -346,90 +401,102 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
     {
         long long i0 = VEC == 2 ? ((P.n & ~1LL) + gtid) : gtid;
         for (long long i = i0; i < P.n; i += stride) {
-            LbItem it{rd_q ? P.q[i] : 0.0, rd_w ? P.w[i] : P.w_uniform, rd_v0 ? P.v0[i] : 0.0, rd_a ? P.ka[i] : 0.0, rd_b ? P.kb[i] : 0.0};
-            double o1 = 0.0, o2 = 0.0;
-            LbDep<K> d0;
-            lb_particle<K, MODE>(P, mode, s_tab, d0, it, o1, o2, sums, A1, A2);
-            if (dep) v_deposit_commit<K, HM>(s_hist, d0);
-            if (wr_q) P.qout[i] = it.q;
-            if (wr_a) P.ka[i] = it.a;
-            if (wr_b) P.kb[i] = it.b;
-            if (wr_o1) P.out[i] = o1;
-            if (wr_o2) P.out2[i] = o2;
+            LbItem it[1] = {{rd_q ? P.q[i] : 0.0, rd_w ? P.w[i] : P.w_uniform, rd_v0 ? P.v0[i] : 0.0, rd_a ? P.ka[i] : 0.0, rd_b ? P.kb[i] : 0.0}};
+            double o1[1] = {0.0}, o2[1] = {0.0};
+            lb_group<K, MODE, HM, 1>(P, mode, s_tab, s_hist, it, o1, o2, sums, A1, A2);
+            if (wr_q) P.qout[i] = it[0].q;
+            if (wr_a) P.ka[i] = it[0].a;
+            if (wr_b) P.kb[i] = it[0].b;
+            if (wr_o1) P.out[i] = o1[0];
+            if (wr_o2) P.out2[i] = o2[0];
         }
     }
 
-    lb_epilogue<HS>(P, mode, dep, s_hbase, s_red, sums);
+    lb_epilogue<HS, false>(P, mode, dep, s_hbase, s_red, sums);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Bulk-async (TMA engine) streaming variant for the compile-time modes: every input stream of the pass
-// (q | v0 | ka | kb | w, whichever the mode reads) arrives as a 4 KB tile of 512 particles in a shared-memory
-// ring filled by 1-D cp.async.bulk copies; an mbarrier per stage tracks the bytes.  The register-prefetch
-// kernel above keeps only one trip (16 B per stream and thread) in flight, which caps the one- and
-// two-stream passes (moments, stage 1, deposit) at ~3-4 TB/s by Little's law; the ring keeps
-// stages x streams x 4 KB per CTA in flight without spending registers.  Stage count is a launch parameter
-// (P.stages, chosen by the host to fill the shared memory left beside the histograms at the target
-// occupancy).  Thread t owns particles 512 g + 2 t, 2 t + 1 of its CTA's tiles, so the summation order
-// differs from lb_pass_kernel's (results agree to rounding); every histogram copy and every reduction still
-// has a fixed order, so the result is reproducible run to run.
+// Warp-specialised bulk-async (TMA engine) ring variant for the compile-time modes.  The CTA has kBlock worker
+// threads plus one PRODUCER warp.  Every input stream of the pass (q | v0 | ka | kb | w, whichever the mode
+// reads) arrives as a 4 KB tile of 512 particles in a shared-memory ring filled by 1-D cp.async.bulk copies;
+// a "full" mbarrier per stage counts the bytes, an "empty" mbarrier per stage counts the worker warps that
+// have copied their operands to registers.  Lane 0 of the producer warp waits on "empty" and re-arms the
+// stage; workers never meet at a CTA-wide barrier inside the loop, so a slow warp (boundary cells, bank
+// conflicts) does not stall the other seven, and the bytes in flight (stages x streams x 4 KB per CTA) cost
+// neither registers nor resident warps.  Stage count is a launch parameter (P.stages, chosen by the host to
+// fill the shared memory left beside the histograms at the target occupancy).  Thread t owns particles
+// 512 g + 2 t, 2 t + 1 of its CTA's tiles, so the summation order differs from lb_pass_kernel's (results agree
+// to rounding); every histogram copy and every reduction still has a fixed order: reproducible run to run.
 // ---------------------------------------------------------------------------------------------
 constexpr int kLbTile = 2 * kBlock;
+constexpr int kLbRingThreads = kBlock + 32;
+constexpr int kLbMaxStages = 8;
 
 template <int K, int MODE>
-__global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT) ? 4 : 2) lb_pass_tma_kernel(const LbDev P)
+__global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT) ? 3 : 2) lb_pass_ring_kernel(const LbDev P)
 {
     static_assert(MODE >= 0, "the ring variant is specialised per mode");
     extern __shared__ __align__(16) double smem[];
-    constexpr int TS = 2 * K - 1;
     using Io = LbIo<MODE>;
     constexpr bool stage = Io::stage;
     constexpr bool dep = Io::dep;
     constexpr bool ev = MODE != LB_DEPOSIT_ONLY;
     // slot of every stream inside a ring stage (compile-time; the weight stream is last so that the
     // uniform-weight variant simply drops it)
-    constexpr bool rd_q = Io::rd_q, rd_v0 = Io::rd_v0, rd_a = Io::rd_v0, rd_b = Io::rd_b;
+    constexpr bool rd_q = Io::rd_q, rd_v0 = Io::rd_v0, rd_a = Io::rd_a, rd_b = Io::rd_b;
     constexpr int iq = 0, iv0 = iq + (rd_q ? 1 : 0), ia = iv0 + (rd_v0 ? 1 : 0), ib = ia + (rd_a ? 1 : 0), iw = ib + (rd_b ? 1 : 0);
-    const bool rd_w = Io::rd_w && !P.use_uw;
+    const bool rd_w = Io::rd_w && !P.use_uw && !P.w_direct;   // weight stream through the ring
+    const bool ld_w = Io::rd_w && !P.use_uw && P.w_direct;    // ... or prefetched in registers one tile ahead
     const int ns = iw + (rd_w ? 1 : 0);
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* s_red = smem;                        // 5 * warps
-    double* s_tab = smem + 5 * (kBlock / 32);    // ncell * TS
-    double* s_hbase = s_tab + (((P.ncell + 1) * TS + 1) & ~1);
+    double* s_tab = smem + 5 * (kBlock / 32);    // (ncell + 1) * TSP
+    double* s_hbase = s_tab + (P.ncell + 1) * TabCfg<K>::TSP;
     double* s_hist = s_hbase + tid;
     double* s_stage = s_hbase + (dep ? (size_t)P.nbfull * kBlock : 0);      // stages x ns x kLbTile
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + (size_t)P.stages * ns * kLbTile);
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_stage + (size_t)P.stages * ns * kLbTile);
+    uint64_t* s_empty = s_full + kLbMaxStages;
 
-    if (ev)   // rows 0..ncell-1 from the field kernel, ghost row ncell = 0
-        for (int i = tid; i < (P.ncell + 1) * TS; i += kBlock) s_tab[i] = i < P.ncell * TS ? P.ftab[i] : 0.0;
+    if (ev) lb_stage_table<K>(P, s_tab, tid, kLbRingThreads);
     if (dep)
-        for (int i = tid; i < P.nbfull * kBlock; i += kBlock) s_hbase[i] = 0.0;
+        for (int i = tid; i < P.nbfull * kBlock; i += kLbRingThreads) s_hbase[i] = 0.0;
     if (tid == 0) {
-        for (int s = 0; s < P.stages; s++) mbar_init(&s_bar[s], 1);
+        for (int s = 0; s < P.stages; s++) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], kBlock / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const double A1 = P.conservative && ev ? P.scal[0] : 0.0, A2 = P.conservative && ev ? P.scal[1] : 1.0;
 
     const long long ntiles = P.n / kLbTile;
-    const uint32_t tile_bytes = kLbTile * sizeof(double);
-    auto issue = [&](int s, long long g) {
-        double* dst = s_stage + (size_t)s * ns * kLbTile;
-        const long long off = g * kLbTile;
-        mbar_expect_tx(&s_bar[s], (uint32_t)ns * tile_bytes);
-        if (rd_q) bulk_g2s(dst + iq * kLbTile, P.q + off, tile_bytes, &s_bar[s]);
-        if (rd_v0) bulk_g2s(dst + iv0 * kLbTile, P.v0 + off, tile_bytes, &s_bar[s]);
-        if (rd_a) bulk_g2s(dst + ia * kLbTile, P.ka + off, tile_bytes, &s_bar[s]);
-        if (rd_b) bulk_g2s(dst + ib * kLbTile, P.kb + off, tile_bytes, &s_bar[s]);
-        if (rd_w) bulk_g2s(dst + iw * kLbTile, P.w + off, tile_bytes, &s_bar[s]);
-    };
-    if (tid == 0)
-        for (int s = 0; s < P.stages; s++) {
-            const long long g = blockIdx.x + (long long)s * gridDim.x;
-            if (g < ntiles) issue(s, g);
+    if (warp == kBlock / 32) {   // ---- producer warp
+        if (lane == 0) {
+            const uint32_t tile_bytes = kLbTile * sizeof(double);
+            int s = 0;
+            uint32_t phase = 1;   // a fresh "empty" barrier passes a wait on parity 1: the first lap does not block
+            for (long long g = blockIdx.x; g < ntiles; g += gridDim.x) {
+                mbar_wait(&s_empty[s], phase);
+                double* dst = s_stage + (size_t)s * ns * kLbTile;
+                const long long off = g * kLbTile;
+                mbar_expect_tx(&s_full[s], (uint32_t)ns * tile_bytes);
+                if (rd_q) bulk_g2s(dst + iq * kLbTile, P.q + off, tile_bytes, &s_full[s]);
+                if (rd_v0) bulk_g2s(dst + iv0 * kLbTile, P.v0 + off, tile_bytes, &s_full[s]);
+                if (rd_a) bulk_g2s(dst + ia * kLbTile, P.ka + off, tile_bytes, &s_full[s]);
+                if (rd_b) bulk_g2s(dst + ib * kLbTile, P.kb + off, tile_bytes, &s_full[s]);
+                if (rd_w) bulk_g2s(dst + iw * kLbTile, P.w + off, tile_bytes, &s_full[s]);
+                if (++s == P.stages) {
+                    s = 0;
+                    phase ^= 1u;
+                }
+            }
         }
+        return;   // the workers synchronise among themselves (named barrier) from here on
+    }
 
+    // ---- worker warps
+    const double A1 = P.conservative && ev ? P.scal[0] : 0.0, A2 = P.conservative && ev ? P.scal[1] : 1.0;
     const bool wr_q = Io::wr_q && stage && P.qout != nullptr;
     const bool wr_o1 = Io::wr_o1 && P.out != nullptr;
     const bool wr_o2 = Io::wr_o2 && P.out2 != nullptr;
@@ -437,34 +504,29 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
     const double2 z2 = make_double2(0, 0), wdef = make_double2(P.w_uniform, P.w_uniform);
     int s = 0;
     uint32_t phase = 0;
+    double2 wpre = wdef;
+    if (ld_w && blockIdx.x < ntiles) wpre = ld_stream2(P.w + (long long)blockIdx.x * kLbTile + 2 * tid);
     for (long long g = blockIdx.x; g < ntiles; g += gridDim.x) {
-        mbar_wait(&s_bar[s], phase);
+        const double2 wcur = wpre;
+        if (ld_w && g + gridDim.x < ntiles) wpre = ld_stream2(P.w + (g + gridDim.x) * kLbTile + 2 * tid);
+        mbar_wait(&s_full[s], phase);
         const double* src = s_stage + (size_t)s * ns * kLbTile + 2 * tid;
         const double2 qa = rd_q ? *reinterpret_cast<const double2*>(src + iq * kLbTile) : z2;
         const double2 va = rd_v0 ? *reinterpret_cast<const double2*>(src + iv0 * kLbTile) : z2;
         const double2 aa = rd_a ? *reinterpret_cast<const double2*>(src + ia * kLbTile) : z2;
         const double2 ba = rd_b ? *reinterpret_cast<const double2*>(src + ib * kLbTile) : z2;
-        const double2 wa = rd_w ? *reinterpret_cast<const double2*>(src + iw * kLbTile) : wdef;
-        LbItem i0{qa.x, wa.x, va.x, aa.x, ba.x}, i1{qa.y, wa.y, va.y, aa.y, ba.y};
-        double2 o1 = z2, o2 = z2;
-        LbDep<K> d0, d1;
-        lb_particle<K, MODE>(P, MODE, s_tab, d0, i0, o1.x, o2.x, sums, A1, A2);
-        lb_particle<K, MODE>(P, MODE, s_tab, d1, i1, o1.y, o2.y, sums, A1, A2);
-        if (dep) {
-            v_deposit_commit<K, 0>(s_hist, d0);
-            v_deposit_commit<K, 0>(s_hist, d1);
-        }
+        const double2 wa = rd_w ? *reinterpret_cast<const double2*>(src + iw * kLbTile) : wcur;
+        LbItem it[2] = {{qa.x, wa.x, va.x, aa.x, ba.x}, {qa.y, wa.y, va.y, aa.y, ba.y}};
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[s]);   // this warp's operands are in registers: the stage may be refilled
+        double o1[2] = {0.0, 0.0}, o2[2] = {0.0, 0.0};
+        lb_group<K, MODE, 0, 2>(P, MODE, s_tab, s_hist, it, o1, o2, sums, A1, A2);
         const long long i = g * kLbTile + 2 * tid;
-        if (wr_q) st_stream2(P.qout + i, make_double2(i0.q, i1.q));
-        if (Io::wr_a) st_stream2(P.ka + i, make_double2(i0.a, i1.a));
-        if (Io::wr_b) st_stream2(P.kb + i, make_double2(i0.b, i1.b));
-        if (wr_o1) st_stream2(P.out + i, o1);
-        if (wr_o2) st_stream2(P.out2 + i, o2);
-        __syncthreads();  // every thread has read stage s: hand it back to the copy engine
-        if (tid == 0) {
-            const long long gn = g + (long long)P.stages * gridDim.x;
-            if (gn < ntiles) issue(s, gn);
-        }
+        if (wr_q) st_stream2(P.qout + i, make_double2(it[0].q, it[1].q));
+        if (Io::wr_a) st_stream2(P.ka + i, make_double2(it[0].a, it[1].a));
+        if (Io::wr_b) st_stream2(P.kb + i, make_double2(it[0].b, it[1].b));
+        if (wr_o1) st_stream2(P.out + i, make_double2(o1[0], o1[1]));
+        if (wr_o2) st_stream2(P.out2 + i, make_double2(o2[0], o2[1]));
         if (++s == P.stages) {
             s = 0;
             phase ^= 1u;
@@ -472,18 +534,16 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
     }
     // remainder (< one tile): plain loads, spread over the grid
     for (long long i = ntiles * kLbTile + (long long)blockIdx.x * kBlock + tid; i < P.n; i += (long long)gridDim.x * kBlock) {
-        LbItem it{rd_q ? P.q[i] : 0.0, rd_w ? P.w[i] : P.w_uniform, rd_v0 ? P.v0[i] : 0.0, rd_a ? P.ka[i] : 0.0, rd_b ? P.kb[i] : 0.0};
-        double o1 = 0.0, o2 = 0.0;
-        LbDep<K> d0;
-        lb_particle<K, MODE>(P, MODE, s_tab, d0, it, o1, o2, sums, A1, A2);
-        if (dep) v_deposit_commit<K, 0>(s_hist, d0);
-        if (wr_q) P.qout[i] = it.q;
-        if (Io::wr_a) P.ka[i] = it.a;
-        if (Io::wr_b) P.kb[i] = it.b;
-        if (wr_o1) P.out[i] = o1;
-        if (wr_o2) P.out2[i] = o2;
+        LbItem it[1] = {{rd_q ? P.q[i] : 0.0, (rd_w || ld_w) ? P.w[i] : P.w_uniform, rd_v0 ? P.v0[i] : 0.0, rd_a ? P.ka[i] : 0.0, rd_b ? P.kb[i] : 0.0}};
+        double o1[1] = {0.0}, o2[1] = {0.0};
+        lb_group<K, MODE, 0, 1>(P, MODE, s_tab, s_hist, it, o1, o2, sums, A1, A2);
+        if (wr_q) P.qout[i] = it[0].q;
+        if (Io::wr_a) P.ka[i] = it[0].a;
+        if (Io::wr_b) P.kb[i] = it[0].b;
+        if (wr_o1) P.out[i] = o1[0];
+        if (wr_o2) P.out2[i] = o2[0];
     }
-    lb_epilogue<kBlock>(P, MODE, dep, s_hbase, s_red, sums);
+    lb_epilogue<kBlock, true>(P, MODE, dep, s_hbase, s_red, sums);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -597,7 +657,6 @@ __global__ void __launch_bounds__(kFieldThreads) lb_field_kernel(const LbFieldDe
 template <int K>
 int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* grid_out)
 {
-    constexpr int TS = 2 * K - 1;
     LbDev P{};
     P.mode = p.mode;
     P.q = p.q; P.w = p.w; P.v0 = p.v0; P.ka = p.ka; P.kb = p.kb; P.qout = p.qout; P.out = p.out; P.out2 = p.out2;
@@ -609,7 +668,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
 
     const bool stage = p.mode >= LB_STAGE1 && p.mode <= LB_STAGE4;
     const bool dep = p.mode == LB_DEPOSIT_ONLY || stage;
-    const size_t base = sizeof(double) * (5 * (kBlock / 32) + (((vs->ncell + 1) * TS + 1) & ~1));
+    const size_t base = sizeof(double) * (5 * (kBlock / 32) + (size_t)(vs->ncell + 1) * TabCfg<K>::TSP);
     int hm = 0;
     if (dep) {
         if (base + sizeof(double) * (size_t)vs->nbfull * kBlock > ctx->smem_optin) hm = 1;  // shared-memory CAS atomics are ~5x slower
@@ -630,40 +689,54 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
     void (*kern)(const LbDev) = nullptr;
     if (p.mode < LB_DEPOSIT_ONLY || p.mode > LB_EVAL) return fail(VPM_ERR_INVALID, "bad LB pass mode");
 
-    // TMA ring variant: size the ring to the shared memory left at the kernel's target occupancy
-    // (2 CTAs/SM beside the histograms, 4 CTAs/SM for the gather-only modes); needs >= 2 stages to pay.
-    int tune_tma = -1;   // test / tuning hook. 0: register-prefetch kernel everywhere; bit m+1 set: ring for mode m
+    // Ring variant: size the ring to the shared memory left at the kernel's target occupancy (2 CTAs/SM beside
+    // the histograms, 3 CTAs/SM for the gather-only modes).
+    // VPM_TUNE_LBTMA (test / tuning hook): 0 = register-prefetch kernel everywhere; bit m+1 set = ring for mode m.
+    // Default: the deposit passes whose streams fit (stages 1, 2, 4, deposit-only; stage 3 with uniform weights).
+    int tune_tma = -1;
     if (const char* e = getenv("VPM_TUNE_LBTMA")) tune_tma = atoi(e);
     size_t smem = smem_reg;
     bool tma = false;
-    if (hm == 0 && vec && p.n >= kLbTile && tune_tma != 0 && (tune_tma < 0 || ((tune_tma >> (p.mode + 1)) & 1))) {
-        const bool st = p.mode >= LB_STAGE1 && p.mode <= LB_STAGE4;
+    const bool want_ring = tune_tma < 0 ? dep : ((tune_tma >> (p.mode + 1)) & 1) != 0;
+    if (hm == 0 && vec && p.n >= kLbTile && want_ring) {
         int ns = 0;
         if (!(p.mode == LB_STAGE2 || p.mode == LB_STAGE3)) ns++;                 // q
-        if (p.mode >= LB_STAGE2 && p.mode <= LB_STAGE4) ns += 2;                 // v0, ka
+        if (p.mode == LB_STAGE2 || p.mode == LB_STAGE3) ns++;                    // v0
+        if (p.mode >= LB_STAGE2 && p.mode <= LB_STAGE4) ns++;                    // ka
         if (p.mode == LB_STAGE3) ns++;                                           // kb
-        if ((st || p.mode == LB_DEPOSIT_ONLY) && !p.use_uw) ns++;                // w
-        const int target = dep ? 2 : 4;
+        if (dep && !p.use_uw) ns++;                                              // w
+        const int target = dep ? 2 : 3;
         const size_t per_cta = ctx->smem_sm / target - ctx->smem_reserved;
-        const size_t stage_bytes = (size_t)ns * kLbTile * sizeof(double);
-        const size_t fixed = smem_reg + 8 * sizeof(uint64_t);
+        const size_t fixed = smem_reg + 2 * kLbMaxStages * sizeof(uint64_t);
+        size_t stage_bytes = (size_t)ns * kLbTile * sizeof(double);
         int stages = per_cta > fixed ? (int)((per_cta - fixed) / stage_bytes) : 0;
+        if (stages < 2 && dep && !p.use_uw && ns > 1) {
+            // a second stage fits when the weight stream bypasses the ring (prefetched in registers instead)
+            const size_t sb = (size_t)(ns - 1) * kLbTile * sizeof(double);
+            const int st2 = per_cta > fixed ? (int)((per_cta - fixed) / sb) : 0;
+            if (st2 >= 2) {
+                P.w_direct = 1;
+                stage_bytes = sb;
+                stages = st2;
+            }
+        }
         if (stages > 6) stages = 6;
-        if (stages >= 2) {
+        if (stages >= 1) {   // one stage is enough to stream: workers release a stage as soon as their operands are in registers
             tma = true;
             P.stages = stages;
-            smem = smem_reg + (size_t)stages * stage_bytes + (size_t)stages * sizeof(uint64_t);
+            smem = fixed + (size_t)stages * stage_bytes;
         }
     }
+    const int block = tma ? kLbRingThreads : kBlock;
     if (tma) switch (p.mode) {
-        case LB_DEPOSIT_ONLY: kern = lb_pass_tma_kernel<K, LB_DEPOSIT_ONLY>; break;
-        case LB_STAGE1: kern = lb_pass_tma_kernel<K, LB_STAGE1>; break;
-        case LB_STAGE2: kern = lb_pass_tma_kernel<K, LB_STAGE2>; break;
-        case LB_STAGE3: kern = lb_pass_tma_kernel<K, LB_STAGE3>; break;
-        case LB_STAGE4: kern = lb_pass_tma_kernel<K, LB_STAGE4>; break;
-        case LB_RHS_OUT: kern = lb_pass_tma_kernel<K, LB_RHS_OUT>; break;
-        case LB_MOMENTS: kern = lb_pass_tma_kernel<K, LB_MOMENTS>; break;
-        case LB_EVAL: kern = lb_pass_tma_kernel<K, LB_EVAL>; break;
+        case LB_DEPOSIT_ONLY: kern = lb_pass_ring_kernel<K, LB_DEPOSIT_ONLY>; break;
+        case LB_STAGE1: kern = lb_pass_ring_kernel<K, LB_STAGE1>; break;
+        case LB_STAGE2: kern = lb_pass_ring_kernel<K, LB_STAGE2>; break;
+        case LB_STAGE3: kern = lb_pass_ring_kernel<K, LB_STAGE3>; break;
+        case LB_STAGE4: kern = lb_pass_ring_kernel<K, LB_STAGE4>; break;
+        case LB_RHS_OUT: kern = lb_pass_ring_kernel<K, LB_RHS_OUT>; break;
+        case LB_MOMENTS: kern = lb_pass_ring_kernel<K, LB_MOMENTS>; break;
+        case LB_EVAL: kern = lb_pass_ring_kernel<K, LB_EVAL>; break;
     }
     else if (hm == 1) kern = vec ? lb_pass_kernel<K, -1, 2, 1> : lb_pass_kernel<K, -1, 1, 1>;
     else if (hm == 2) kern = vec ? lb_pass_kernel<K, -1, 2, 2> : lb_pass_kernel<K, -1, 1, 2>;
@@ -680,7 +753,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
     }
     int occ = 0;
     {
-        const int rc_occ = kernel_occupancy(ctx, (const void*)kern, kBlock, smem, &occ);
+        const int rc_occ = kernel_occupancy(ctx, (const void*)kern, block, smem, &occ);
         if (rc_occ) return rc_occ;
     }
     if (occ < 1) return fail(VPM_ERR_UNSUPPORTED, "lb pass kernel does not fit on an SM");
@@ -694,7 +767,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
     P.partials = ctx->partials;
     P.red_partials = ctx->partials + (size_t)grid * vs->nbfull;
     prof_begin(ctx, PROF_LB_PASS);
-    kern<<<(unsigned)grid, kBlock, smem, ctx->stream>>>(P);
+    kern<<<(unsigned)grid, block, smem, ctx->stream>>>(P);
     prof_end(ctx);
     ctx->launches++;
     VPM_CUDA(cudaGetLastError());
