@@ -68,7 +68,7 @@ __device__ __forceinline__ void vp_particle(const VpDev& P, const int flags_rt, 
     if (flags & VP_KICK1) {
         int ci;
         double u;
-        split_floor((x - P.lo) * P.invh, ci, u);
+        split_floor(x - P.lo, P.invh, ci, u);
         const double* e = s_etab + wrap_index(ci, P.fm) * ES;
         double E = e[K - 2];
 #pragma unroll
@@ -86,7 +86,7 @@ __device__ __forceinline__ void vp_particle(const VpDev& P, const int flags_rt, 
     if (flags & VP_DEPOSIT) {
         int ci;
         double u, b[K];
-        split_floor((x - P.lo) * P.invh, ci, u);
+        split_floor(x - P.lo, P.invh, ci, u);
         if (HM == 3) {  // tile-sorted deposit: hand the cell and local coordinate back to the caller
             *dep_c = wrap_index(ci, P.fm);
             *dep_u = u;

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kBlock) x_gather_kernel(const double* __restri
     for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
         int ci;
         double u;
-        split_floor((x[i] - lo) * invh, ci, u);
+        split_floor(x[i] - lo, invh, ci, u);
         const double* e = s_tab + wrap_index(ci, fm) * ts;
         double r = e[nc - 1];
         for (int m = nc - 2; m >= 0; m--) r = fma(r, u, e[m]);

@@ -59,18 +59,15 @@ __device__ __forceinline__ void basis_uniform(double u, double (&b)[K])
     }
 }
 
-// t = ci + u with ci = floor(t), u in [0,1]; valid for |t| < 2^31.  Uses the 1.5*2^52 rounding
-// constant instead of FRND/F2I (conversion-pipe instructions) so only DADDs are issued.
-__device__ __forceinline__ void split_floor(double t, int& ci, double& u)
+// t = d * invh = ci + u with ci = floor(t), u in [0,1]; valid for |t| < 2^31.  One round-DOWN fma against
+// 1.5 * 2^52 leaves floor(t) (two's complement) in the low mantissa word of the sum: no FRND/F2I
+// (conversion-pipe instructions), no compare-and-fix-up; three fp64 instructions in total.
+__device__ __forceinline__ void split_floor(double d, double invh, int& ci, double& u)
 {
     const double M = 6755399441055744.0;
-    const double tm = t + M;
+    const double tm = __fma_rd(d, invh, M);
     ci = __double2loint(tm);
-    u = t - (tm - M);
-    if (u < 0.0) {
-        u += 1.0;
-        ci -= 1;
-    }
+    u = fma(d, invh, -(tm - M));
 }
 
 // ci mod d for possibly negative ci (|ci| < 2^30), result clamped into [0,d) for safety
