@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="vp", choices=["vp", "lb", "clb"])
+    ap.add_argument("--load", default="bump_on_tail", choices=["bump_on_tail", "uniform", "one_cell", "sorted"],
+                    help="vp particle load: the config-2 sampler (default) or the synthetic loads of SURVEY 8(d): uniform x / "
+                         "all particles in one cell (worst case for atomics-based deposits) / cell-sorted x")
     ap.add_argument("--n-basis", type=int, default=16, help="x-space basis size (headline config: 16)")
     ap.add_argument("--order", type=int, default=4, help="spline order (headline config: 4 = cubic)")
     ap.add_argument("--field", default="selfconsistent", choices=["selfconsistent", "frozen"],
@@ -190,11 +193,21 @@ def main():
     if args.workload == "vp":
         d = vpm.ParticleDistribution(1, 1, n, ctx)
         vpm.initialize_(d, vpm.BumpOnTail(kappa=KAPPA), offset=rank * n, ntotal=ntotal)
+        if args.load != "bump_on_tail":   # synthetic throughput loads, generated on the host (seeded), w = L / N
+            rng = np.random.default_rng(0x5EED0002 + rank)
+            if args.load == "one_cell":    # every particle in cell 5 and slow enough to stay there for the whole run
+                xs_, vs_ = (5.3 + 0.2 * rng.random(n)) * (L / NH), 1e-4 * rng.standard_normal(n)
+            else:
+                xs_, vs_ = L * rng.random(n), rng.standard_normal(n)
+                if args.load == "sorted":
+                    xs_.sort()
+            d.set(xs_, vs_, np.full(n, L / ntotal))
+            del xs_, vs_
         pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), ORDER, NH), ctx)
 
         def run_steps(k):
             vpm.check(lib.vpm_vp_strang_steps_async(pot._h, d._h, DT, CHI, int(k), 1 if args.field == "frozen" else 0, 0))
-        kind_pass, bytes_unit, wl = 0, BYTES_PER_STEP, "vp_bump_on_tail_strang_" + args.field
+        kind_pass, bytes_unit, wl = 0, BYTES_PER_STEP, "vp_" + args.load + "_strang_" + args.field
         passes_per_call = lambda k: k + 1
     else:
         cons = args.workload == "clb"
