@@ -248,6 +248,45 @@ def test_lb_golden(vpm, name, ring, monkeypatch):
         np.testing.assert_allclose(gi.diagnostics, g[kd], rtol=1e-11)
 
 
+def test_lb_large_properties(vpm, monkeypatch):
+    """Size-independent properties of the LB / CLB path at 2e7 particles (BASELINE configs 3, 4; the oracle would
+    take minutes): partition of unity of the clamped deposit, linearity of the projection in the weights,
+    ring passes == register-prefetch passes to rounding, a run split in two calls == one run, CLB invariants."""
+    n = 20_000_003                                        # not a multiple of the 512-particle tile
+    sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
+    ent = vpm.CollisionEntropy(sd)
+    d = vpm.ParticleDistribution(1, 1, n)
+    vpm.initialize_(d, vpm.DoubleMaxwellian((-10.0, 10.0), 2.0))
+    v0 = d.get("v")
+    fs = vpm.projection(None, d, sd)
+    # every particle is far from the domain ends, where the removed boundary functions vanish: sum_j rhs_j = sum w
+    assert abs(sd.rhs.sum() - 1.0) < 1e-12
+    c1 = fs.coefficients.copy()
+    d.set(w=np.full(n, 3.0 / n))
+    c3 = vpm.projection(None, d, sd).coefficients.copy()
+    assert nrm(c3, 3.0 * c1) < 1e-12
+    d.set(w=np.full(n, 1.0 / n))
+    res = {}
+    for ring in ("-1", "0"):
+        monkeypatch.setenv("VPM_TUNE_LBTMA", ring)
+        d.set(v=v0)
+        gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d, ent, nu=1.0), (0.0, 0.04), 1e-2)
+        vpm.run_(gi)
+        res[ring] = (d.get("v"), gi.diagnostics.copy())
+    assert nrm(res["-1"][0], res["0"][0]) < 1e-13
+    np.testing.assert_allclose(res["-1"][1], res["0"][1], rtol=1e-12)
+    monkeypatch.setenv("VPM_TUNE_LBTMA", "-1")
+    d.set(v=v0)
+    for _ in range(2):                                    # 2 + 2 steps in two calls
+        gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d, ent, nu=1.0), (0.0, 0.02), 1e-2)
+        vpm.run_(gi)
+    assert nrm(d.get("v"), res["-1"][0]) < 1e-13
+    dg = res["-1"][1]
+    assert abs(dg[-1, 0] - dg[0, 0]) < 1e-9 * n           # sum v
+    assert abs(dg[-1, 1] - dg[0, 1]) < 1e-9 * dg[0, 1]    # sum v^2
+    assert abs(dg[0, 1] / n - 5.0) < 5e-3                 # two unit Maxwellians at +-2: <v^2> = 5
+
+
 def test_lb_relaxation_physics(vpm):
     """KAT-7: CLB conserves sum v and sum v^2 to integrator order; plain LB does not conserve energy."""
     n = 200000
