@@ -82,3 +82,57 @@ def test_oracle_matches_golden_lb(oracle, name):
     np.testing.assert_allclose(vs.lb_rhs(g["v"], g["w"], 0.7, True)[0], g["vdot_clb"], atol=1e-13)
     v2, d = vs.rk438(g["v"], g["w"], 0.7, float(g["dt"]), int(g["nsteps"]), conservative=True)
     np.testing.assert_allclose(v2, g["v_clb"], atol=1e-12)
+
+
+def _split_top(s):
+    """split a comma-separated list at nesting depth 0"""
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "({[":
+            depth += 1
+        elif ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_shim_binds_the_declared_abi():
+    """julia/VPMB200.jl cannot run here (no Julia toolchain), so check statically what a `ccall` would trip over:
+    every bound symbol is declared in include/vpm_b200.h, with the same number of arguments, pointer arguments
+    where the header has pointers and 64-bit integers where the header has int64_t / uint64_t."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "vpm_b200.h")).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|int64_t|const char\*|void)\s+(vpm_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        args = [a for a in _split_top(m.group(2)) if a and a != "void"]
+        protos[m.group(1)] = args
+    jl = open(os.path.join(ROOT, "julia", "VPMB200.jl")).read()
+    calls = list(re.finditer(r"ccall\(\(:(vpm_[a-z0-9_]+),\s*libvpm\),\s*(\w+),\s*\(", jl))
+    assert len(calls) >= 30
+    for m in calls:
+        name = m.group(1)
+        assert name in protos, f"julia shim binds {name}, which include/vpm_b200.h does not declare"
+        # the argument-type tuple starts at the '(' that ends the match
+        i, depth = m.end(), 1
+        while depth:
+            depth += {"(": 1, ")": -1}.get(jl[i], 0)
+            i += 1
+        jtypes = _split_top(jl[m.end():i - 1])
+        cargs = protos[name]
+        assert len(jtypes) == len(cargs), f"{name}: julia passes {len(jtypes)} arguments, header declares {len(cargs)}"
+        for jt, ca in zip(jtypes, cargs):
+            is_ptr_c = "*" in ca
+            is_ptr_j = jt.startswith(("Ptr{", "Ref{")) or jt == "Cstring"
+            assert is_ptr_c == is_ptr_j, f"{name}: '{ca}' bound as {jt}"
+            if not is_ptr_c:
+                if "int64_t" in ca:
+                    assert jt in ("Int64", "UInt64"), f"{name}: '{ca}' bound as {jt}"
+                elif re.match(r"\s*(const\s+)?double\b", ca):
+                    assert jt == "Float64", f"{name}: '{ca}' bound as {jt}"
+                else:
+                    assert jt == "Cint", f"{name}: '{ca}' bound as {jt}"
