@@ -248,6 +248,33 @@ def test_lb_golden(vpm, name, ring, monkeypatch):
         np.testing.assert_allclose(gi.diagnostics, g[kd], rtol=1e-11)
 
 
+@pytest.mark.parametrize("n", [0, 1, 2, 511, 512, 513, 1024, 1537])
+def test_lb_edge_sizes(vpm, oracle, n):
+    """Empty and ragged inputs around the 512-particle tile of the ring passes (whole tiles through the TMA ring,
+    the remainder through plain loads), both models, against the oracle."""
+    rng = np.random.default_rng(100 + n)
+    v = rng.standard_normal(n) * 1.3
+    if n >= 4:
+        v[:4] = [-10.0, 10.0, -10.5, 11.0]                 # domain ends and out-of-domain particles
+    w = rng.uniform(0.5, 1.5, n) / max(n, 1)
+    vs = oracle.VSpace(-10.0, 10.0, 41, 4)
+    sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
+    for cons in (False, True):
+        if cons and n < 64:
+            continue                                       # the CLB coefficients are 0/0 for a handful of particles
+        d = vpm.ParticleDistribution(1, 1, n).set(np.zeros(n), v, w)
+        model = (vpm.ConservativeLenardBernstein if cons else vpm.LenardBernstein)(d, vpm.CollisionEntropy(sd), nu=0.9)
+        gi = vpm.GeometricIntegrator(model, (0.0, 0.04), 0.02)
+        vpm.run_(gi)
+        vo, do = vs.rk438(v, w, 0.9, 0.02, 2, conservative=cons)
+        assert gi.diagnostics.shape == (3, 2)
+        if n == 0:
+            assert np.all(gi.diagnostics == 0.0)
+            continue
+        assert np.abs(d.get("v") - vo).max() <= 1e-11 * max(1.0, np.abs(vo).max()), (n, cons)
+        np.testing.assert_allclose(gi.diagnostics, do, rtol=1e-10, atol=1e-12)
+
+
 def test_lb_large_properties(vpm, monkeypatch):
     """Size-independent properties of the LB / CLB path at 2e7 particles (BASELINE configs 3, 4; the oracle would
     take minutes): partition of unity of the clamped deposit, linearity of the projection in the weights,

@@ -561,15 +561,32 @@ struct LbFieldDev {
     P2PDev p2p;
 };
 
-__global__ void __launch_bounds__(kFieldThreads) lb_field_kernel(const LbFieldDev F)
+// The kernel is a chain of latencies (L2 round trips of the partial rows, the sequential band solve), not of
+// work: 1024 threads so that the column sums need two rounds of two load batches, the Cholesky factor staged
+// (zero-padded to kMaxOrder columns, diagonal as reciprocals) while those loads are in flight, and the
+// substitution sweeps of thread 0 carry the last K-1 unknowns in registers so that one fma + one multiply
+// per row sit on the critical path.
+constexpr int kLbFieldThreads = 1024;
+constexpr int kCholW = kMaxOrder;
+
+__global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbFieldDev F)
 {
     extern __shared__ double sm[];
-    double* s_full = sm;                 // nbfull
-    double* s_y = s_full + F.nbfull;     // nv
-    double* s_chol = s_y + F.nv;         // nv * K
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kFieldThreads / 32;
+    double* s_full = sm;                    // nbfull
+    double* s_y = s_full + F.nbfull;        // nv
+    double* s_chol = s_y + F.nv;            // (nv + kCholW - 1) * kCholW: padded rows, trailing zero rows
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nwarps = nt / 32;
     const int K = F.K, nv = F.nv;
 
+    if (F.phases & LBF_SOLVE) {
+        // s_chol[i][0] = 1 / L(i,i), s_chol[i][k] = L(i, i-k) for 1 <= k < K, k <= i; zero elsewhere
+        for (int i = tid; i < (nv + kCholW - 1) * kCholW; i += nt) {
+            const int r = i / kCholW, k = i - r * kCholW;
+            double c = 0.0;
+            if (r < nv && k < K && k <= r) c = F.chol[r * K + k];
+            s_chol[i] = (k == 0 && r < nv) ? 1.0 / c : c;
+        }
+    }
     if (F.phases & LBF_REDUCE) {
         for (int b = warp; b < F.nbfull; b += nwarps) {
             const double s = warp_sum(strided_sum(F.partials + b, (size_t)F.nbfull, F.nparts, lane));
@@ -577,7 +594,7 @@ __global__ void __launch_bounds__(kFieldThreads) lb_field_kernel(const LbFieldDe
         }
         __syncthreads();
         // contributions to the functions removed by the Dirichlet recombination are dropped
-        for (int i = tid; i < nv; i += kFieldThreads) F.rhs[i] = s_full[i + F.off];
+        for (int i = tid; i < nv; i += nt) F.rhs[i] = s_full[i + F.off];
         __syncthreads();
     }
     if (F.phases & LBF_SCALRED) {
@@ -588,6 +605,7 @@ __global__ void __launch_bounds__(kFieldThreads) lb_field_kernel(const LbFieldDe
         }
         __syncthreads();
     }
+    const bool reduced_here = (F.phases & LBF_REDUCE) && !F.p2p.seq;   // rhs of this rank is still in s_full
     if (F.p2p.seq && (F.phases & (LBF_REDUCE | LBF_SCALRED))) {
         // multi-GPU: rhs | scalar sums are contiguous; one fused peer-memory all-reduce
         const int start = (F.phases & LBF_REDUCE) ? 0 : nv;
@@ -596,42 +614,51 @@ __global__ void __launch_bounds__(kFieldThreads) lb_field_kernel(const LbFieldDe
     }
     if (F.phases & LBF_SOLVE) {
         // ldiv!(coefficients, cholesky(M), rhs): banded forward / backward substitution
-        // factor staged in shared memory (diagonal as reciprocals) so the sequential sweeps of thread 0 are
-        // chains of shared-memory loads, not L2 round trips
-        for (int i = tid; i < nv; i += kFieldThreads) s_y[i] = F.rhs[i];
-        for (int i = tid; i < nv * K; i += kFieldThreads) {
-            const double c = F.chol[i];
-            s_chol[i] = (i % K == 0) ? 1.0 / c : c;
-        }
+        for (int i = tid; i < nv; i += nt) s_y[i] = reduced_here ? s_full[i + F.off] : F.rhs[i];
         __syncthreads();
         if (tid == 0) {
+            double y1 = 0.0, y2 = 0.0, y3 = 0.0, y4 = 0.0, y5 = 0.0;
             for (int i = 0; i < nv; i++) {
-                double s = s_y[i];
-                for (int k = 1; k < K && k <= i; k++) s -= s_chol[i * K + k] * s_y[i - k];
-                s_y[i] = s * s_chol[i * K];
+                const double* c = s_chol + i * kCholW;
+                double t = s_y[i];
+                t = fma(-c[5], y5, t);
+                t = fma(-c[4], y4, t);
+                t = fma(-c[3], y3, t);
+                t = fma(-c[2], y2, t);
+                t = fma(-c[1], y1, t);   // the only term that waits for the previous row
+                const double y = t * c[0];
+                s_y[i] = y;
+                y5 = y4; y4 = y3; y3 = y2; y2 = y1; y1 = y;
             }
+            y1 = y2 = y3 = y4 = y5 = 0.0;
             for (int i = nv - 1; i >= 0; i--) {
-                double s = s_y[i];
-                for (int k = 1; k < K && i + k < nv; k++) s -= s_chol[(i + k) * K + k] * s_y[i + k];
-                s_y[i] = s * s_chol[i * K];
+                const double* c = s_chol + i * kCholW;   // L(i+k, i) = s_chol[i+k][k]; rows >= nv are zero
+                double t = s_y[i];
+                t = fma(-c[5 * kCholW + 5], y5, t);
+                t = fma(-c[4 * kCholW + 4], y4, t);
+                t = fma(-c[3 * kCholW + 3], y3, t);
+                t = fma(-c[2 * kCholW + 2], y2, t);
+                t = fma(-c[1 * kCholW + 1], y1, t);
+                const double y = t * c[0];
+                s_y[i] = y;
+                y5 = y4; y4 = y3; y3 = y2; y2 = y1; y1 = y;
             }
         }
         __syncthreads();
-        for (int i = tid; i < nv; i += kFieldThreads) F.coef[i] = s_y[i];
-        __syncthreads();
+        for (int i = tid; i < nv; i += nt) F.coef[i] = s_y[i];
     } else if (F.phases & LBF_TABLE) {
-        for (int i = tid; i < nv; i += kFieldThreads) s_y[i] = F.coef[i];
+        for (int i = tid; i < nv; i += nt) s_y[i] = F.coef[i];
         __syncthreads();
     }
     if (F.phases & LBF_TABLE) {
         // F_c(u) = sum_j cfull[c+j] P_{c,j}(u) ; G_c(u) = F_c'(u)/h   (exact derivative of the piece)
         const int TS = 2 * K - 1;
-        for (int i = tid; i < F.nbfull; i += kFieldThreads) {
+        for (int i = tid; i < F.nbfull; i += nt) {
             const int j = i - F.off;
             s_full[i] = (j >= 0 && j < nv) ? s_y[j] : 0.0;
         }
         __syncthreads();
-        for (int idx = tid; idx < F.ncell * K; idx += kFieldThreads) {
+        for (int idx = tid; idx < F.ncell * K; idx += nt) {
             const int c = idx / K, m = idx - c * K;
             double s = 0.0;
             for (int j = 0; j < K; j++) s = fma(s_full[c + j], F.pieces[((size_t)c * K + j) * K + m], s);
@@ -799,7 +826,7 @@ int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nr
     F.chol = vs->chol; F.pieces = vs->pieces;
     F.nv = vs->nv; F.nbfull = vs->nbfull; F.ncell = vs->ncell; F.K = vs->K; F.off = vs->dirichlet ? 1 : 0;
     F.invh = vs->invh;
-    const size_t smem = sizeof(double) * ((size_t)vs->nbfull + vs->nv + (size_t)vs->nv * vs->K);
+    const size_t smem = sizeof(double) * ((size_t)vs->nbfull + vs->nv + ((size_t)vs->nv + kCholW - 1) * kCholW);
     if (smem > ctx->smem_optin) return fail(VPM_ERR_UNSUPPORTED, "v-space too large for the single-CTA field kernel");
     if (smem > 48 * 1024) VPM_CUDA(cudaFuncSetAttribute(lb_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
@@ -812,7 +839,7 @@ int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nr
     } else if (ctx->comm.comm && red) {
         F.phases = red;
         prof_begin(ctx, PROF_LB_FIELD);
-    lb_field_kernel<<<1, kFieldThreads, smem, ctx->stream>>>(F);
+    lb_field_kernel<<<1, kLbFieldThreads, smem, ctx->stream>>>(F);
     prof_end(ctx);
         ctx->launches++;
         VPM_CUDA(cudaGetLastError());
@@ -827,7 +854,7 @@ int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nr
     }
     F.phases = phases;
     prof_begin(ctx, PROF_LB_FIELD);
-    lb_field_kernel<<<1, kFieldThreads, smem, ctx->stream>>>(F);
+    lb_field_kernel<<<1, kLbFieldThreads, smem, ctx->stream>>>(F);
     prof_end(ctx);
     ctx->launches++;
     VPM_CUDA(cudaGetLastError());

@@ -466,7 +466,11 @@ struct FieldDev {
     P2PDev p2p;
 };
 
-__global__ void __launch_bounds__(kFieldThreads) vp_field_kernel(const FieldDev F)
+// 1024 threads: the kernel is a chain of L2 round trips (column sums of the partial rows), and 32 warps
+// cover the K + nh - 1 bins in one round of two load batches
+constexpr int kVpFieldThreads = 1024;
+
+__global__ void __launch_bounds__(kVpFieldThreads) vp_field_kernel(const FieldDev F)
 {
     extern __shared__ double sm[];
     double* s_ru = sm;               // nb (unwrapped bins) + 2
@@ -477,15 +481,15 @@ __global__ void __launch_bounds__(kFieldThreads) vp_field_kernel(const FieldDev 
     double* s_stiff = s_ginv + F.nh; // 2K-1
     double* s_dpiece = s_stiff + 2 * F.K - 1;  // (K-1)^2
     __shared__ double s_scal[4];
-    __shared__ double s_w[kFieldThreads / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kFieldThreads / 32;
+    __shared__ double s_w[kVpFieldThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nwarps = nt / 32;
     const int nh = F.nh, K = F.K;
     // constant operators into shared memory up front: their L2 latency overlaps the partial-row loads
     if (F.phases & FIELD_SOLVE)
-        for (int i = tid; i < nh; i += kFieldThreads) s_ginv[i] = F.ginv[i];
+        for (int i = tid; i < nh; i += nt) s_ginv[i] = F.ginv[i];
     if (F.phases & (FIELD_SOLVE | FIELD_TABLE)) {
-        for (int i = tid; i < 2 * K - 1; i += kFieldThreads) s_stiff[i] = F.stiff[i];
-        for (int i = tid; i < (K - 1) * (K - 1); i += kFieldThreads) s_dpiece[i] = F.dpiece[i];
+        for (int i = tid; i < 2 * K - 1; i += nt) s_stiff[i] = F.stiff[i];
+        for (int i = tid; i < (K - 1) * (K - 1); i += nt) s_dpiece[i] = F.dpiece[i];
     }
 
     if (F.phases & FIELD_REDUCE) {
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(kFieldThreads) vp_field_kernel(const FieldDev 
         }
         __syncthreads();
         if (F.has_dep)
-            for (int i = tid; i < nh; i += kFieldThreads) {
+            for (int i = tid; i < nh; i += nt) {
                 // bin b holds basis function (b - (K-1)) mod nh: fold the wrapped bins
                 double s = 0.0;
                 for (int b = (i + K - 1) % nh; b < F.nb; b += nh) s += s_ru[b];
@@ -518,7 +522,7 @@ __global__ void __launch_bounds__(kFieldThreads) vp_field_kernel(const FieldDev 
 
     if (F.phases & FIELD_SOLVE) {
         // S phi = rhs - mean(rhs), zero-mean gauge: phi = pinv(S) (rhs - mean) by circular convolution
-        for (int i = tid; i < nh; i += kFieldThreads) s_b[i] = F.rhs[i];
+        for (int i = tid; i < nh; i += nt) s_b[i] = F.rhs[i];
         __syncthreads();
         if (warp == 0) {
             double s = 0.0;
@@ -528,7 +532,7 @@ __global__ void __launch_bounds__(kFieldThreads) vp_field_kernel(const FieldDev 
         }
         __syncthreads();
         const double mean = s_scal[0];
-        for (int i = tid; i < nh; i += kFieldThreads) {
+        for (int i = tid; i < nh; i += nt) {
             double s = 0.0;
             for (int j = 0; j < nh; j++) {
                 int d = i - j;
@@ -542,7 +546,7 @@ __global__ void __launch_bounds__(kFieldThreads) vp_field_kernel(const FieldDev 
         if (F.w_slot >= 0 && F.diag) {
             // W = phi' S phi / 2 (src/electric_field.jl:47), scaled by 1/chi^2 (:33)
             double s = 0.0;
-            for (int i = tid; i < nh; i += kFieldThreads) {
+            for (int i = tid; i < nh; i += nt) {
                 double r = 0.0;
                 for (int d = -(K - 1); d <= K - 1; d++) {
                     int j = (i + d) % nh;
@@ -562,17 +566,17 @@ __global__ void __launch_bounds__(kFieldThreads) vp_field_kernel(const FieldDev 
             __syncthreads();
         }
     } else if (F.phases & FIELD_TABLE) {
-        for (int i = tid; i < nh; i += kFieldThreads) s_phi[i] = F.phi[i];
+        for (int i = tid; i < nh; i += nt) s_phi[i] = F.phi[i];
         __syncthreads();
     }
 
     if (F.phases & FIELD_TABLE) {
         // phi' = sum_i d_i B^{K-1}_i, d_i = (phi_i - phi_{i-1})/h ; on cell c the functions
         // i = c-K+2..c are the pieces dpiece[j][m]; E-table = escale * phi' in monomials of u
-        for (int i = tid; i < nh; i += kFieldThreads) s_d[i] = (s_phi[i] - s_phi[(i + nh - 1) % nh]) * F.invh;
+        for (int i = tid; i < nh; i += nt) s_d[i] = (s_phi[i] - s_phi[(i + nh - 1) % nh]) * F.invh;
         __syncthreads();
         const int K1 = K - 1;
-        for (int idx = tid; idx < nh * K1; idx += kFieldThreads) {
+        for (int idx = tid; idx < nh * K1; idx += nt) {
             const int c = idx / K1, m = idx - c * K1;
             double s = 0.0;
             for (int j = 0; j < K1; j++) {
@@ -738,7 +742,7 @@ int launch_vp_field(vpm_ctx* ctx, vpm_xspace* xs, int phases, int nparts, int ha
         F.phases = FIELD_REDUCE;
         F.w_slot = F.km_slot = -1;
         prof_begin(ctx, PROF_VP_FIELD);
-    vp_field_kernel<<<1, kFieldThreads, smem, ctx->stream>>>(F);
+    vp_field_kernel<<<1, kVpFieldThreads, smem, ctx->stream>>>(F);
     prof_end(ctx);
         ctx->launches++;
         VPM_CUDA(cudaGetLastError());
@@ -750,7 +754,7 @@ int launch_vp_field(vpm_ctx* ctx, vpm_xspace* xs, int phases, int nparts, int ha
     }
     F.phases = phases;
     prof_begin(ctx, PROF_VP_FIELD);
-    vp_field_kernel<<<1, kFieldThreads, smem, ctx->stream>>>(F);
+    vp_field_kernel<<<1, kVpFieldThreads, smem, ctx->stream>>>(F);
     prof_end(ctx);
     ctx->launches++;
     VPM_CUDA(cudaGetLastError());

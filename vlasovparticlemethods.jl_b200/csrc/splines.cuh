@@ -87,20 +87,20 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// s = a[lane*stride] + a[(lane+32)*stride] + ... in exactly that (sequential) order, with eight loads in
-// flight per lane so the single-CTA field kernels are not a chain of L2 round trips
+// s = a[lane*stride] + a[(lane+32)*stride] + ... in exactly that (sequential) order, loaded in batches of eight
+// independent (predicated) loads per lane, tail included, so the single-CTA field kernels pay one L2 round trip
+// per 256 rows instead of one per row of the remainder
 __device__ __forceinline__ double strided_sum(const double* __restrict__ a, size_t stride, int n, int lane)
 {
     double s = 0.0;
-    int p = lane;
-    for (; p + 224 < n; p += 256) {
+    for (int p = lane; p < n; p += 256) {
         double t[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) t[k] = a[(size_t)(p + 32 * k) * stride];
+        for (int k = 0; k < 8; k++) t[k] = (p + 32 * k < n) ? a[(size_t)(p + 32 * k) * stride] : 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) s += t[k];
+        for (int k = 0; k < 8; k++)
+            if (p + 32 * k < n) s += t[k];
     }
-    for (; p < n; p += 32) s += a[(size_t)p * stride];
     return s;
 }
 
