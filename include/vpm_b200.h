@@ -98,6 +98,11 @@ int vpm_sample_bump_on_tail(vpm_particles* p, int64_t offset, int64_t ntotal, ui
                             double eps, double kappa, double alpha, double sigma, double v0);
 int vpm_sample_maxwellian(vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed,
                           double xlo, double xhi, double shift, int doubled, double wnum);
+/* UniformDistribution (src/examples/uniform.jl:11-34) and ShiftedUniformDistribution (shifteduniform.jl:12-38):
+ * x uniform on [xlo, xhi), v uniform on [vlo, vhi) + shift, w = wnum / ntotal.  (ShiftedNormalV,
+ * shiftednormalv.jl:10-37, is vpm_sample_maxwellian with doubled = 0.) */
+int vpm_sample_uniform(vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed,
+                       double xlo, double xhi, double vlo, double vhi, double shift, double wnum);
 /* NormalDistribution (src/examples/normal.jl:10-36): x0, v ~ N(0,1), x = ((x0 + xmax)/(2 xmax)) (xhi-xlo) + xlo with
  * xmax = ceil(max |x0|) (the data-dependent map of normal.jl:19-25), w = 1/ntotal.  xmax <= 0: take the maximum
  * over this rank's particles; multi-rank callers pass one agreed value.  *xmax_used (optional) returns it. */

@@ -10,7 +10,8 @@ module VPMB200
 using VlasovMethods
 import VlasovMethods: projection!, projection, run!, initialize!, DistributionFunction,
                       SplittingMethod, GeometricIntegrator, VlasovPoisson,
-                      LenardBernstein, ConservativeLenardBernstein, BumpOnTail, DoubleMaxwellian
+                      LenardBernstein, ConservativeLenardBernstein, BumpOnTail, DoubleMaxwellian,
+                      UniformDistribution, ShiftedUniformDistribution, ShiftedNormalV
 
 const libvpm = get(ENV, "LIBVPM_B200", "libvpm_b200.so")
 
@@ -230,6 +231,18 @@ end
 function initialize!(d::DeviceParticleDistribution, p::DoubleMaxwellian; seed::UInt64 = 0x000000005EED0001, offset::Integer = 0, ntotal::Integer = d.n)
     check(ccall((:vpm_sample_maxwellian, libvpm), Cint, (Ptr{Cvoid}, Int64, Int64, UInt64, Float64, Float64, Float64, Cint, Float64),
                 d.h, offset, ntotal, seed, p.domain[1], p.domain[2], p.shift, 1, 1.0))
+    d
+end
+# UniformDistribution / ShiftedUniformDistribution / ShiftedNormalV: src/examples/{uniform,shifteduniform,shiftednormalv}.jl
+function initialize!(d::DeviceParticleDistribution, p::Union{UniformDistribution,ShiftedUniformDistribution}; seed::UInt64 = 0x000000005EED0001, offset::Integer = 0, ntotal::Integer = d.n)
+    shift = p isa ShiftedUniformDistribution ? Float64(p.shift) : 0.0
+    check(ccall((:vpm_sample_uniform, libvpm), Cint, (Ptr{Cvoid}, Int64, Int64, UInt64, Float64, Float64, Float64, Float64, Float64, Float64),
+                d.h, offset, ntotal, seed, p.xdomain[1], p.xdomain[2], p.vdomain[1], p.vdomain[2], shift, 1.0))
+    d
+end
+function initialize!(d::DeviceParticleDistribution, p::ShiftedNormalV; seed::UInt64 = 0x000000005EED0001, offset::Integer = 0, ntotal::Integer = d.n)
+    check(ccall((:vpm_sample_maxwellian, libvpm), Cint, (Ptr{Cvoid}, Int64, Int64, UInt64, Float64, Float64, Float64, Cint, Float64),
+                d.h, offset, ntotal, seed, p.domain[1], p.domain[2], p.shift, 0, 1.0))
     d
 end
 

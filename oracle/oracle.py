@@ -80,6 +80,7 @@ def lib():
             "vpo_sample_bump_on_tail": (None, [i64, i64, i64, u64, f64, f64, f64, f64, f64, _D, _D, _D]),
             "vpo_sample_normal": (f64, [i64, i64, i64, u64, f64, f64, f64, _D, _D, _D]),
             "vpo_sample_maxwellian": (None, [i64, i64, i64, u64, f64, f64, f64, i32, f64, _D, _D, _D]),
+            "vpo_sample_uniform": (None, [i64, i64, i64, u64, f64, f64, f64, f64, f64, f64, _D, _D, _D]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -279,6 +280,13 @@ def sample_normal(N, offset=0, Ntotal=None, seed=0x5EED0001, xlo=0.0, xhi=1.0, x
     x, v, w = np.zeros(N), np.zeros(N), np.zeros(N)
     used = lib().vpo_sample_normal(N, offset, Ntotal, seed, xlo, xhi, xmax, _dp(x), _dp(v), _dp(w))
     return x, v, w, used
+
+
+def sample_uniform(N, offset=0, Ntotal=None, seed=0x5EED0001, xlo=0.0, xhi=1.0, vlo=-2.0, vhi=2.0, shift=0.0, wnum=1.0):
+    Ntotal = N if Ntotal is None else Ntotal
+    x, v, w = np.empty(N), np.empty(N), np.empty(N)
+    lib().vpo_sample_uniform(N, offset, Ntotal, seed, xlo, xhi, vlo, vhi, shift, wnum, _dp(x), _dp(v), _dp(w))
+    return x, v, w
 
 
 def sample_maxwellian(N, offset=0, Ntotal=None, seed=0x5EED0001, xlo=0.0, xhi=1.0, shift=0.0, doubled=False, wnum=1.0):

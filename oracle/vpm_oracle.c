@@ -790,6 +790,19 @@ VPO_API double vpo_sample_normal(int64_t N, int64_t offset, int64_t Ntotal, uint
     return xmax;
 }
 
+/* UniformDistribution / ShiftedUniformDistribution (src/examples/uniform.jl:11-34, shifteduniform.jl:12-38):
+ * x uniform on [xlo,xhi), v uniform on [vlo,vhi) + shift, w = wnum/Ntotal */
+VPO_API void vpo_sample_uniform(int64_t N, int64_t offset, int64_t Ntotal, uint64_t seed, double xlo, double xhi,
+                                double vlo, double vhi, double shift, double wnum, double *x, double *v, double *w)
+{
+    for (int64_t p = 0; p < N; p++) {
+        uint64_t gi = (uint64_t)(offset + p);
+        x[p] = xlo + (xhi - xlo) * vpo_uniform(seed, gi, 0);
+        v[p] = vlo + (vhi - vlo) * vpo_uniform(seed, gi, 1) + shift;
+        w[p] = wnum / (double)Ntotal;
+    }
+}
+
 /* Maxwellian mixture in v, uniform x on [xlo,xhi):
  *   nshift=0: v~N(0,1)   (NormalDistribution v-part, src/examples/normal.jl:16)
  *   DoubleMaxwellian: first floor(Ntotal/2) particles +shift, rest -shift (doublemaxwellian.jl:17-29)

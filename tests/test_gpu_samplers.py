@@ -31,6 +31,29 @@ def test_normal_distribution_sampler(vpm, oracle):
     np.testing.assert_allclose(d2.get("x"), xo2, rtol=1e-13, atol=1e-14)
 
 
+def test_uniform_and_shifted_samplers(vpm, oracle):
+    """UniformDistribution, ShiftedUniformDistribution, ShiftedNormalV (src/examples/{uniform,shifteduniform,
+    shiftednormalv}.jl) against their CPU twins, as slabs of a larger ensemble."""
+    n, off, ntot = 4001, 1234, 20000
+    d = vpm.ParticleDistribution(1, 1, n)
+    vpm.initialize_(d, vpm.UniformDistribution((0.5, 2.5), (-3.0, 1.0)), offset=off, ntotal=ntot)
+    xo, vo, wo = oracle.sample_uniform(n, off, ntot, xlo=0.5, xhi=2.5, vlo=-3.0, vhi=1.0)
+    x, v, w = d.get()
+    np.testing.assert_allclose(x, xo, rtol=1e-14)
+    np.testing.assert_allclose(v, vo, rtol=1e-14, atol=1e-15)
+    np.testing.assert_array_equal(w, wo)
+    assert 0.5 <= x.min() and x.max() < 2.5 and -3.0 <= v.min() and v.max() < 1.0 and w[0] == 1.0 / ntot
+    vpm.initialize_(d, vpm.ShiftedUniformDistribution((0.0, 1.0), (-2.0, 2.0), 2.0), offset=off, ntotal=ntot)
+    xo, vo, wo = oracle.sample_uniform(n, off, ntot, shift=2.0)
+    np.testing.assert_allclose(d.get("v"), vo, rtol=1e-14, atol=1e-15)
+    assert 0.0 <= d.get("v").min() and d.get("v").max() < 4.0
+    vpm.initialize_(d, vpm.ShiftedNormalV((-5.0, 5.0), 2.0), offset=off, ntotal=ntot)
+    xo, vo, wo = oracle.sample_maxwellian(n, off, ntot, xlo=-5.0, xhi=5.0, shift=2.0)
+    np.testing.assert_allclose(d.get("x"), xo, rtol=1e-14, atol=1e-15)
+    np.testing.assert_allclose(d.get("v"), vo, rtol=1e-13, atol=1e-14)
+    assert abs(d.get("v").mean() - 2.0) < 0.1
+
+
 def test_config1_vlasov_poisson_script(vpm, oracle):
     """scripts/vlasov_poisson.jl:6-30 with its shipped parameters, both field modes, against the oracle."""
     npart, nknot, order, tstep, tspan, domain = 10000, 16, 3, 0.1, (0.0, 20.0), (0.0, 1.0)

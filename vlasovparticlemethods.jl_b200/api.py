@@ -732,8 +732,24 @@ class NormalDistribution:
 
 
 class UniformDistribution:
-    def __init__(self, domain=(0.0, 1.0)):
-        self.domain = domain
+    """UniformDistribution(xdomain, vdomain): x and v uniform (src/examples/uniform.jl:2-8)"""
+
+    def __init__(self, xdomain=(0.0, 1.0), vdomain=(-2.0, 2.0)):
+        self.xdomain, self.vdomain = xdomain, vdomain
+
+
+class ShiftedUniformDistribution:
+    """ShiftedUniformDistribution(xdomain, vdomain, shift): v uniform on vdomain + shift (src/examples/shifteduniform.jl:2-9)"""
+
+    def __init__(self, xdomain=(0.0, 1.0), vdomain=(-2.0, 2.0), shift=2.0):
+        self.xdomain, self.vdomain, self.shift = xdomain, vdomain, shift
+
+
+class ShiftedNormalV:
+    """ShiftedNormalV(domain, shift): x uniform on domain, v ~ N(shift, 1) (src/examples/shiftednormalv.jl:1-7)"""
+
+    def __init__(self, domain=(-5.0, 5.0), shift=2.0):
+        self.domain, self.shift = domain, shift
 
 
 class BumpOnTail:
@@ -765,9 +781,12 @@ def initialize_(dist, params, seed=DEFAULT_SEED, offset=0, ntotal=None, xmax=Non
     elif isinstance(params, DoubleMaxwellian):
         check(_lib().vpm_sample_maxwellian(dist._h, int(offset), ntotal, int(seed), params.domain[0], params.domain[1],
                                             float(params.shift), 1, 1.0))
-    elif isinstance(params, UniformDistribution):
+    elif isinstance(params, ShiftedNormalV):
         check(_lib().vpm_sample_maxwellian(dist._h, int(offset), ntotal, int(seed), params.domain[0], params.domain[1],
-                                            0.0, 0, 1.0))
+                                            float(params.shift), 0, 1.0))
+    elif isinstance(params, (UniformDistribution, ShiftedUniformDistribution)):
+        check(_lib().vpm_sample_uniform(dist._h, int(offset), ntotal, int(seed), params.xdomain[0], params.xdomain[1],
+                                         params.vdomain[0], params.vdomain[1], float(getattr(params, "shift", 0.0)), 1.0))
     elif isinstance(params, NormalDistribution):
         used = C.c_double()
         check(_lib().vpm_sample_normal(dist._h, int(offset), ntotal, int(seed), params.domain[0], params.domain[1],

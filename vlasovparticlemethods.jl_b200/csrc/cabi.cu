@@ -455,6 +455,15 @@ int vpm_sample_maxwellian(vpm_particles* p, int64_t offset, int64_t ntotal, uint
     return launch_sample_maxwellian(p->ctx, p, offset, ntotal, seed, xlo, xhi, shift, doubled, wnum);
 }
 
+int vpm_sample_uniform(vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed, double xlo, double xhi, double vlo,
+                       double vhi, double shift, double wnum)
+{
+    VPM_REQUIRE(p && ntotal > 0, "vpm_sample_uniform: bad arguments");
+    VPM_CUDA(cudaSetDevice(p->ctx->device));
+    p->uw = false;
+    return launch_sample_uniform(p->ctx, p, offset, ntotal, seed, xlo, xhi, vlo, vhi, shift, wnum);
+}
+
 /* ---------------------------------------------------------------- x-space */
 
 int vpm_xspace_create(vpm_ctx* ctx, double lo, double hi, int order, int n_basis, vpm_xspace** out)

@@ -121,6 +121,20 @@ __global__ void sample_maxwellian_kernel(long long n, long long offset, long lon
     }
 }
 
+// UniformDistribution / ShiftedUniformDistribution (src/examples/uniform.jl:11-34, shifteduniform.jl:12-38)
+__global__ void sample_uniform_kernel(long long n, long long offset, long long ntotal, uint64_t seed, double xlo, double xhi,
+                                      double vlo, double vhi, double shift, double wnum, double* __restrict__ x,
+                                      double* __restrict__ v, double* __restrict__ w)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t gi = (uint64_t)(offset + i);
+        x[i] = xlo + (xhi - xlo) * uniform01(seed, gi, 0);
+        v[i] = vlo + (vhi - vlo) * uniform01(seed, gi, 1) + shift;
+        w[i] = wnum / (double)ntotal;
+    }
+}
+
 __global__ void fill_kernel(double* __restrict__ a, long long n, double value)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -238,6 +252,16 @@ int launch_sample_maxwellian(vpm_ctx* ctx, vpm_particles* p, int64_t offset, int
 {
     sample_maxwellian_kernel<<<grid_for(ctx, p->n, 256), 256, 0, ctx->stream>>>(p->n, offset, ntotal, seed, xlo, xhi, shift, doubled,
                                                                              wnum, p->x, p->v, p->w);
+    ctx->launches++;
+    VPM_CUDA(cudaGetLastError());
+    return VPM_OK;
+}
+
+int launch_sample_uniform(vpm_ctx* ctx, vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed, double xlo, double xhi,
+                          double vlo, double vhi, double shift, double wnum)
+{
+    sample_uniform_kernel<<<grid_for(ctx, p->n, 256), 256, 0, ctx->stream>>>(p->n, offset, ntotal, seed, xlo, xhi, vlo, vhi, shift, wnum,
+                                                                          p->x, p->v, p->w);
     ctx->launches++;
     VPM_CUDA(cudaGetLastError());
     return VPM_OK;
