@@ -324,7 +324,7 @@ VPO_API void vpo_mass_solve_x(const vpo_xspace *s, const double *rhs, double *rh
  * phi(x, Derivative(1)) [3P functor; call sites src/models/vlasov_poisson.jl:27,48,65] */
 VPO_API double vpo_xeval(const vpo_xspace *s, const double *coef, double x, int deriv)
 {
-    double xr, tl[2 * VPO_MAXK], b[VPO_MAXK];
+    double xr, tl[2 * VPO_MAXK] = {0.0}, b[VPO_MAXK];
     int c = xlocate(s, x, &xr);
     xwindow(s, c, tl);
     if (deriv == 0) basis_window(tl, s->K, xr, b);
