@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <new>
 
@@ -61,6 +62,15 @@ int kernel_occupancy(vpm_ctx* ctx, const void* kern, int block, size_t smem, int
     VPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, block, smem));
     cache[key] = *occ;
     return VPM_OK;
+}
+
+bool pdl_enabled()
+{
+    static const bool on = []() {
+        const char* e = getenv("VPM_TUNE_PDL");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
 }
 
 int ensure_partials(vpm_ctx* ctx, size_t doubles) { return grow(&ctx->partials, &ctx->partials_cap, doubles, ctx->stream); }

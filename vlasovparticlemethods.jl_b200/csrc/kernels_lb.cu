@@ -337,9 +337,11 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
     double* s_hbase = s_tab + (P.ncell + 1) * TabCfg<K>::TSP;
     double* s_hist = s_hbase + (HM == 0 ? tid : (HM == 1 ? (tid >> 5) : 0));
 
-    if (ev) lb_stage_table<K>(P, s_tab, tid, kBlock);
+    pdl_trigger();
     if (dep)
         for (int i = tid; i < P.nbfull * HS; i += kBlock) s_hbase[i] = 0.0;
+    pdl_wait();   // everything below reads what the previous kernels of the stream wrote (f table, A, stage vectors)
+    if (ev) lb_stage_table<K>(P, s_tab, tid, kBlock);
     __syncthreads();
     const double A1 = P.conservative && ev ? P.scal[0] : 0.0, A2 = P.conservative && ev ? P.scal[1] : 1.0;
 
@@ -458,7 +460,7 @@ __global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE ==
     uint64_t* s_full = reinterpret_cast<uint64_t*>(s_stage + (size_t)P.stages * ns * kLbTile);
     uint64_t* s_empty = s_full + kLbMaxStages;
 
-    if (ev) lb_stage_table<K>(P, s_tab, tid, kLbRingThreads);
+    pdl_trigger();
     if (dep)
         for (int i = tid; i < P.nbfull * kBlock; i += kLbRingThreads) s_hbase[i] = 0.0;
     if (tid == 0) {
@@ -468,6 +470,8 @@ __global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE ==
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_wait();   // everything below reads what the previous kernels of the stream wrote (f table, A, stage vectors)
+    if (ev) lb_stage_table<K>(P, s_tab, tid, kLbRingThreads);
     __syncthreads();
 
     const long long ntiles = P.n / kLbTile;
@@ -578,8 +582,10 @@ __global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbField
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nwarps = nt / 32;
     const int K = F.K, nv = F.nv;
 
+    pdl_trigger();
     if (F.phases & LBF_SOLVE) {
         // s_chol[i][0] = 1 / L(i,i), s_chol[i][k] = L(i, i-k) for 1 <= k < K, k <= i; zero elsewhere
+        // (constant operator: staged before the dependency wait, while the particle pass drains)
         for (int i = tid; i < (nv + kCholW - 1) * kCholW; i += nt) {
             const int r = i / kCholW, k = i - r * kCholW;
             double c = 0.0;
@@ -587,6 +593,7 @@ __global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbField
             s_chol[i] = (k == 0 && r < nv) ? 1.0 / c : c;
         }
     }
+    pdl_wait();
     if (F.phases & LBF_REDUCE) {
         for (int b = warp; b < F.nbfull; b += nwarps) {
             const double s = warp_sum(strided_sum(F.partials + b, (size_t)F.nbfull, F.nparts, lane));
@@ -794,7 +801,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
     P.partials = ctx->partials;
     P.red_partials = ctx->partials + (size_t)grid * vs->nbfull;
     prof_begin(ctx, PROF_LB_PASS);
-    kern<<<(unsigned)grid, block, smem, ctx->stream>>>(P);
+    VPM_CUDA(launch_pdl(kern, (unsigned)grid, (unsigned)block, smem, ctx->stream, P));
     prof_end(ctx);
     ctx->launches++;
     VPM_CUDA(cudaGetLastError());
@@ -839,7 +846,7 @@ int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nr
     } else if (ctx->comm.comm && red) {
         F.phases = red;
         prof_begin(ctx, PROF_LB_FIELD);
-    lb_field_kernel<<<1, kLbFieldThreads, smem, ctx->stream>>>(F);
+    VPM_CUDA(launch_pdl(lb_field_kernel, 1u, (unsigned)kLbFieldThreads, smem, ctx->stream, F));
     prof_end(ctx);
         ctx->launches++;
         VPM_CUDA(cudaGetLastError());
@@ -854,7 +861,7 @@ int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nr
     }
     F.phases = phases;
     prof_begin(ctx, PROF_LB_FIELD);
-    lb_field_kernel<<<1, kLbFieldThreads, smem, ctx->stream>>>(F);
+    VPM_CUDA(launch_pdl(lb_field_kernel, 1u, (unsigned)kLbFieldThreads, smem, ctx->stream, F));
     prof_end(ctx);
     ctx->launches++;
     VPM_CUDA(cudaGetLastError());

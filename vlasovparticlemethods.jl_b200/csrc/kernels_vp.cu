@@ -120,10 +120,12 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
     double* s_hbase = s_etab + ((P.nh * ES + 1) & ~1);                          // nb * HS
     double* s_hist = s_hbase + (HM == 0 ? tid : (HM == 1 ? (tid >> 5) : 0));  // this thread's copy
 
-    if (flags & VP_KICK1)
-        for (int i = tid; i < P.nh * ES; i += kBlock) s_etab[i] = P.etab[i];
+    pdl_trigger();
     if (flags & VP_DEPOSIT)
         for (int i = tid; i < nb * HS; i += kBlock) s_hbase[i] = 0.0;
+    pdl_wait();   // everything below reads what the previous kernels of the stream wrote (E table, particles)
+    if (flags & VP_KICK1)
+        for (int i = tid; i < P.nh * ES; i += kBlock) s_etab[i] = P.etab[i];
     __syncthreads();
 
     double ksum = 0.0, msum = 0.0;
@@ -231,12 +233,14 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_tma_kernel(const VpDev P
     double* s_stage = s_hbase + (size_t)nb * kBlock;                 // kTmaStages x {x, v, w} x kTmaTile
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + (size_t)kTmaStages * 3 * kTmaTile);
 
-    for (int i = tid; i < P.nh * ES; i += kBlock) s_etab[i] = P.etab[i];
+    pdl_trigger();
     for (int i = tid; i < nb * kBlock; i += kBlock) s_hbase[i] = 0.0;
     if (tid == 0) {
         for (int s = 0; s < kTmaStages; s++) mbar_init(&s_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_wait();   // everything below reads what the previous kernels of the stream wrote (E table, particles)
+    for (int i = tid; i < P.nh * ES; i += kBlock) s_etab[i] = P.etab[i];
     __syncthreads();
 
     const long long ntiles = P.n / kTmaTile;
@@ -335,10 +339,12 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_tiled_kernel(const VpDev
     int* s_off = s_cnt + nh;                                // nh + 1
     __shared__ int s_wsum[kBlock / 32];
 
-    if (flags & VP_KICK1)
-        for (int i = tid; i < nh * ES; i += kBlock) s_etab[i] = P.etab[i];
+    pdl_trigger();
     for (int i = tid; i < nh * K; i += kBlock) s_acc[i] = 0.0;
     for (int i = tid; i < nh; i += kBlock) s_cnt[i] = 0;
+    pdl_wait();
+    if (flags & VP_KICK1)
+        for (int i = tid; i < nh * ES; i += kBlock) s_etab[i] = P.etab[i];
     __syncthreads();
 
     double ksum = 0.0, msum = 0.0;
@@ -484,13 +490,16 @@ __global__ void __launch_bounds__(kVpFieldThreads) vp_field_kernel(const FieldDe
     __shared__ double s_w[kVpFieldThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nwarps = nt / 32;
     const int nh = F.nh, K = F.K;
-    // constant operators into shared memory up front: their L2 latency overlaps the partial-row loads
+    // constant operators into shared memory up front (before the dependency wait: they are never written by a
+    // kernel); their L2 latency overlaps the tail of the particle pass and the partial-row loads
+    pdl_trigger();
     if (F.phases & FIELD_SOLVE)
         for (int i = tid; i < nh; i += nt) s_ginv[i] = F.ginv[i];
     if (F.phases & (FIELD_SOLVE | FIELD_TABLE)) {
         for (int i = tid; i < 2 * K - 1; i += nt) s_stiff[i] = F.stiff[i];
         for (int i = tid; i < (K - 1) * (K - 1); i += nt) s_dpiece[i] = F.dpiece[i];
     }
+    pdl_wait();
 
     if (F.phases & FIELD_REDUCE) {
         // fixed-order reduction of the per-CTA partial rows: lane-strided partial sums + xor tree
@@ -692,7 +701,7 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     P.kin_partials = ctx->partials + (size_t)grid * nb;
 
     prof_begin(ctx, PROF_VP_PASS);
-    kern<<<(unsigned)grid, kBlock, smem, ctx->stream>>>(P);
+    VPM_CUDA(launch_pdl(kern, (unsigned)grid, (unsigned)kBlock, smem, ctx->stream, P));
     prof_end(ctx);
     ctx->launches++;
     VPM_CUDA(cudaGetLastError());
@@ -742,7 +751,7 @@ int launch_vp_field(vpm_ctx* ctx, vpm_xspace* xs, int phases, int nparts, int ha
         F.phases = FIELD_REDUCE;
         F.w_slot = F.km_slot = -1;
         prof_begin(ctx, PROF_VP_FIELD);
-    vp_field_kernel<<<1, kVpFieldThreads, smem, ctx->stream>>>(F);
+    VPM_CUDA(launch_pdl(vp_field_kernel, 1u, (unsigned)kVpFieldThreads, smem, ctx->stream, F));
     prof_end(ctx);
         ctx->launches++;
         VPM_CUDA(cudaGetLastError());
@@ -754,7 +763,7 @@ int launch_vp_field(vpm_ctx* ctx, vpm_xspace* xs, int phases, int nparts, int ha
     }
     F.phases = phases;
     prof_begin(ctx, PROF_VP_FIELD);
-    vp_field_kernel<<<1, kVpFieldThreads, smem, ctx->stream>>>(F);
+    VPM_CUDA(launch_pdl(vp_field_kernel, 1u, (unsigned)kVpFieldThreads, smem, ctx->stream, F));
     prof_end(ctx);
     ctx->launches++;
     VPM_CUDA(cudaGetLastError());

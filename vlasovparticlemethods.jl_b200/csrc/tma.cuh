@@ -42,4 +42,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "memory");
 }
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-serialization
+// attribute may become resident while its predecessor in the stream is still draining.  pdl_trigger() lets the
+// NEXT kernel of the stream start its prologue early; pdl_wait() blocks until the PREVIOUS kernel has completed
+// and its memory is visible -- everything before it must touch only this CTA's own shared memory or constants.
+// Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace vpm

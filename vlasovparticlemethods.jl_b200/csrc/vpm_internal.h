@@ -131,6 +131,26 @@ enum ProfKind : int { PROF_VP_PASS = 0, PROF_VP_FIELD = 1, PROF_LB_PASS = 2, PRO
 void prof_begin(vpm_ctx* ctx, int kind);   // no-ops unless ctx->profile
 void prof_end(vpm_ctx* ctx);
 
+// Launch with programmatic stream serialization (PDL): the kernel may start its prologue while the previous
+// kernel of the stream drains; it must call pdl_wait() (tma.cuh) before touching that kernel's results.
+// VPM_TUNE_PDL=0 falls back to plain stream-ordered launches.
+bool pdl_enabled();
+template <typename P>
+cudaError_t launch_pdl(void (*kern)(const P), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, const P& arg)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, arg);
+}
+
 // ---------------- Vlasov-Poisson passes (kernels_vp.cu) ----------------
 enum VpFlags : int {
     VP_PRE = 1,        // x += tau_pre * v before the kick
