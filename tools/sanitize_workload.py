@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Small end-to-end workload for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): every particle
+pass variant of the library at sizes that exercise whole ring tiles plus a ragged remainder, both histogram
+fallbacks, the tiled large-grid deposit, the operators and the samplers.  Checks results against the oracle so
+that a sanitizer-clean run is also a correct one.
+
+    compute-sanitizer --tool racecheck python tools/sanitize_workload.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import vpm_b200 as vpm
+    from oracle import oracle as orc
+    nrm = lambda a, b: np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+    n = 3 * 512 + 77
+    # ---- Vlasov-Poisson: TMA main pass, prologue/epilogue passes, field kernel, both modes
+    bot = vpm.BumpOnTail()
+    x, v, w = orc.sample_bump_on_tail(n)
+    for field in ("selfconsistent", "frozen"):
+        d = vpm.ParticleDistribution(1, 1, n).set(x, v, w)
+        pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, bot.L), 4, 16))
+        m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 0.3), 0.1, field=field)
+        vpm.run_(m, diag_mode=1)
+        xs = orc.XSpace(0.0, bot.L, 4, 16)
+        if field == "selfconsistent":
+            xo, vo, _, _ = xs.strang_selfconsistent(x, v, w, 0.1, 3)
+        else:
+            xo, vo, _ = xs.strang_frozen(x, v, x, w, 0.1, 3)
+        xg, vg, _ = d.get()
+        assert nrm(xg, xo) < 1e-12 and nrm(vg, vo) < 1e-12, field
+    # large grid: tiled segmented-reduction deposit
+    d = vpm.ParticleDistribution(1, 1, n).set(x, v, w)
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, bot.L), 4, 400))
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 0.2), 0.1, field="selfconsistent")
+    vpm.run_(m, diag_mode=1)
+    xo, vo, _, _ = orc.XSpace(0.0, bot.L, 4, 400).strang_selfconsistent(x, v, w, 0.1, 2)
+    assert nrm(d.get("x"), xo) < 1e-12
+    # ---- Lenard-Bernstein: ring passes, register passes, histogram fallbacks, uniform weights
+    vv = np.r_[np.random.default_rng(1).standard_normal(n - 4) * 1.2, [-10.0, 10.0, -10.5, 11.0]]
+    ww = np.full(n, 1.0 / n)
+    vs = orc.VSpace(-10.0, 10.0, 41, 4)
+    sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
+    for env in ({"VPM_TUNE_LBTMA": "-1"}, {"VPM_TUNE_LBTMA": "0"}, {"VPM_TUNE_LBTMA": "190"}, {"VPM_TUNE_HM": "1"}, {"VPM_TUNE_HM": "2"}):
+        os.environ.pop("VPM_TUNE_LBTMA", None)
+        os.environ.pop("VPM_TUNE_HM", None)
+        os.environ.update(env)
+        for cons in (False, True):
+            for uw in (False, True):
+                d = vpm.ParticleDistribution(1, 1, n).set(np.zeros(n), vv, ww)
+                if uw:
+                    d.set_uniform_weight(1.0 / n)
+                model = (vpm.ConservativeLenardBernstein if cons else vpm.LenardBernstein)(d, vpm.CollisionEntropy(sd), nu=0.8)
+                gi = vpm.GeometricIntegrator(model, (0.0, 0.04), 0.02)
+                vpm.run_(gi)
+                vo, _ = vs.rk438(vv, ww, 0.8, 0.02, 2, conservative=cons)
+                assert np.abs(d.get("v") - vo).max() < 1e-10, (env, cons, uw)
+    os.environ.pop("VPM_TUNE_LBTMA", None)
+    os.environ.pop("VPM_TUNE_HM", None)
+    # operators and samplers
+    d = vpm.ParticleDistribution(1, 1, n)
+    vpm.initialize_(d, vpm.DoubleMaxwellian((-10.0, 10.0), 2.0))
+    fs = vpm.projection(None, d, sd)
+    fs(d.get("v"))
+    vpm.compute_f_densities(sd, d.get("v"))
+    vpm.initialize_(d, vpm.NormalDistribution((0.0, 1.0)))
+    vpm.initialize_(d, vpm.UniformDistribution())
+    print("sanitize workload: all results match the oracle")
+
+
+if __name__ == "__main__":
+    main()
