@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_tma_kernel(const VpDev P
     double* s_hbase = s_etab + ((P.nh * ES + 1) & ~1);
     double* s_hist = s_hbase + tid;
     double* s_stage = s_hbase + (size_t)nb * kBlock;                 // kTmaStages x {x, v, w} x kTmaTile
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + (size_t)kTmaStages * 3 * kTmaTile);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + (size_t)kTmaStages * (P.use_uw ? 2 : 3) * kTmaTile);
 
     pdl_trigger();
     for (int i = tid; i < nb * kBlock; i += kBlock) s_hbase[i] = 0.0;
@@ -244,10 +244,11 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_tma_kernel(const VpDev P
     __syncthreads();
 
     const long long ntiles = P.n / kTmaTile;
+    const int nstream = P.use_uw ? 2 : 3;   // uniform weights: no w tile, a stage is two tiles
     auto issue = [&](int s, long long g) {
-        double* dst = s_stage + (size_t)s * 3 * kTmaTile;
+        double* dst = s_stage + (size_t)s * nstream * kTmaTile;
         const bool uw = P.use_uw;
-        mbar_expect_tx(&s_bar[s], (uint32_t)((uw ? 2 : 3) * kTmaTile * sizeof(double)));
+        mbar_expect_tx(&s_bar[s], (uint32_t)(nstream * kTmaTile * sizeof(double)));
         bulk_g2s(dst, P.x_in + g * kTmaTile, kTmaTile * sizeof(double), &s_bar[s]);
         bulk_g2s(dst + kTmaTile, P.v_in + g * kTmaTile, kTmaTile * sizeof(double), &s_bar[s]);
         if (!uw) bulk_g2s(dst + 2 * kTmaTile, P.w + g * kTmaTile, kTmaTile * sizeof(double), &s_bar[s]);
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_tma_kernel(const VpDev P
         if (g >= ntiles) break;
         const int s = (int)(it % kTmaStages);
         mbar_wait(&s_bar[s], (uint32_t)((it / kTmaStages) & 1));
-        const double* src = s_stage + (size_t)s * 3 * kTmaTile;
+        const double* src = s_stage + (size_t)s * nstream * kTmaTile;
         double2 xa = *reinterpret_cast<const double2*>(src + 2 * tid);
         double2 va = *reinterpret_cast<const double2*>(src + kTmaTile + 2 * tid);
         double2 wa = P.use_uw ? wdef : *reinterpret_cast<const double2*>(src + 2 * kTmaTile + 2 * tid);
@@ -667,13 +668,18 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     }();
     const bool tma = tune_tma && !tiled && hm == 0 && vec && (p.flags == kMainFlags || p.flags == kFrozenFlags);
     if (tma && p.flags == kFrozenFlags) {  // no histograms: a deeper ring fits
-        smem += sizeof(double) * (size_t)4 * 3 * kTmaTile + sizeof(uint64_t) * 4;
+        smem += sizeof(double) * (size_t)4 * (p.use_uw ? 2 : 3) * kTmaTile + sizeof(uint64_t) * 4;
         kern = vp_pass_tma_kernel<K, kFrozenFlags, 3, 4>;
+    } else if (tma && p.use_uw && tune_tma == 1) {
+        // uniform weights: two tiles per stage, so a third stage fits in the shared memory of the 3-CTA/SM configuration
+        smem += sizeof(double) * (size_t)3 * 2 * kTmaTile + sizeof(uint64_t) * 3;
+        kern = vp_pass_tma_kernel<K, kMainFlags, 3, 3>;
     } else if (tma) {
-        const int stages = tune_tma == 2 ? 3 : (tune_tma == 3 ? 4 : 2);
-        smem += sizeof(double) * (size_t)stages * 3 * kTmaTile + sizeof(uint64_t) * stages;
+        const int stages = (tune_tma == 2 || tune_tma == 4) ? 3 : (tune_tma == 3 ? 4 : 2);
+        smem += sizeof(double) * (size_t)stages * (p.use_uw ? 2 : 3) * kTmaTile + sizeof(uint64_t) * stages;
         kern = tune_tma == 2 ? vp_pass_tma_kernel<K, kMainFlags, 2, 3>
-             : (tune_tma == 3 ? vp_pass_tma_kernel<K, kMainFlags, 2, 4> : vp_pass_tma_kernel<K, kMainFlags, 3, 2>);
+             : tune_tma == 3 ? vp_pass_tma_kernel<K, kMainFlags, 2, 4>
+             : tune_tma == 4 ? vp_pass_tma_kernel<K, kMainFlags, 3, 3> : vp_pass_tma_kernel<K, kMainFlags, 3, 2>;
     } else if (tiled) kern = tune_tile == 1 ? vp_pass_tiled_kernel<K, 8, 2> : (tune_tile == 2 ? vp_pass_tiled_kernel<K, 4, 2> : vp_pass_tiled_kernel<K, 4, 3>);
     else if (hm == 1) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 1> : vp_pass_kernel<K, -1, 1, 3, 1>;
     else if (hm == 2) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 2> : vp_pass_kernel<K, -1, 1, 3, 2>;
