@@ -193,6 +193,13 @@ int vpm_lb_rk438_steps(vpm_vspace* vs, vpm_particles* p, double nu, double dt, i
                        double* diag_host);
 int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double dt, int nsteps, int conservative);
 int vpm_vspace_get(vpm_vspace* vs, double* rhs_host, double* coef_host);
+/* projection!(init::SplineDistribution, final::ParticleDistribution) -- an empty TODO upstream
+ * (src/projections/distribution.jl:57-61): draw the velocities of p from the spline f_s by stratified inverse-CDF
+ * sampling (quantile (offset + i + r) / ntotal of the cell-wise clipped CDF; r = 1/2, or a counter-based uniform when
+ * jitter != 0) with equal weights w = (integral of f_s) / ntotal; x is left untouched.  coef_host == NULL uses the
+ * coefficients of the last projection / mass solve.  *mass_out (optional) returns the integral. */
+int vpm_resample_v(vpm_vspace* vs, const double* coef_host, vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed,
+                   int jitter, double* mass_out);
 
 /* ---- host-side operator construction (no GPU needed; what the spaces upload at creation) ----------- */
 /* galerkin_matrix of the periodic basis: first rows (circulant) of the mass and stiffness matrices and of

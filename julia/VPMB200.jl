@@ -246,4 +246,14 @@ function initialize!(d::DeviceParticleDistribution, p::ShiftedNormalV; seed::UIn
     d
 end
 
+# projection!(init::SplineDistribution, final::ParticleDistribution): an empty TODO upstream
+# (src/projections/distribution.jl:57-61) -- stratified inverse-CDF resampling of the velocities from the spline
+function projection!(init::DeviceSplineDistribution, final::DeviceParticleDistribution; seed::UInt64 = 0x000000005EED0001,
+                     offset::Integer = 0, ntotal::Integer = final.n, jitter::Bool = false)
+    mass = Ref{Float64}(0.0)
+    check(ccall((:vpm_resample_v, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}, Int64, Int64, UInt64, Cint, Ref{Float64}),
+                init.h, C_NULL, final.h, offset, ntotal, seed, jitter ? 1 : 0, mass))
+    final
+end
+
 end # module

@@ -80,6 +80,7 @@ def lib():
             "vpo_sample_bump_on_tail": (None, [i64, i64, i64, u64, f64, f64, f64, f64, f64, _D, _D, _D]),
             "vpo_sample_normal": (f64, [i64, i64, i64, u64, f64, f64, f64, _D, _D, _D]),
             "vpo_sample_maxwellian": (None, [i64, i64, i64, u64, f64, f64, f64, i32, f64, _D, _D, _D]),
+            "vpo_resample_v": (f64, [vp, _D, i64, i64, i64, u64, i32, _D, _D]),
             "vpo_sample_uniform": (None, [i64, i64, i64, u64, f64, f64, f64, f64, f64, f64, _D, _D, _D]),
         }
         for name, (res, args) in sig.items():
@@ -245,6 +246,14 @@ class VSpace:
         A = np.zeros(2)
         lib().vpo_lb_rhs(self._h, v.size, _dp(v), _dp(w), float(nu), int(conservative), _dp(vdot), _dp(coef), _dp(A))
         return vdot, coef, A
+
+    def resample(self, coef, N, offset=0, Ntotal=None, seed=0x5EED0001, jitter=False):
+        """spline -> particles by stratified inverse-CDF sampling (quadrature + bisection); returns v, w, mass"""
+        coef = _f64(coef)
+        Ntotal = N if Ntotal is None else Ntotal
+        v, w = np.empty(N), np.empty(N)
+        mass = lib().vpo_resample_v(self._h, _dp(coef), N, offset, Ntotal, seed, int(jitter), _dp(v), _dp(w))
+        return v, w, mass
 
     def rk438(self, v, w, nu, dt, nsteps, conservative=False, diag=True):
         v, w = _f64(v).copy(), _f64(w)

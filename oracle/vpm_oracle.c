@@ -691,6 +691,58 @@ VPO_API void vpo_lb_rk438(const vpo_vspace *s, int64_t N, double *v, const doubl
     free(k1); free(k2); free(k3); free(k4); free(q);
 }
 
+/* ---- spline -> particles: stratified inverse-CDF sampling of f_s --------------
+ * projection!(init::SplineDistribution, final::ParticleDistribution) is an empty TODO upstream
+ * (src/projections/distribution.jl:57-61); this is the checker for the library's vpm_resample_v, by an
+ * independent route: cell masses and partial integrals by Gauss-Legendre quadrature of vpo_veval (de Boor
+ * evaluation), inversion by plain bisection.  Quantile of particle gi: (gi + r)/Ntotal * M with r = 1/2 or the
+ * counter-based uniform of stream 7 (jitter). */
+VPO_API double vpo_uniform(uint64_t seed, uint64_t idx, uint32_t stream);
+
+static double vint(const vpo_vspace *s, const double *coef, double a, double b, const double *xq, const double *wq)
+{
+    double r = 0.0;
+    for (int q = 0; q < s->K; q++) r += wq[q] * vpo_veval(s, coef, 0.5 * (a + b) + 0.5 * (b - a) * xq[q], 0);
+    return 0.5 * (b - a) * r;
+}
+
+VPO_API double vpo_resample_v(const vpo_vspace *s, const double *coef, int64_t N, int64_t offset, int64_t Ntotal,
+                              uint64_t seed, int jitter, double *v, double *w)
+{
+    double xq[VPO_MAXK], wq[VPO_MAXK];
+    gauss_legendre(s->K, xq, wq);
+    double *cum = (double *)malloc((size_t)(s->ncell + 1) * sizeof(double));
+    cum[0] = 0.0;
+    for (int c = 0; c < s->ncell; c++) {
+        double m = vint(s, coef, s->br[c], s->br[c + 1], xq, wq);
+        cum[c + 1] = cum[c] + (m > 0.0 ? m : 0.0);
+    }
+    const double M = cum[s->ncell];
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) if (g_threads > 1 && N > 1024)
+#endif
+    for (int64_t p = 0; p < N; p++) {
+        uint64_t gi = (uint64_t)(offset + p);
+        double r = jitter ? vpo_uniform(seed, gi, 7) : 0.5;
+        double y = ((double)gi + r) / (double)Ntotal * M;
+        int a = 0, b = s->ncell;
+        while (b - a > 1) {
+            int mid = (a + b) >> 1;
+            if (cum[mid] <= y) a = mid; else b = mid;
+        }
+        double target = y - cum[a], lo = s->br[a], hi = s->br[a + 1];
+        for (int it = 0; it < 80 && hi > lo; it++) {
+            double mid = 0.5 * (lo + hi);
+            if (mid <= lo || mid >= hi) break;
+            if (vint(s, coef, s->br[a], mid, xq, wq) > target) hi = mid; else lo = mid;
+        }
+        v[p] = 0.5 * (lo + hi);
+        w[p] = M / (double)Ntotal;
+    }
+    free(cum);
+    return M;
+}
+
 /* ---- samplers: CPU twin of the device generators --------------------------- */
 /* The reference draws from an unseeded global RNG + Sobol (src/examples/ .jl files), so bit parity
  * is impossible by construction; the target *distributions* are restated with a counter-based

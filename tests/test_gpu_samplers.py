@@ -54,6 +54,41 @@ def test_uniform_and_shifted_samplers(vpm, oracle):
     assert abs(d.get("v").mean() - 2.0) < 0.1
 
 
+def test_resample_spline_to_particles(vpm, oracle):
+    """projection!(init::SplineDistribution, final::ParticleDistribution) (an empty TODO upstream,
+    src/projections/distribution.jl:57-61): the device resampler against its CPU twin (which integrates by
+    quadrature and inverts by bisection -- an independent route), slab-wise, with and without jitter, and the
+    round trip particles -> spline -> particles -> spline at 2e6 particles."""
+    nrm = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
+    vs = oracle.VSpace(-10.0, 10.0, 41, 4)
+    src = vpm.ParticleDistribution(1, 1, 200000)
+    vpm.initialize_(src, vpm.DoubleMaxwellian((-10.0, 10.0), 2.0))
+    fs = vpm.projection(None, src, sd)
+    c = fs.coefficients.copy()
+    n, off, ntot = 30011, 7000, 50000
+    for jitter in (False, True):
+        d = vpm.ParticleDistribution(1, 1, n).set(np.arange(n, dtype=float), np.zeros(n), np.zeros(n))
+        vpm.projection_(sd, d, offset=off, ntotal=ntot, jitter=jitter)
+        vo, wo, mass = vs.resample(c, n, offset=off, Ntotal=ntot, jitter=jitter)
+        x, v, w = d.get()
+        np.testing.assert_array_equal(x, np.arange(n, dtype=float))          # positions untouched
+        assert abs(d.resampled_mass - mass) < 1e-13 and np.allclose(w, wo, rtol=1e-13)
+        assert nrm(v, vo) < 1e-11 and np.abs(v - vo).max() < 1e-8, (jitter, np.abs(v - vo).max())
+    # round trip at size: the re-projected coefficients agree to the stratification error O(1/N)
+    big = vpm.ParticleDistribution(1, 1, 2_000_000)
+    vpm.projection_(sd, big)
+    v = big.get("v")
+    assert np.all(np.diff(v) >= 0.0) and abs(big.get("w").sum() - big.resampled_mass) < 1e-9
+    sd2 = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
+    c2 = vpm.projection(None, big, sd2).coefficients
+    assert nrm(c2, c) < 1e-5
+    with pytest.raises(vpm.VpmError):                                         # a spline with no positive mass
+        sd3 = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
+        sd3.mass_solve(-np.ones(len(sd3)))
+        vpm.projection_(sd3, big)
+
+
 def test_config1_vlasov_poisson_script(vpm, oracle):
     """scripts/vlasov_poisson.jl:6-30 with its shipped parameters, both field modes, against the oracle."""
     npart, nknot, order, tstep, tspan, domain = 10000, 16, 3, 0.1, (0.0, 20.0), (0.0, 1.0)

@@ -272,3 +272,35 @@ def test_samplers(oracle):
     x, v, w = oracle.sample_maxwellian(N, shift=2.0, doubled=True, xlo=-10, xhi=10)
     assert abs(v[: N // 2].mean() - 2) < 2e-2 and abs(v[N // 2:].mean() + 2) < 2e-2
     np.testing.assert_allclose(w, 1.0 / N)
+
+
+def test_resample_twin_reproduces_the_spline():
+    """KAT for the spline -> particle resampling checker (projection!(::SplineDistribution, ::ParticleDistribution)
+    is an empty TODO upstream, src/projections/distribution.jl:57-61): stratified inverse-CDF samples carry the
+    spline's mass, reproduce its low moments to O(1/N) and re-project onto (nearly) the same coefficients."""
+    from oracle import oracle as orc
+    vs = orc.VSpace(-10.0, 10.0, 41, 4)
+    rng = np.random.default_rng(5)
+    v = np.r_[rng.standard_normal(40000) + 2.0, rng.standard_normal(40000) - 2.0]
+    w = np.full(v.size, 1.0 / v.size)
+    c = vs.project(v, w)
+    # reference moments of the (clipped) spline by fine quadrature
+    g = np.linspace(-10.0, 10.0, 400001)
+    f = np.maximum(vs.eval(c, g), 0.0)
+    m0 = np.trapezoid(f, g)
+    m1 = np.trapezoid(f * g, g)
+    m2 = np.trapezoid(f * g * g, g)
+    n = 20000
+    vr, wr, mass = vs.resample(c, n)
+    assert np.all(np.diff(vr) >= 0.0) and vr.min() > -10.0 and vr.max() < 10.0     # quantiles are ordered
+    assert abs(mass - m0) < 2e-4 and abs(wr.sum() - mass) < 1e-12                   # cell-wise vs point-wise clipping
+    assert abs((wr * vr).sum() - m1) < 2e-4 and abs((wr * vr * vr).sum() - m2) < 2e-3
+    c2 = vs.project(vr, wr)
+    assert np.linalg.norm(c2 - c) < 1e-3 * np.linalg.norm(c)
+    # slabs of one ensemble concatenate to the whole; jitter stays inside the particle's stratum
+    va, _, _ = vs.resample(c, 5000, offset=0, Ntotal=n)
+    vb, _, _ = vs.resample(c, 15000, offset=5000, Ntotal=n)
+    np.testing.assert_array_equal(np.r_[va, vb], vr)
+    vj, _, _ = vs.resample(c, n, jitter=True)
+    edges = np.r_[-10.0, 0.5 * (vr[1:] + vr[:-1]), 10.0]
+    assert np.all(np.diff(vj) >= 0.0) and np.abs(vj - vr).max() < 5 * np.diff(edges).max()

@@ -45,6 +45,7 @@ SIGNATURES = {
     "vpm_particles_set_uniform_weight": (_i32, [_vp, _f64]),
     "vpm_sample_bump_on_tail": (_i32, [_vp, _i64, _i64, _u64, _f64, _f64, _f64, _f64, _f64]),
     "vpm_sample_maxwellian": (_i32, [_vp, _i64, _i64, _u64, _f64, _f64, _f64, _i32, _f64]),
+    "vpm_resample_v": (_i32, [_vp, _vp, _vp, _i64, _i64, _u64, _i32, _vp]),
     "vpm_sample_uniform": (_i32, [_vp, _i64, _i64, _u64, _f64, _f64, _f64, _f64, _f64, _f64]),
     "vpm_sample_normal": (_i32, [_vp, _i64, _i64, _u64, _f64, _f64, _f64, _D]),
     "vpm_xspace_create": (_i32, [_vp, _f64, _f64, _i32, _i32, C.POINTER(_vp)]),

@@ -24,6 +24,7 @@ from . import _cabi
 from ._cabi import VpmError, check
 
 _vp = C.c_void_p
+DEFAULT_SEED = 0x5EED0001   # seed of the counter-based device samplers
 
 
 def _lib():
@@ -472,11 +473,35 @@ def update_(potential):
     return potential
 
 
-def projection_(potential, distribution):
-    """projection!(potential, distribution): src/projections/potential.jl:2-22"""
-    x, v, w = distribution.ptrs()
-    check(_lib().vpm_deposit_x(potential._h, x, w, distribution.npart, None))
-    return potential
+def projection_(init, final, seed=DEFAULT_SEED, offset=0, ntotal=None, jitter=False):
+    """projection!(a, b), dispatched on the argument types like the reference's methods:
+
+    projection!(potential::Potential, distribution::ParticleDistribution)     src/projections/potential.jl:2-22
+        charge deposit into potential.rhs;
+    projection!(init::ParticleDistribution, final::SplineDistribution)        src/projections/distribution.jl:7-32
+        (commented out upstream but called by update_entropy!, lenard_bernstein.jl:15-17): deposit + mass solve;
+    projection!(init::SplineDistribution, final::ParticleDistribution)        src/projections/distribution.jl:57-61
+        (an empty TODO upstream): resample the particle velocities from the spline by stratified inverse-CDF
+        sampling, equal weights summing to the integral of the spline; x is left untouched;
+    same-type pairs                                                            src/projections/distribution.jl:64-71
+        do nothing, as upstream.
+    """
+    if isinstance(init, Potential):
+        x, v, w = final.ptrs()
+        check(_lib().vpm_deposit_x(init._h, x, w, final.npart, None))
+        return init
+    if isinstance(init, ParticleDistribution) and isinstance(final, SplineDistribution):
+        projection(None, init, final)
+        return final
+    if isinstance(init, SplineDistribution) and isinstance(final, ParticleDistribution):
+        mass = C.c_double()
+        check(_lib().vpm_resample_v(init._h, None, final._h, int(offset), int(final.npart if ntotal is None else ntotal),
+                                    int(seed), int(bool(jitter)), C.byref(mass)))
+        final.resampled_mass = mass.value
+        return final
+    if type(init) is type(final):
+        return final
+    raise TypeError(f"no projection_ method for ({type(init).__name__}, {type(final).__name__})")
 
 
 def projection(velocities, dist, final_dist):
@@ -723,7 +748,6 @@ def run_(method, h5file=None, save_stride=None, diag_mode=1):
 # ------------------------------------------------------------------------------------------------
 # examples / initial conditions
 # ------------------------------------------------------------------------------------------------
-DEFAULT_SEED = 0x5EED0001
 
 
 class NormalDistribution:

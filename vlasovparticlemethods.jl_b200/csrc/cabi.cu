@@ -902,6 +902,17 @@ static int set_coef(vpm_vspace* vs, const double* coef_host)
     return lb_field_local(vs->ctx, vs, LBF_TABLE);
 }
 
+int vpm_resample_v(vpm_vspace* vs, const double* coef_host, vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed, int jitter,
+                   double* mass_out)
+{
+    VPM_REQUIRE(vs && p && vs->ctx == p->ctx && ntotal > 0 && offset >= 0, "vpm_resample_v: bad arguments");
+    vpm_ctx* ctx = vs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    VPM_CHECK(set_coef(vs, coef_host));
+    p->uw = false;
+    return launch_resample_v(ctx, vs, p, offset, ntotal, seed, jitter, mass_out);
+}
+
 int vpm_gather_v(vpm_vspace* vs, const double* coef_host, const double* v_dev, int64_t n, double* f_dev, double* df_dev)
 {
     VPM_REQUIRE(vs && v_dev && n >= 0, "vpm_gather_v: bad arguments");

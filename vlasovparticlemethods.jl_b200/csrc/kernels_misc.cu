@@ -135,6 +135,76 @@ __global__ void sample_uniform_kernel(long long n, long long offset, long long n
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Spline -> particles (the inverse projection the reference leaves as an empty TODO,
+// src/projections/distribution.jl:57-61): stratified inverse-CDF sampling of f_s.
+//   cum[c+1] - cum[c] = max(integral of f_s over cell c, 0)      (exact: h * sum_m f_m / (m+1))
+//   particle gi of ntotal gets the quantile y = (gi + r) / ntotal * M, r = 1/2 (deterministic) or a
+//   counter-based uniform (jitter), M = cum[ncell]; its cell by binary search, its local coordinate by a
+//   bracketed Newton iteration on the cell's primitive; w = M / ntotal.
+// ---------------------------------------------------------------------------------------------
+__global__ void resample_cdf_kernel(const double* __restrict__ ftab, int ncell, int K, int TS, double h, double* __restrict__ cum)
+{
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
+        double m = 0.0;
+        for (int k = K - 1; k >= 0; k--) m += ftab[(size_t)c * TS + k] / (double)(k + 1);
+        cum[c + 1] = fmax(m * h, 0.0);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        cum[0] = 0.0;
+        for (int c = 1; c <= ncell; c++) {
+            s += cum[c];
+            cum[c] = s;
+        }
+    }
+}
+
+__global__ void resample_v_kernel(long long n, long long offset, long long ntotal, uint64_t seed, int jitter,
+                                  const double* __restrict__ ftab, const double* __restrict__ cum, int ncell, int K, int TS,
+                                  double lo, double h, double* __restrict__ v, double* __restrict__ w)
+{
+    const double M = cum[ncell];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t gi = (uint64_t)(offset + i);
+        const double r = jitter ? uniform01(seed, gi, 7) : 0.5;
+        const double y = ((double)gi + r) / (double)ntotal * M;
+        int a = 0, b = ncell;   // cum[a] <= y, and b is the first index known to lie above (or ncell)
+        while (b - a > 1) {
+            const int mid = (a + b) >> 1;
+            if (cum[mid] <= y) a = mid;
+            else b = mid;
+        }
+        const double target = y - cum[a];
+        const double mc = cum[a + 1] - cum[a];
+        double f[kMaxOrder], g[kMaxOrder];   // f_m and f_m / (m+1)
+        for (int k = 0; k < K; k++) {
+            f[k] = ftab[(size_t)a * TS + k];
+            g[k] = f[k] / (double)(k + 1);
+        }
+        double ulo = 0.0, uhi = 1.0, u = mc > 0.0 ? fmin(fmax(target / mc, 0.0), 1.0) : 0.5;
+        for (int it = 0; it < 64; it++) {
+            double G = g[K - 1], F = f[K - 1];
+            for (int k = K - 2; k >= 0; k--) {
+                G = fma(G, u, g[k]);
+                F = fma(F, u, f[k]);
+            }
+            const double res = G * u * h - target;
+            if (res > 0.0) uhi = u;
+            else ulo = u;
+            if (res == 0.0 || uhi - ulo <= 2e-16) break;
+            double un = F > 0.0 ? u - res / (F * h) : 0.5 * (ulo + uhi);
+            if (!(un > ulo && un < uhi)) un = 0.5 * (ulo + uhi);
+            if (un == u) break;
+            u = un;
+        }
+        v[i] = lo + h * ((double)a + u);
+        w[i] = M / (double)ntotal;
+    }
+}
+
 __global__ void fill_kernel(double* __restrict__ a, long long n, double value)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -252,6 +322,28 @@ int launch_sample_maxwellian(vpm_ctx* ctx, vpm_particles* p, int64_t offset, int
 {
     sample_maxwellian_kernel<<<grid_for(ctx, p->n, 256), 256, 0, ctx->stream>>>(p->n, offset, ntotal, seed, xlo, xhi, shift, doubled,
                                                                              wnum, p->x, p->v, p->w);
+    ctx->launches++;
+    VPM_CUDA(cudaGetLastError());
+    return VPM_OK;
+}
+
+int launch_resample_v(vpm_ctx* ctx, const vpm_vspace* vs, vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed, int jitter,
+                      double* mass_out)
+{
+    const int TS = 2 * vs->K - 1;
+    int rc = ensure_red(ctx, (size_t)vs->ncell + 2);
+    if (rc) return rc;
+    double* cum = ctx->red;
+    resample_cdf_kernel<<<1, 256, 0, ctx->stream>>>(vs->ftab, vs->ncell, vs->K, TS, vs->h, cum);
+    ctx->launches++;
+    VPM_CUDA(cudaGetLastError());
+    double M = 0.0;
+    VPM_CUDA(cudaMemcpyAsync(&M, cum + vs->ncell, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (mass_out) *mass_out = M;
+    if (!(M > 0.0)) return fail(VPM_ERR_INVALID, "vpm_resample_v: the spline has no positive mass");
+    resample_v_kernel<<<grid_for(ctx, p->n, 256), 256, 0, ctx->stream>>>(p->n, offset, ntotal, seed, jitter, vs->ftab, cum, vs->ncell, vs->K,
+                                                                      TS, vs->lo, vs->h, p->v, p->w);
     ctx->launches++;
     VPM_CUDA(cudaGetLastError());
     return VPM_OK;

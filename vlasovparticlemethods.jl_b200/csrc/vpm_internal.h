@@ -228,6 +228,8 @@ int launch_sample_bump_on_tail(vpm_ctx* ctx, vpm_particles* p, int64_t offset, i
                                double eps, double kappa, double alpha, double sigma, double v0);
 int launch_sample_maxwellian(vpm_ctx* ctx, vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed,
                              double xlo, double xhi, double shift, int doubled, double wnum);
+int launch_resample_v(vpm_ctx* ctx, const vpm_vspace* vs, vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed, int jitter,
+                      double* mass_out);
 int launch_sample_uniform(vpm_ctx* ctx, vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed,
                           double xlo, double xhi, double vlo, double vhi, double shift, double wnum);
 
