@@ -75,14 +75,18 @@ def test_resample_spline_to_particles(vpm, oracle):
         np.testing.assert_array_equal(x, np.arange(n, dtype=float))          # positions untouched
         assert abs(d.resampled_mass - mass) < 1e-13 and np.allclose(w, wo, rtol=1e-13)
         assert nrm(v, vo) < 1e-11 and np.abs(v - vo).max() < 1e-8, (jitter, np.abs(v - vo).max())
-    # round trip at size: the re-projected coefficients agree to the stratification error O(1/N)
+    # round trip at size.  A projected (noisy) spline has small negative lobes in the tails, which the sampler
+    # clips cell-wise: the re-projected coefficients agree up to that clipped part (independent of N) ...
     big = vpm.ParticleDistribution(1, 1, 2_000_000)
     vpm.projection_(sd, big)
     v = big.get("v")
     assert np.all(np.diff(v) >= 0.0) and abs(big.get("w").sum() - big.resampled_mass) < 1e-9
     sd2 = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
-    c2 = vpm.projection(None, big, sd2).coefficients
-    assert nrm(c2, c) < 1e-5
+    assert nrm(vpm.projection(None, big, sd2).coefficients, c) < 1e-3
+    # ... and for a positive spline to the stratification error O(1/N): 2e-4 at 2e4 particles, 2e-6 at 2e6
+    cpos = 0.1 * np.exp(-np.linspace(-10.0, 10.0, len(sd)) ** 2 / 8.0)
+    vpm.projection_(sd, big, coefficients=cpos)
+    assert nrm(vpm.projection(None, big, sd2).coefficients, cpos) < 1e-5
     with pytest.raises(vpm.VpmError):                                         # a spline with no positive mass
         sd3 = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
         sd3.mass_solve(-np.ones(len(sd3)))

@@ -473,7 +473,7 @@ def update_(potential):
     return potential
 
 
-def projection_(init, final, seed=DEFAULT_SEED, offset=0, ntotal=None, jitter=False):
+def projection_(init, final, seed=DEFAULT_SEED, offset=0, ntotal=None, jitter=False, coefficients=None):
     """projection!(a, b), dispatched on the argument types like the reference's methods:
 
     projection!(potential::Potential, distribution::ParticleDistribution)     src/projections/potential.jl:2-22
@@ -482,7 +482,8 @@ def projection_(init, final, seed=DEFAULT_SEED, offset=0, ntotal=None, jitter=Fa
         (commented out upstream but called by update_entropy!, lenard_bernstein.jl:15-17): deposit + mass solve;
     projection!(init::SplineDistribution, final::ParticleDistribution)        src/projections/distribution.jl:57-61
         (an empty TODO upstream): resample the particle velocities from the spline by stratified inverse-CDF
-        sampling, equal weights summing to the integral of the spline; x is left untouched;
+        sampling, equal weights summing to the integral of the spline; x is left untouched (`coefficients`:
+        spline coefficients to sample from instead of those of the last projection);
     same-type pairs                                                            src/projections/distribution.jl:64-71
         do nothing, as upstream.
     """
@@ -495,7 +496,10 @@ def projection_(init, final, seed=DEFAULT_SEED, offset=0, ntotal=None, jitter=Fa
         return final
     if isinstance(init, SplineDistribution) and isinstance(final, ParticleDistribution):
         mass = C.c_double()
-        check(_lib().vpm_resample_v(init._h, None, final._h, int(offset), int(final.npart if ntotal is None else ntotal),
+        coef = None if coefficients is None else _f64(coefficients)
+        if coef is not None and coef.size != len(init):
+            raise ValueError("coefficients must have one entry per basis function")
+        check(_lib().vpm_resample_v(init._h, _hp(coef), final._h, int(offset), int(final.npart if ntotal is None else ntotal),
                                     int(seed), int(bool(jitter)), C.byref(mass)))
         final.resampled_mass = mass.value
         return final
