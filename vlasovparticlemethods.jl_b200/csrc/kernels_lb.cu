@@ -13,11 +13,16 @@
 //
 // Stage vectors are kept in "k form": a pass stores only its derivative k_s (8 B) and the next pass
 // RECOMPUTES its stage input q_s = v + dt sum_j a_sj k_j from v and the stored k's with the same fma
-// sequence (rk_q2/rk_q3/rk_q4 below), instead of storing both q_s and a running accumulator:
-//   stage 1: read v, w        write k1            (24 B)      stage 3: read v, k1, k2, w   write q4, acc (48 B)
-//   stage 2: read v, k1, w    write k2            (32 B)      stage 4: read q4, v, acc, w  write v       (40 B)
-// = 144 B per RK438 particle-step (the accumulate-and-store form needed 184 B).  The conservative model
+// sequence (rk_q2/rk_q3/rk_q4 below), instead of storing both q_s and a running accumulator; stage 3 folds
+// the history into q4 and a = v + dt (k1 + 3 k2 + 3 k3)/8, so stage 4 does not read v:
+//   stage 1: read v, w        write k1   (24 B)      stage 3: read v, k1, k2, w   write q4, a         (48 B)
+//   stage 2: read v, k1, w    write k2   (32 B)      stage 4: read q4, a, w       write v = a + dt k4/8 (32 B)
+// = 136 B per RK438 particle-step (the accumulate-and-store form needed 184 B).  The conservative model
 // also needs q_2, q_3 in memory for its moments pass (qout != nullptr in stages 1, 2: +8 B each).
+//
+// Kernels: lb_pass_ring_kernel (warp-specialised TMA ring, default for the deposit passes), lb_pass_kernel
+// (register prefetch: gather-only modes, unaligned / tiny inputs, per-warp and per-CTA histogram fallbacks),
+// lb_field_kernel (one CTA: reduce, all-reduce, banded Cholesky solve, per-cell table, CLB coefficients).
 #include <cstdlib>
 
 #include "splines.cuh"
