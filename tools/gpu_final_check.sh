@@ -1,0 +1,6 @@
+# what the driver does at round end, on one GPU: build artefacts are in-tree; tests, smoke, default bench, reference arm
+set -x
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python __graft_entry__.py smoke 2>&1 | tail -1
+python bench.py 2>&1 | tail -1 > gpurun_out/final_bench_default.json; cut -c1-250 gpurun_out/final_bench_default.json
+python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1 | cut -c1-200
