@@ -155,8 +155,9 @@ int vpm_vp_strang_steps_async(vpm_xspace* xs, vpm_particles* p, double dt, doubl
                               int diag_mode);
 /* Host-array drop-in for one Strang step of the integrator state (flows of
  * src/models/vlasov_poisson.jl:53-67 on z = 2 x N host matrix): uploads z_in, steps on the device,
- * downloads into z_out (may alias).  Weights stay resident in p (model.distribution).  Chunked and
- * pipelined over PCIe; z buffers should be pinned (vpm_host_alloc) for full overlap. */
+ * downloads into z_out (may alias).  Weights stay resident in p (model.distribution).  PCIe-bound (the
+ * kick of any particle needs the deposit of all, so upload and download cannot overlap within a step);
+ * z buffers should be pinned (vpm_host_alloc) to reach the link rate. */
 int vpm_vp_strang_step_host(vpm_xspace* xs, vpm_particles* p, const double* z_in, double* z_out,
                             double dt, double chi, int mode);
 /* current device-side potential / rhs coefficients to the host */
@@ -200,6 +201,34 @@ int vpm_vspace_get(vpm_vspace* vs, double* rhs_host, double* coef_host);
  * coefficients of the last projection / mass solve.  *mass_out (optional) returns the integral. */
 int vpm_resample_v(vpm_vspace* vs, const double* coef_host, vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t seed,
                    int jitter, double* mass_out);
+
+/* ---- run! drivers with the reference's on-disk trajectory format ------------------------ */
+/* Minimal HDF5 writer (no libhdf5; csrc/h5min.cpp) for files laid out as run! writes them: every dataset is
+ * fp64, chunked with one chunk per frame and unlimited along the frame axis.  dims are in HDF5 (row-major)
+ * order = Julia's dimensions reversed, dims[0] = number of frames: run!(::SplittingMethod) "z" (nd, np, nt+1)
+ * chunk (nd, np, 1) (src/methods/splitting.jl:32-34) is rank 3, dims {nt+1, np, nd}; run!(::GeometricIntegrator)
+ * "z" (np, nt+1) and "t" (nt+1) (src/methods/geometric_integrator.jl:21-25) are dims {nt+1, np} and {nt+1}.
+ * create -> add_dataset (up to 8) -> commit (writes all metadata, sizes the file) -> write frames in any order,
+ * whole or in pieces -> close.  Host only: no GPU needed. */
+typedef struct vpm_h5 vpm_h5;
+int vpm_h5_create(const char* path, vpm_h5** out);
+int vpm_h5_add_dataset(vpm_h5* f, const char* name, int rank, const int64_t* dims, int* id_out);
+int vpm_h5_commit(vpm_h5* f);
+int vpm_h5_write(vpm_h5* f, int id, int64_t frame, int64_t offset_doubles, int64_t count, const double* data);
+int vpm_h5_close(vpm_h5* f);
+/* run!(method::SplittingMethod, h5file) (src/methods/splitting.jl:23-52): nsteps Strang steps as
+ * vpm_vp_strang_steps (same mode / diag_mode / diag_host; in mode FROZEN the field is deposited once, from the
+ * positions at call time, for the whole run).  If h5path != NULL and save_stride > 0 the state (x, v) at steps
+ * 0, save_stride, 2 save_stride, ..., nsteps goes to dataset "z" of h5path (save_stride = 1 is the reference's
+ * every-step output) and the step numbers of the saved frames times dt to "t".  The state never leaves
+ * the device between steps: a frame is snapshotted device-to-device, and its device-to-host copy and file write
+ * run on a second stream / the host while the next steps compute.  *frames_out (optional) = frames written. */
+int vpm_vp_run(vpm_xspace* xs, vpm_particles* p, double dt, double chi, int nsteps, int mode, int diag_mode,
+               int save_stride, const char* h5path, double* diag_host, int* frames_out);
+/* run!(method::GeometricIntegrator, h5file) (src/methods/geometric_integrator.jl:12-44): RK438 steps as
+ * vpm_lb_rk438_steps; datasets "z" (velocities per saved frame) and "t" (t0 + step * dt). */
+int vpm_lb_run(vpm_vspace* vs, vpm_particles* p, double nu, double dt, double t0, int nsteps, int conservative,
+               int save_stride, const char* h5path, double* diag_host, int* frames_out);
 
 /* ---- host-side operator construction (no GPU needed; what the spaces upload at creation) ----------- */
 /* galerkin_matrix of the periodic basis: first rows (circulant) of the mass and stiffness matrices and of

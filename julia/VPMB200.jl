@@ -194,12 +194,18 @@ end
 SplittingMethod(model::VlasovPoisson{1,1,DeviceParticleDistribution,DevicePotential}, tspan::Tuple, tstep::Real;
                 field::Symbol = :frozen, χ::Real = 1.0) = DeviceSplittingMethod(model, Float64.(tspan), Float64(tstep), field, Float64(χ))
 
-function run!(m::DeviceSplittingMethod; diag_mode::Integer = 1)
+# run!(method, h5file) as upstream (src/methods/splitting.jl:23-52): the trajectory goes to dataset "z" of h5file with the
+# reference's layout (nd, np, nt+1), chunk (nd, np, 1), written by the library itself while the next steps compute, so
+# `z = h5read(h5file, "z")` in scripts/vlasov_poisson.jl:38 keeps working.  save_stride = k keeps every k-th step (plus the
+# last); the times of the saved frames are in dataset "t".  run!(method) without a file keeps everything on the device.
+function run!(m::DeviceSplittingMethod, h5file::Union{AbstractString,Nothing} = nothing; save_stride::Integer = 1, diag_mode::Integer = 1)
     nt = round(Int, (m.tspan[2] - m.tspan[1]) / m.tstep)
     diag = zeros(3, nt + 1)          # rows W, K, M (src/vlasov_poisson.jl:58-67)
-    check(ccall((:vpm_vp_strang_steps, libvpm), Cint,
-                (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, Cint, Cint, Cint, Ptr{Float64}),
-                m.model.potential.h, m.model.distribution.h, m.tstep, m.χ, nt, m.field === :frozen ? 1 : 0, diag_mode, diag))
+    frames = Ref{Cint}(0)
+    check(ccall((:vpm_vp_run, libvpm), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, Cint, Cint, Cint, Cint, Cstring, Ptr{Float64}, Ref{Cint}),
+                m.model.potential.h, m.model.distribution.h, m.tstep, m.χ, nt, m.field === :frozen ? 1 : 0, diag_mode,
+                h5file === nothing ? 0 : save_stride, h5file === nothing ? C_NULL : h5file, diag, frames))
     m.model.distribution, diag
 end
 
@@ -213,11 +219,15 @@ end
 GeometricIntegrator(model::Union{LenardBernstein{1,1,DeviceParticleDistribution},ConservativeLenardBernstein{1,1,DeviceParticleDistribution}},
                     tspan::Tuple, tstep::Real) = DeviceRK438(model, Float64.(tspan), Float64(tstep))
 
-function run!(m::DeviceRK438)
+# run!(method, h5file): datasets "z" (np, nt+1) chunk (np, 1) and "t" (nt+1) as src/methods/geometric_integrator.jl:21-35
+function run!(m::DeviceRK438, h5file::Union{AbstractString,Nothing} = nothing; save_stride::Integer = 1)
     nt = round(Int, (m.tspan[2] - m.tspan[1]) / m.tstep)
     diag = zeros(2, nt + 1)          # rows Σv, Σv² (scripts/lenard_bernstein_conservative.jl:49-50)
-    check(ccall((:vpm_lb_rk438_steps, libvpm), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, Cint, Cint, Ptr{Float64}),
-                m.model.ent.dist.h, m.model.dist.h, m.model.ν, m.tstep, nt, m.model isa ConservativeLenardBernstein, diag))
+    frames = Ref{Cint}(0)
+    check(ccall((:vpm_lb_run, libvpm), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, Float64, Cint, Cint, Cint, Cstring, Ptr{Float64}, Ref{Cint}),
+                m.model.ent.dist.h, m.model.dist.h, m.model.ν, m.tstep, m.tspan[1], nt, m.model isa ConservativeLenardBernstein,
+                h5file === nothing ? 0 : save_stride, h5file === nothing ? C_NULL : h5file, diag, frames))
     m.model.dist, diag
 end
 

@@ -1,0 +1,128 @@
+"""Trajectory files: libvpm_b200's own HDF5 writer (vpm_h5_*, csrc/h5min.cpp) reproduces the
+layout run! writes (src/methods/splitting.jl:32-34, src/methods/geometric_integrator.jl:21-25).  No HDF5
+library exists in this image, so the files are read back with tests/h5mini.py, an independent reader that is
+first pinned on a file written by the real HDF5 library (scipy ships MATLAB's v7.3 = HDF5 sample next to the
+same variable in the classic format, which scipy itself can read)."""
+import os
+
+import numpy as np
+import pytest
+
+import h5mini
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def vpm():
+    import __graft_entry__ as g
+    g.build()
+    import vpm_b200
+    return vpm_b200
+
+
+def test_reader_is_pinned_on_a_file_written_by_libhdf5():
+    import scipy.io
+    d = os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data")
+    h5, classic = os.path.join(d, "testhdf5_7.4_GLNX86.mat"), os.path.join(d, "testdouble_7.4_GLNX86.mat")
+    if not (os.path.exists(h5) and os.path.exists(classic)):
+        pytest.skip("scipy's MATLAB sample files are not installed")
+    f = h5mini.File(h5)
+    assert f.base == 512 and f.sb_version == 0 and (f.leaf_k, f.internal_k) == (4, 16)
+    assert list(f.datasets) == ["testdouble"]
+    ds = f.datasets["testdouble"]
+    assert ds.dtype == np.dtype("<f8") and ds.layout == "contiguous"
+    want = scipy.io.loadmat(classic)["testdouble"]          # (1, 9), MATLAB column-major
+    got = f.read("testdouble")                              # HDF5 row-major view of the same array: (9, 1)
+    np.testing.assert_array_equal(got.T, want)
+    np.testing.assert_allclose(got[:, 0], np.linspace(0, 2 * np.pi, 9), rtol=1e-15)
+    # conventions the writer copies from this file: the heap's free list ends with 1, not with the undefined address
+    (heap,) = f.group_info["heaps"].values()
+    free = f._abs(heap["data_addr"]) + heap["free_head"]
+    assert f._u(free, 8) == 1 and heap["free_head"] + f._u(free + 8, 8) == heap["data_size"]
+
+
+def test_splitting_layout_roundtrip(vpm, tmp_path):
+    nd, npart, nt = 2, 7, 5
+    rng = np.random.default_rng(1)
+    z = rng.standard_normal((nt + 1, npart, nd))            # file order = Julia (nd, np, nt+1) reversed
+    path = tmp_path / "vp.h5"
+    with vpm.H5Writer(path).create_dataset("z", (nd, npart, nt + 1)).create_dataset("t", (nt + 1,)).commit() as w:
+        for n in (3, 0, 5, 1, 4, 2):                        # any order
+            w.write_frame("z", n, z[n])
+            w.write_frame("t", n, [0.1 * n])
+    f = h5mini.File(path)
+    assert f.eof_addr == os.path.getsize(path) and f.base == 0 and f.flags == 0
+    assert sorted(f.datasets) == ["t", "z"]
+    dz = f.datasets["z"]
+    assert dz.shape == (nt + 1, npart, nd) and dz.maxshape == (None, npart, nd) and dz.chunk == (1, npart, nd)
+    assert dz.dtype == np.dtype("<f8") and dz.layout == "chunked" and not dz.filters
+    np.testing.assert_array_equal(f.read("z"), z)
+    # what h5read(h5file, "z") returns in Julia: z[:, :, n+1] is the 2 x np state after step n
+    zj = np.transpose(f.read("z"), (2, 1, 0))
+    np.testing.assert_array_equal(zj[:, :, 3], z[3].T)
+    dt = f.datasets["t"]
+    assert dt.shape == (nt + 1,) and dt.maxshape == (None,) and dt.chunk == (1,)
+    np.testing.assert_array_equal(f.read("t"), 0.1 * np.arange(nt + 1))
+
+
+def test_geometric_integrator_layout_many_frames(vpm, tmp_path):
+    """z[np, nt+1] chunk (np, 1) and t[nt+1] chunk (1): 5001 frames need a three-level chunk B-tree
+    (64 entries per node), written in pieces as the device-to-host ring does"""
+    npart, nframes = 33, 5001
+    rng = np.random.default_rng(2)
+    z = rng.standard_normal((nframes, npart))
+    t = 0.01 * np.arange(nframes)
+    path = tmp_path / "lb.h5"
+    with vpm.H5Writer(path).create_dataset("z", (npart, nframes)).create_dataset("t", (nframes,)).commit() as w:
+        for n in range(nframes):
+            w.write_frame("z", n, z[n, :20])
+            w.write_frame("z", n, z[n, 20:], offset=20)
+            w.write_frame("t", n, t[n:n + 1])
+    f = h5mini.File(path)
+    np.testing.assert_array_equal(f.read("z"), z)
+    np.testing.assert_array_equal(f.read("t"), t)
+    nodes = f.group_info["chunk_nodes"]
+    for ds in ("z", "t"):
+        assert len(f.datasets[ds].chunks) == nframes
+    assert max(n["level"] for n in nodes) == 2
+    leaves = [n for n in nodes if n["level"] == 0]
+    assert len(leaves) == 2 * 79 and all(n["used"] <= 64 for n in nodes)
+    # sibling links form one left-to-right chain per level and dataset
+    by_addr = {n["addr"]: n for n in nodes}
+    for n in nodes:
+        if n["right"] != h5mini.UNDEF:
+            r = by_addr[n["right"]]
+            assert r["left"] == n["addr"] and r["level"] == n["level"] and r["first"][2] == n["last"][2]
+    assert f.eof_addr == os.path.getsize(path)
+
+
+def test_unwritten_frames_read_as_zeros_and_file_is_valid_before_close(vpm, tmp_path):
+    path = tmp_path / "partial.h5"
+    w = vpm.H5Writer(path).create_dataset("z", (2, 3, 4)).commit()
+    w.write_frame("z", 1, np.ones((3, 2)))
+    got = h5mini.File(path).read("z")           # read while still open: metadata is complete after commit
+    assert got.shape == (4, 3, 2) and got[1].min() == 1.0 and np.abs(got[[0, 2, 3]]).max() == 0.0
+    w.close()
+    w.close()                                   # idempotent
+
+
+def test_writer_errors(vpm, tmp_path):
+    with pytest.raises(vpm.VpmError, match="cannot open"):
+        vpm.H5Writer(tmp_path / "no_such_dir" / "x.h5")
+    w = vpm.H5Writer(tmp_path / "e.h5").create_dataset("z", (2, 4, 3))
+    with pytest.raises(vpm.VpmError, match="duplicate"):
+        w.create_dataset("z", (3,))
+    with pytest.raises(vpm.VpmError, match="4 GiB"):
+        w.create_dataset("big", (2, 300_000_000, 3))       # 4.8 GB per frame: HDF5's chunk-size limit
+    with pytest.raises(vpm.VpmError, match="commit"):
+        w.write_frame("z", 0, np.zeros(8))
+    w.commit()
+    with pytest.raises(vpm.VpmError, match="already committed"):
+        w.create_dataset("t", (3,))
+    for frame, data, off in ((3, np.zeros(8), 0), (-1, np.zeros(8), 0), (0, np.zeros(9), 0), (0, np.zeros(4), 5)):
+        with pytest.raises(vpm.VpmError, match="outside"):
+            w.write_frame("z", frame, data, offset=off)
+    w.close()
+    with pytest.raises(vpm.VpmError, match="no datasets"):
+        vpm.H5Writer(tmp_path / "empty.h5").commit()

@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Measurement for the run! driver with trajectory output: how much of the device-to-host copy and
+file write of the saved frames hides behind the stepping.  Runs the bump-on-tail configuration for `--steps`
+self-consistent Strang steps with frames every `--stride` steps, and for `--steps-every` steps with the reference's
+every-step output, each next to the same run without output, and prints one JSON object (wall-clock around the blocking C call; the state is resident before the timer starts).
+
+    python tools/run_h5_overlap.py --particles 25000000 --steps 40 --stride 10
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--particles", type=int, default=25_000_000)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--stride", type=int, default=10)
+    ap.add_argument("--steps-every", type=int, default=8, help="steps of the every-step-output run")
+    ap.add_argument("--dir", default=tempfile.gettempdir())
+    a = ap.parse_args()
+    import numpy as np
+    import vpm_b200 as vpm
+    import h5mini
+
+    n, dt = a.particles, 0.1
+    bot = vpm.BumpOnTail()
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, bot.L), 4, 16))
+    out = {"particles": n, "dir": a.dir, "frame_bytes": 16 * n}
+
+    def run(h5, stride, steps):
+        d = vpm.initialize_(vpm.ParticleDistribution(1, 1, n), bot)
+        m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, steps * dt), dt, field="selfconsistent")
+        d.ctx.sync()
+        t0 = time.perf_counter()
+        vpm.run_(m, h5, save_stride=stride, diag_mode=1)
+        d.ctx.sync()
+        return time.perf_counter() - t0, m, d
+
+    run(None, None, a.steps)                            # warm-up (module load, allocations)
+    for label, stride, steps in (("stride", a.stride, a.steps), ("every_step", 1, a.steps_every)):
+        t_none, m0, d0 = run(None, None, steps)
+        path = os.path.join(a.dir, f"vpm_overlap_{label}.h5")
+        t, m, d = run(path, stride, steps)
+        frames = m.frames
+        size = os.path.getsize(path)
+        # the last frame must be the final device state, and the history must match the run without output
+        z_last = h5mini.File(path).read("z")[-1] if size < 6e9 else None
+        ok = True
+        if z_last is not None:
+            xg, vg, _ = d.get()
+            ok = bool(np.array_equal(z_last[:, 0], xg) and np.array_equal(z_last[:, 1], vg))
+        ok = ok and bool(np.allclose(m.diagnostics, m0.diagnostics, rtol=1e-12, atol=1e-14))
+        os.remove(path)
+        d2h = 16.0 * n * frames
+        out[label] = {"save_stride": stride, "steps": steps, "frames": frames, "file_bytes": size, "seconds": t,
+                      "no_output_seconds": t_none, "particle_steps_per_s": n * steps / t,
+                      "no_output_particle_steps_per_s": n * steps / t_none, "frames_GBps": d2h / t / 1e9,
+                      "serial_estimate_s": t_none + d2h / 50e9,   # D2H alone at ~50 GB/s, no overlap, no file write
+                      "verified": ok}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -76,6 +76,13 @@ SIGNATURES = {
     "vpm_lb_rk438_steps": (_i32, [_vp, _vp, _f64, _f64, _i32, _i32, _vp]),
     "vpm_lb_rk438_steps_async": (_i32, [_vp, _vp, _f64, _f64, _i32, _i32]),
     "vpm_vspace_get": (_i32, [_vp, _vp, _vp]),
+    "vpm_h5_create": (_i32, [C.c_char_p, C.POINTER(_vp)]),
+    "vpm_h5_add_dataset": (_i32, [_vp, C.c_char_p, _i32, C.POINTER(_i64), C.POINTER(_i32)]),
+    "vpm_h5_commit": (_i32, [_vp]),
+    "vpm_h5_write": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp]),
+    "vpm_h5_close": (_i32, [_vp]),
+    "vpm_vp_run": (_i32, [_vp, _vp, _f64, _f64, _i32, _i32, _i32, _i32, C.c_char_p, _vp, C.POINTER(_i32)]),
+    "vpm_lb_run": (_i32, [_vp, _vp, _f64, _f64, _f64, _i32, _i32, _i32, C.c_char_p, _vp, C.POINTER(_i32)]),
     "vpm_galerkin_periodic": (_i32, [_f64, _f64, _i32, _i32, _vp, _vp, _vp]),
     "vpm_galerkin_clamped": (_i32, [_f64, _f64, _i32, _i32, _i32, C.POINTER(_i32), _vp, _vp]),
     "vpm_selftest_wrap": (_i32, [_i32]),

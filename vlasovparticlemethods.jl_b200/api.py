@@ -17,6 +17,7 @@ Reference files mirrored (paths relative to the reference checkout):
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 
@@ -647,24 +648,42 @@ def _ntime(tspan, tstep):
     return int(round((tspan[1] - tspan[0]) / tstep))
 
 
-class _Trajectory:
-    """run! output: the reference writes HDF5 datasets z[nd,np,nt+1] (splitting.jl:32-34) or z[np,nt+1], t
-    (geometric_integrator.jl:21-25).  h5py is not in this image, so the same arrays go to an .npz with
-    the same dataset names; if h5py is importable an HDF5 file with the reference layout is written."""
+class H5Writer:
+    """The trajectory files of run! (datasets z[nd,np,nt+1] chunk (nd,np,1), splitting.jl:32-34; z[np,nt+1] and t,
+    geometric_integrator.jl:21-25) written by the library's own minimal HDF5 writer (csrc/h5min.cpp): h5py / HDF5.jl
+    are not needed.  Shapes are given Julia-style (column-major, frame axis last) and reversed for the file exactly
+    as HDF5.jl does.  Host-only."""
 
     def __init__(self, path):
-        self.path, self.data = path, {}
+        self._h = C.c_void_p()
+        check(_lib().vpm_h5_create(os.fsencode(path), C.byref(self._h)))
+        self._ids = {}
 
-    def save(self):
-        if self.path is None:
-            return
-        try:
-            import h5py  # noqa
-            with h5py.File(self.path, "w") as f:
-                for k, a in self.data.items():
-                    f.create_dataset(k, data=np.ascontiguousarray(a.T))  # Julia column-major on disk
-        except ImportError:
-            np.savez(self.path if str(self.path).endswith(".npz") else str(self.path) + ".npz", **self.data)
+    def create_dataset(self, name, julia_shape):
+        dims = (C.c_int64 * len(julia_shape))(*reversed([int(d) for d in julia_shape]))
+        ident = C.c_int(-1)
+        check(_lib().vpm_h5_add_dataset(self._h, name.encode(), len(julia_shape), dims, C.byref(ident)))
+        self._ids[name] = ident.value
+        return self
+
+    def commit(self):
+        check(_lib().vpm_h5_commit(self._h))
+        return self
+
+    def write_frame(self, name, frame, data, offset=0):
+        a = np.ascontiguousarray(data, dtype=np.float64)
+        check(_lib().vpm_h5_write(self._h, self._ids[name], int(frame), int(offset), a.size, _hp(a)))
+
+    def close(self):
+        if self._h:
+            check(_lib().vpm_h5_close(self._h))
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 class SplittingMethod:
@@ -701,50 +720,31 @@ class GeometricIntegrator:
 def run_(method, h5file=None, save_stride=None, diag_mode=1):
     """run!(method, h5file): src/methods/splitting.jl:23-52, src/methods/geometric_integrator.jl:12-44.
 
-    The state stays on the device between steps.  save_stride=None writes no trajectory (the reference
-    writes every step); save_stride=k stores every k-th step plus the initial state.
-    Diagnostics (W,K,M) or (sum v, sum v^2) of every step are kept in method.diagnostics.
+    The state stays on the device between steps (vpm_vp_run / vpm_lb_run).  With h5file, the frames of steps
+    0, k, 2k, ..., nt (k = save_stride, default 1 = the reference's every-step output) are written to an HDF5
+    file in the reference's layout (dataset "z", plus "t"), copied off the device while the next steps compute.
+    Without h5file no trajectory is kept.  Diagnostics (W,K,M) or (sum v, sum v^2) of every step are kept in
+    method.diagnostics; method.frames = number of frames written.
     """
     nt = _ntime(method.tspan, method.tstep)
-    traj = _Trajectory(h5file if save_stride else None)
+    stride = int(save_stride or 1) if h5file is not None else 0
+    path = os.fsencode(h5file) if h5file is not None else None
+    frames = C.c_int(0)
     if isinstance(method, SplittingMethod):
-        d = method.model.distribution
-        frames = [d.download_aos(2)] if save_stride else []
-        diags = []
-        done = 0
-        while done < nt:
-            chunk = min(save_stride, nt - done) if save_stride else nt
-            dg = _vp_steps(method, chunk, diag_mode)
-            if dg is not None:
-                diags.append(dg if not diags else dg[1:])
-            done += chunk
-            if save_stride:
-                frames.append(d.download_aos(2))
-        method.diagnostics = np.concatenate(diags) if diags else None
-        if save_stride:
-            traj.data["z"] = np.stack(frames, axis=-1)  # (nd, np, nframes)
-            traj.save()
+        d, pot = method.model.distribution, method.model.potential
+        diag = np.zeros((nt + 1, 3)) if diag_mode else None
+        mode = _cabi.VP_FROZEN if method.field == "frozen" else _cabi.VP_SELFCONSISTENT
+        check(_lib().vpm_vp_run(pot._h, d._h, method.tstep, method.chi, nt, mode, int(diag_mode), stride, path, _hp(diag),
+                                C.byref(frames)))
+        method.diagnostics, method.frames = diag, frames.value
         return d
     if isinstance(method, GeometricIntegrator):
         m = method.model
         d, sd = m.dist, m.ent.dist
-        frames = [d.get("v")] if save_stride else []
-        times = [method.tspan[0]]
-        diags, done = [], 0
-        while done < nt:
-            chunk = min(save_stride, nt - done) if save_stride else nt
-            dg = np.zeros((chunk + 1, 2))
-            check(_lib().vpm_lb_rk438_steps(sd._h, d._h, m.nu, method.tstep, chunk, int(m.conservative), _hp(dg)))
-            diags.append(dg if not diags else dg[1:])
-            done += chunk
-            if save_stride:
-                frames.append(d.get("v"))
-                times.append(method.tspan[0] + done * method.tstep)
-        method.diagnostics = np.concatenate(diags)
-        if save_stride:
-            traj.data["z"] = np.stack(frames, axis=-1)  # (np, nframes)
-            traj.data["t"] = np.asarray(times)
-            traj.save()
+        diag = np.zeros((nt + 1, 2))
+        check(_lib().vpm_lb_run(sd._h, d._h, m.nu, method.tstep, float(method.tspan[0]), nt, int(m.conservative), stride, path,
+                                _hp(diag), C.byref(frames)))
+        method.diagnostics, method.frames = diag, frames.value
         return d
     raise TypeError("run_ expects a SplittingMethod or a GeometricIntegrator")
 

@@ -2,6 +2,7 @@
 // spaces, operator-level entry points and the whole-step device-resident steppers.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -664,7 +665,7 @@ int vpm_xspace_get(vpm_xspace* xs, double* rhs_host, double* phi_host)
 // Strang stepping on SoA arrays (x, v evolve; w and the frozen-field deposit positions are inputs)
 static int vp_steps(vpm_xspace* xs, double* x, double* v, const double* w, int64_t n, const double* xdep,
                     const double* wdep, int64_t ndep, double dt, double chi, int nsteps, int mode, int diag_mode,
-                    bool uw = false, double wu = 0.0)
+                    bool uw = false, double wu = 0.0, bool keep_field = false)
 {
     vpm_ctx* ctx = xs->ctx;
     const double Dt = dt * chi, escale = -1.0 / (chi * chi), wscale = 1.0 / (chi * chi);
@@ -678,12 +679,15 @@ static int vp_steps(vpm_xspace* xs, double* x, double* v, const double* w, int64
 
     if (mode == VPM_VP_FROZEN) {
         // field of model.distribution, fixed for the whole run
-        VpPass pd{};
-        pd.x_in = xdep; pd.w = wdep; pd.n = ndep; pd.flags = VP_DEPOSIT;
-        pd.use_uw = uw; pd.w_uniform = wu;
-        VPM_CHECK(launch_vp_pass(ctx, xs, pd, &grid));
-        VPM_CHECK(launch_vp_field(ctx, xs, ALL, grid, 1, 0, escale, wscale, diag_mode ? 0 : -1, -1));
-        if (diag_mode) {
+        // (keep_field: a later leg of one run -- the kick table of the first leg stays in place)
+        if (!keep_field) {
+            VpPass pd{};
+            pd.x_in = xdep; pd.w = wdep; pd.n = ndep; pd.flags = VP_DEPOSIT;
+            pd.use_uw = uw; pd.w_uniform = wu;
+            VPM_CHECK(launch_vp_pass(ctx, xs, pd, &grid));
+            VPM_CHECK(launch_vp_field(ctx, xs, ALL, grid, 1, 0, escale, wscale, diag_mode ? 0 : -1, -1));
+        }
+        if (diag_mode && !keep_field) {
             VpPass pk = ps;
             pk.flags = VP_DIAG;
             VPM_CHECK(launch_vp_pass(ctx, xs, pk, &grid));
@@ -1031,6 +1035,214 @@ int vpm_vspace_get(vpm_vspace* vs, double* rhs_host, double* coef_host)
     VPM_CUDA(cudaSetDevice(vs->ctx->device));
     if (rhs_host) VPM_CHECK(d2h(vs->ctx, rhs_host, vs->rhs, vs->nv));
     if (coef_host) VPM_CHECK(d2h(vs->ctx, coef_host, vs->coef, vs->nv));
+    return VPM_OK;
+}
+
+/* ---------------------------------------------------------------- run! drivers with trajectory output */
+
+}  // extern "C"
+
+namespace {
+
+// Saved frames leave the device without stalling the stepper: the compute stream snapshots the state into one
+// of two device buffers (a D2D pass, ~0.5 ms per 1e8 particles), records an event, and carries on with the next
+// leg of steps; a second stream copies the snapshot to the host through a small ring of pinned buffers and the
+// host thread writes each piece into its place in the HDF5 file (h5min.cpp) while the GPU computes.
+struct FrameWriter {
+    static constexpr int kSlots = 4;
+    vpm_ctx* ctx = nullptr;
+    vpm_h5* h5 = nullptr;
+    int ds_z = -1, ds_t = -1;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr};
+    double* snap[2] = {nullptr, nullptr};
+    size_t frame_doubles = 0, piece = 0;
+    double* slot[kSlots] = {};
+    cudaEvent_t slot_ev[kSlots] = {};
+
+    int open(vpm_ctx* c, const char* path, int64_t nframes, int64_t n, int nd)
+    {
+        ctx = c;
+        if (n < 1) return fail(VPM_ERR_INVALID, "trajectory output needs at least one particle");
+        frame_doubles = (size_t)n * (size_t)nd;
+        piece = std::min<size_t>(frame_doubles, (size_t)4 << 20);  // 32 MiB pieces
+        VPM_CHECK(vpm_h5_create(path, &h5));
+        const int64_t dz3[3] = {nframes, n, nd}, dz2[2] = {nframes, n}, dt1[1] = {nframes};
+        VPM_CHECK(nd > 1 ? vpm_h5_add_dataset(h5, "z", 3, dz3, &ds_z) : vpm_h5_add_dataset(h5, "z", 2, dz2, &ds_z));
+        VPM_CHECK(vpm_h5_add_dataset(h5, "t", 1, dt1, &ds_t));
+        VPM_CHECK(vpm_h5_commit(h5));
+        VPM_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            VPM_CUDA(cudaEventCreateWithFlags(&ready[b], cudaEventDisableTiming));
+            if (cudaMalloc((void**)&snap[b], frame_doubles * sizeof(double)) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(VPM_ERR_NOMEM, "cudaMalloc of the trajectory snapshot buffers failed");
+            }
+        }
+        for (int i = 0; i < kSlots; i++) {
+            VPM_CUDA(cudaEventCreateWithFlags(&slot_ev[i], cudaEventDisableTiming));
+            VPM_CUDA(cudaMallocHost((void**)&slot[i], piece * sizeof(double)));
+        }
+        return VPM_OK;
+    }
+
+    // the snapshot of frame f has been enqueued into snap[f & 1] on the compute stream
+    int mark_ready(int64_t f)
+    {
+        VPM_CUDA(cudaEventRecord(ready[f & 1], ctx->stream));
+        return VPM_OK;
+    }
+
+    // device -> pinned ring -> file, for frame f; returns when the frame is in the file
+    int drain(int64_t f, double t)
+    {
+        const double* src = snap[f & 1];
+        VPM_CUDA(cudaStreamWaitEvent(copy, ready[f & 1], 0));
+        const size_t npieces = (frame_doubles + piece - 1) / piece;
+        for (size_t i = 0; i < npieces + kSlots; i++) {
+            if (i >= (size_t)kSlots) {
+                const size_t j = i - kSlots;
+                if (j < npieces) {
+                    const size_t cnt = std::min(piece, frame_doubles - j * piece);
+                    VPM_CUDA(cudaEventSynchronize(slot_ev[j % kSlots]));
+                    VPM_CHECK(vpm_h5_write(h5, ds_z, f, (int64_t)(j * piece), (int64_t)cnt, slot[j % kSlots]));
+                }
+            }
+            if (i < npieces) {
+                const size_t cnt = std::min(piece, frame_doubles - i * piece);
+                VPM_CUDA(cudaMemcpyAsync(slot[i % kSlots], src + i * piece, cnt * sizeof(double), cudaMemcpyDeviceToHost, copy));
+                VPM_CUDA(cudaEventRecord(slot_ev[i % kSlots], copy));
+            }
+        }
+        return vpm_h5_write(h5, ds_t, f, 0, 1, &t);
+    }
+
+    ~FrameWriter()
+    {
+        if (copy) cudaStreamSynchronize(copy);
+        for (int i = 0; i < kSlots; i++) {
+            if (slot[i]) cudaFreeHost(slot[i]);
+            if (slot_ev[i]) cudaEventDestroy(slot_ev[i]);
+        }
+        for (int b = 0; b < 2; b++) {
+            if (snap[b]) cudaFree(snap[b]);
+            if (ready[b]) cudaEventDestroy(ready[b]);
+        }
+        if (copy) cudaStreamDestroy(copy);
+        if (h5) vpm_h5_close(h5);
+    }
+};
+
+struct DeviceScratch {
+    double* p = nullptr;
+    ~DeviceScratch() { if (p) cudaFree(p); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int vpm_vp_run(vpm_xspace* xs, vpm_particles* p, double dt, double chi, int nsteps, int mode, int diag_mode, int save_stride,
+               const char* h5path, double* diag_host, int* frames_out)
+{
+    if (frames_out) *frames_out = 0;
+    if (!h5path || save_stride <= 0) return vpm_vp_strang_steps(xs, p, dt, chi, nsteps, mode, diag_mode, diag_host);
+    VPM_REQUIRE(xs && p && xs->ctx == p->ctx, "vpm_vp_run: bad handles");
+    VPM_REQUIRE(nsteps >= 0 && chi > 0 && (mode == VPM_VP_SELFCONSISTENT || mode == VPM_VP_FROZEN) && diag_mode >= 0 && diag_mode <= 2,
+                "vpm_vp_run: bad arguments");
+    if (!diag_host) diag_mode = 0;
+    vpm_ctx* ctx = xs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    const int64_t nframes = 1 + ((int64_t)nsteps + save_stride - 1) / save_stride;
+    FrameWriter fw;
+    VPM_CHECK(fw.open(ctx, h5path, nframes, p->n, 2));
+    DeviceScratch hist;  // W, K, M rows of the whole run (every leg restarts its own history at row 0)
+    if (diag_mode) {
+        if (cudaMalloc((void**)&hist.p, sizeof(double) * 3 * ((size_t)nsteps + 1)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(VPM_ERR_NOMEM, "cudaMalloc of the diagnostics history failed");
+        }
+    }
+    VPM_CHECK(launch_soa_to_aos(ctx, p->x, p->v, nullptr, 2, p->n, fw.snap[0]));
+    VPM_CHECK(fw.mark_ready(0));
+    int done = 0;
+    if (nsteps == 0 && diag_mode) {
+        VPM_CHECK(vp_steps(xs, p->x, p->v, p->w, p->n, p->x, p->w, p->n, dt, chi, 0, mode, diag_mode, p->uw, p->wu, false));
+        VPM_CUDA(cudaMemcpyAsync(hist.p, xs->diag, sizeof(double) * 3, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    for (int64_t f = 0; f < nframes; f++) {
+        if (done < nsteps) {
+            // enqueue the next leg and its snapshot before draining frame f, so the GPU computes while the host writes
+            const int leg = std::min(save_stride, nsteps - done);
+            VPM_CHECK(vp_steps(xs, p->x, p->v, p->w, p->n, p->x, p->w, p->n, dt, chi, leg, mode, diag_mode, p->uw, p->wu, done > 0));
+            if (diag_mode) {
+                const int skip = done > 0 ? 1 : 0;   // row 0 of a later leg repeats the previous leg's last row
+                VPM_CUDA(cudaMemcpyAsync(hist.p + 3 * (size_t)(done + skip), xs->diag + 3 * skip,
+                                         sizeof(double) * 3 * (size_t)(leg + 1 - skip), cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            done += leg;
+            VPM_CHECK(launch_soa_to_aos(ctx, p->x, p->v, nullptr, 2, p->n, fw.snap[(f + 1) & 1]));
+            VPM_CHECK(fw.mark_ready(f + 1));
+        }
+        const int64_t step = std::min<int64_t>(f * save_stride, nsteps);
+        VPM_CHECK(fw.drain(f, (double)step * dt));
+    }
+    if (diag_mode) {
+        VPM_CHECK(d2h(ctx, diag_host, hist.p, 3 * ((size_t)nsteps + 1)));
+        if (mode == VPM_VP_FROZEN)
+            for (int it = 1; it <= nsteps; it++) diag_host[3 * it] = diag_host[0];  // the field never changes
+    } else {
+        VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (frames_out) *frames_out = (int)nframes;
+    return VPM_OK;
+}
+
+int vpm_lb_run(vpm_vspace* vs, vpm_particles* p, double nu, double dt, double t0, int nsteps, int conservative, int save_stride,
+               const char* h5path, double* diag_host, int* frames_out)
+{
+    if (frames_out) *frames_out = 0;
+    if (!h5path || save_stride <= 0) return vpm_lb_rk438_steps(vs, p, nu, dt, nsteps, conservative, diag_host);
+    VPM_REQUIRE(vs && p && vs->ctx == p->ctx && nsteps >= 0, "vpm_lb_run: bad arguments");
+    vpm_ctx* ctx = vs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    const int64_t nframes = 1 + ((int64_t)nsteps + save_stride - 1) / save_stride;
+    FrameWriter fw;
+    VPM_CHECK(fw.open(ctx, h5path, nframes, p->n, 1));
+    DeviceScratch hist;  // (sum v, sum v^2) rows of the whole run
+    if (diag_host) {
+        if (cudaMalloc((void**)&hist.p, sizeof(double) * 2 * ((size_t)nsteps + 1)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(VPM_ERR_NOMEM, "cudaMalloc of the diagnostics history failed");
+        }
+    }
+    const size_t vbytes = sizeof(double) * (size_t)p->n;
+    VPM_CUDA(cudaMemcpyAsync(fw.snap[0], p->v, vbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    VPM_CHECK(fw.mark_ready(0));
+    int done = 0;
+    if (nsteps == 0 && diag_host) {
+        VPM_CHECK(vpm_lb_rk438_steps_async(vs, p, nu, dt, 0, conservative));
+        VPM_CUDA(cudaMemcpyAsync(hist.p, vs->diag, sizeof(double) * 2, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    for (int64_t f = 0; f < nframes; f++) {
+        if (done < nsteps) {
+            const int leg = std::min(save_stride, nsteps - done);
+            VPM_CHECK(vpm_lb_rk438_steps_async(vs, p, nu, dt, leg, conservative));
+            if (diag_host) {
+                const int skip = done > 0 ? 1 : 0;
+                VPM_CUDA(cudaMemcpyAsync(hist.p + 2 * (size_t)(done + skip), vs->diag + 2 * skip,
+                                         sizeof(double) * 2 * (size_t)(leg + 1 - skip), cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            done += leg;
+            VPM_CUDA(cudaMemcpyAsync(fw.snap[(f + 1) & 1], p->v, vbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+            VPM_CHECK(fw.mark_ready(f + 1));
+        }
+        const int64_t step = std::min<int64_t>(f * save_stride, nsteps);
+        VPM_CHECK(fw.drain(f, t0 + (double)step * dt));
+    }
+    if (diag_host) VPM_CHECK(d2h(ctx, diag_host, hist.p, 2 * ((size_t)nsteps + 1)));
+    else VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (frames_out) *frames_out = (int)nframes;
     return VPM_OK;
 }
 
