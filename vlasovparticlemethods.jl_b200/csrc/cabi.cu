@@ -1047,7 +1047,10 @@ namespace {
 // Saved frames leave the device without stalling the stepper: the compute stream snapshots the state into one
 // of two device buffers (a D2D pass, ~0.5 ms per 1e8 particles), records an event, and carries on with the next
 // leg of steps; a second stream copies the snapshot to the host through a small ring of pinned buffers and the
-// host thread writes each piece into its place in the HDF5 file (h5min.cpp) while the GPU computes.
+// host thread writes each piece into its place in the HDF5 file (h5min.cpp) while the GPU computes.  The file
+// system sets the pace (measured 3-4 GB/s of buffered writes into the page cache or tmpfs against ~50 GB/s of
+// PCIe; a pool of 8 writer threads measured no faster, buffered writes to one file serialise on its inode lock),
+// so a frame is hidden completely once a leg of steps computes for longer than frame bytes / 3 GB/s.
 struct FrameWriter {
     static constexpr int kSlots = 4;
     vpm_ctx* ctx = nullptr;
