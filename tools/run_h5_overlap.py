@@ -58,11 +58,17 @@ def main():
         size = os.path.getsize(path)
         # the last frame must be the final device state, and the history must match the run without output
         z_last = h5mini.File(path).read("z")[-1] if size < 6e9 else None
-        ok = True
+        last_ok = None
         if z_last is not None:
             xg, vg, _ = d.get()
-            ok = bool(np.array_equal(z_last[:, 0], xg) and np.array_equal(z_last[:, 1], vg))
-        ok = ok and bool(np.allclose(m.diagnostics, m0.diagnostics, rtol=1e-12, atol=1e-14))
+            last_ok = bool(np.array_equal(z_last[:, 0], xg) and np.array_equal(z_last[:, 1], vg))
+        # legs of `stride` steps split the fused pass at the saved steps; the history may then differ from the run
+        # without output by summation order (and, over thousands of steps, by what the dynamics make of that)
+        x0, v0, _ = d0.get()
+        xg, vg, _ = d.get()
+        scale = np.abs(m0.diagnostics).max(axis=0)
+        diag_diff = float((np.abs(m.diagnostics - m0.diagnostics) / scale).max())
+        state_diff = float(max(np.abs(xg - x0).max() / np.abs(x0).max(), np.abs(vg - v0).max() / np.abs(v0).max()))
         os.remove(path)
         d2h = 16.0 * n * frames
         out[label] = {"save_stride": stride, "steps": steps, "frames": frames, "file_bytes": size, "seconds": t,
@@ -70,7 +76,8 @@ def main():
                       "no_output_particle_steps_per_s": n * steps / t_none, "frames_GBps": d2h / t / 1e9,
                       "exposed_seconds_per_frame": (t - t_none) / frames,
                       "serial_d2h_estimate_s": t_none + d2h / 50e9,   # D2H alone at ~50 GB/s, no overlap, no file write
-                      "verified": ok}
+                      "last_frame_is_final_state": last_ok, "diag_max_rel_diff_vs_no_output": diag_diff,
+                      "state_max_rel_diff_vs_no_output": state_diff}
     print(json.dumps(out))
 
 

@@ -15,10 +15,52 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def run_h5(vpm, orc, nrm):
+    """run! drivers with trajectory output: snapshot passes, copy stream, pinned ring (several pieces), legs of steps"""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import h5mini
+    n = (9 << 20) // 2 + 77      # frame = 2 n doubles > two 32 MiB ring pieces, with a ragged tail
+    bot = vpm.BumpOnTail()
+    x, v, w = orc.sample_bump_on_tail(n)
+    with tempfile.TemporaryDirectory() as tmp:
+        for field in ("selfconsistent", "frozen"):
+            d = vpm.ParticleDistribution(1, 1, n).set(x, v, w)
+            pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, bot.L), 4, 16))
+            m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 0.3), 0.1, field=field)
+            path = os.path.join(tmp, field + ".h5")
+            vpm.run_(m, path, save_stride=2, diag_mode=1)
+            z = h5mini.File(path).read("z")
+            xs = orc.XSpace(0.0, bot.L, 4, 16)
+            if field == "selfconsistent":
+                xo, vo, _, _ = xs.strang_selfconsistent(x, v, w, 0.1, 2)
+            else:
+                xo, vo, _ = xs.strang_frozen(x, v, x, w, 0.1, 2)
+            assert z.shape == (3, n, 2) and nrm(z[1, :, 0], xo) < 1e-12 and nrm(z[1, :, 1], vo) < 1e-12, field
+            xg, vg, _ = d.get()
+            assert np.array_equal(z[2, :, 0], xg) and np.array_equal(z[2, :, 1], vg), field
+        nl = 3 * 512 + 77
+        vv = np.random.default_rng(1).standard_normal(nl) * 1.2
+        ww = np.full(nl, 1.0 / nl)
+        sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
+        for cons in (False, True):
+            d = vpm.ParticleDistribution(1, 1, nl).set(np.zeros(nl), vv, ww)
+            model = (vpm.ConservativeLenardBernstein if cons else vpm.LenardBernstein)(d, vpm.CollisionEntropy(sd), nu=0.8)
+            gi = vpm.GeometricIntegrator(model, (0.0, 0.06), 0.02)
+            path = os.path.join(tmp, f"lb{int(cons)}.h5")
+            vpm.run_(gi, path, save_stride=2)
+            z = h5mini.File(path).read("z")
+            vo, _ = orc.VSpace(-10.0, 10.0, 41, 4).rk438(vv, ww, 0.8, 0.02, 2, conservative=cons)
+            assert z.shape == (3, nl) and np.abs(z[1] - vo).max() < 1e-10 and np.array_equal(z[2], d.get("v")), cons
+    print("sanitize workload (run! with HDF5 output): all results match the oracle")
+
+
 def main():
     import vpm_b200 as vpm
     from oracle import oracle as orc
     nrm = lambda a, b: np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+    if "--run-h5" in sys.argv:
+        return run_h5(vpm, orc, nrm)
     n = 3 * 512 + 77
     # ---- Vlasov-Poisson: TMA main pass, prologue/epilogue passes, field kernel, both modes
     bot = vpm.BumpOnTail()
