@@ -126,3 +126,42 @@ def test_writer_errors(vpm, tmp_path):
     w.close()
     with pytest.raises(vpm.VpmError, match="no datasets"):
         vpm.H5Writer(tmp_path / "empty.h5").commit()
+
+
+def test_writer_fuzz(vpm, tmp_path):
+    """random files: 1-8 datasets of rank 1-3, 1-200 frames (one- and two-level chunk B-trees), random names, frames
+    written in random order and random pieces; every dataset must read back exactly"""
+    from hypothesis import given, settings, strategies as st
+
+    names = st.text(alphabet="abcdefghijklmnopqrstuvwxyzABCXYZ_0123456789", min_size=1, max_size=12)
+    dset = st.tuples(names, st.lists(st.integers(1, 6), min_size=0, max_size=2))
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(dset, min_size=1, max_size=8, unique_by=lambda d: d[0]), st.integers(1, 200), st.integers(0, 2**32 - 1))
+    def run(dsets, nframes, seed):
+        rng = np.random.default_rng(seed)
+        path = tmp_path / "fuzz.h5"
+        w = vpm.H5Writer(path)
+        data = {}
+        for name, inner in dsets:
+            shape = tuple(inner) + (nframes,)                       # Julia order: frame axis last
+            w.create_dataset(name, shape)
+            data[name] = rng.standard_normal((nframes,) + tuple(reversed(inner)))
+        w.commit()
+        for name, a in data.items():
+            for n in rng.permutation(nframes):
+                flat = a[n].ravel()
+                cut = int(rng.integers(0, flat.size + 1))
+                if cut:
+                    w.write_frame(name, n, flat[:cut])
+                if cut < flat.size:
+                    w.write_frame(name, n, flat[cut:], offset=cut)
+        w.close()
+        f = h5mini.File(path)
+        assert sorted(f.datasets) == sorted(data) and f.eof_addr == os.path.getsize(path)
+        for name, a in data.items():
+            ds = f.datasets[name]
+            assert ds.shape == a.shape and ds.chunk == (1,) + a.shape[1:] and ds.maxshape == (None,) + a.shape[1:]
+            np.testing.assert_array_equal(f.read(name), a)
+
+    run()

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <new>
 
 #include "vpm_internal.h"
@@ -49,6 +50,8 @@ int kernel_occupancy(vpm_ctx* ctx, const void* kern, int block, size_t smem, int
     };
     static std::map<Key, int> cache;                           // occupancy per (device, kernel, smem)
     static std::map<std::pair<int, const void*>, size_t> attr;  // largest dynamic-smem attribute set so far
+    static std::mutex mu;                                      // contexts of different GPUs may live on different host threads
+    std::lock_guard<std::mutex> guard(mu);
     size_t& cur = attr[{ctx->device, kern}];
     if (smem > cur) {  // the attribute is per kernel: only ever raise it
         VPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
