@@ -11,7 +11,7 @@ the whole history is kept and checked:
   E[(v-m)^4]/var^2 goes from 43/25 = 1.72 (two unit Maxwellians at +-2) to 3, the sixth E[(v-m)^6]/var^3 to 15;
 * plain LB relaxes to the unit Maxwellian instead (variance 5 -> 1): energy is NOT conserved.
 
-Prints one JSON object (profiles/r1_physics_clb_1e7.json is a copy).  Usage: python tools/lb_checks.py [N] [nsteps]
+Prints one JSON object (profiles/r1_physics_clb_1e7.json is a copy).  Usage: python tools/lb_checks.py [N] [nsteps] [clb,lb]
 """
 import json
 import os
@@ -54,11 +54,11 @@ def run(vpm, n, nsteps, conservative, chunk):
     return dg, snaps, wall
 
 
-def main(n=int(1e7), nsteps=50000):
+def main(n=int(1e7), nsteps=50000, models=("clb", "lb")):
     import vpm_b200 as vpm
     out = {"particles": n, "steps": nsteps, "dt": 1e-2, "nu": 1.0}
     chunk = max(nsteps // 10, 1)
-    for cons in (True, False):
+    for cons in [m == "clb" for m in models]:
         dg, snaps, wall = run(vpm, n, nsteps, cons, chunk)
         key = "clb" if cons else "lb"
         out[key] = {
@@ -78,4 +78,5 @@ def main(n=int(1e7), nsteps=50000):
 
 
 if __name__ == "__main__":
-    main(int(float(sys.argv[1])) if len(sys.argv) > 1 else int(1e7), int(sys.argv[2]) if len(sys.argv) > 2 else 50000)
+    main(int(float(sys.argv[1])) if len(sys.argv) > 1 else int(1e7), int(sys.argv[2]) if len(sys.argv) > 2 else 50000,
+         tuple(sys.argv[3].split(",")) if len(sys.argv) > 3 else ("clb", "lb"))
