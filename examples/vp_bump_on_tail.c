@@ -2,9 +2,11 @@
  *
  *   gcc -O2 -Iinclude examples/vp_bump_on_tail.c -o examples/vp_bump_on_tail \
  *       -Lvlasovparticlemethods.jl_b200/lib -lvpm_b200 -Wl,-rpath,'$ORIGIN/../vlasovparticlemethods.jl_b200/lib' -lm
- *   ./examples/vp_bump_on_tail [particles] [steps]
+ *   ./examples/vp_bump_on_tail [particles] [steps] [h5file] [save_stride]
  *
- * Prints the W, K, M history (src/vlasov_poisson.jl:58-67) every 50 steps and the throughput. */
+ * Prints the W, K, M history (src/vlasov_poisson.jl:58-67) every 50 steps and the throughput.  With h5file the
+ * states of every save_stride-th step (default 50) go to dataset "z" of that file in the layout of
+ * run!(::SplittingMethod, h5file) (src/methods/splitting.jl:32-34), streamed off the device while it computes. */
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -25,6 +27,8 @@ int main(int argc, char** argv)
 {
     const long long n = argc > 1 ? atoll(argv[1]) : 10000000LL;
     const int nsteps = argc > 2 ? atoi(argv[2]) : 500;
+    const char* h5file = argc > 3 ? argv[3] : NULL;
+    const int stride = argc > 4 ? atoi(argv[4]) : 50;
     const double kappa = 0.3, dt = 0.1, L = 2.0 * M_PI / kappa;
 
     vpm_ctx* ctx = NULL;
@@ -39,7 +43,8 @@ int main(int argc, char** argv)
     CHECK(vpm_sync(ctx));
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
-    CHECK(vpm_vp_strang_steps(xs, p, dt, 1.0, nsteps, VPM_VP_SELFCONSISTENT, 1, diag));
+    int frames = 0;
+    CHECK(vpm_vp_run(xs, p, dt, 1.0, nsteps, VPM_VP_SELFCONSISTENT, 1, stride, h5file, diag, &frames));
     clock_gettime(CLOCK_MONOTONIC, &t1);
     const double sec = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 
@@ -50,6 +55,8 @@ int main(int argc, char** argv)
     const double e1 = diag[3] + diag[4], eN = diag[3 * nsteps] + diag[3 * nsteps + 1];
     printf("particles %lld steps %d: %.3f s, %.3e particle-steps/s, kernels launched %lld, energy drift %.2e\n", n, nsteps,
            sec, (double)n * nsteps / sec, (long long)vpm_launch_count(ctx), fabs(eN - e1) / e1);
+
+    if (h5file) printf("%d frames of %lld particles written to %s\n", frames, n, h5file);
 
     free(diag);
     CHECK(vpm_xspace_destroy(xs));

@@ -87,3 +87,15 @@ def test_plain_c_driver_runs():
     assert "particle-steps/s" in last
     drift = float(last.split("energy drift")[1])
     assert drift < 5e-3
+    # the same driver with trajectory output: run!(method, h5file) from plain C
+    import tempfile
+    import h5mini
+    with tempfile.TemporaryDirectory() as tmp:
+        h5 = os.path.join(tmp, "bot.h5")
+        out = subprocess.run([exe, "200000", "100", h5, "40"], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        assert "4 frames" in out.stdout.strip().splitlines()[-1]
+        f = h5mini.File(h5)
+        assert f.datasets["z"].shape == (4, 200000, 2)
+        t = f.read("t")
+        assert abs(t[-1] - 10.0) < 1e-12 and abs(t[1] - 4.0) < 1e-12
