@@ -116,9 +116,11 @@ int vpm_xspace_destroy(vpm_xspace* xs);
 int vpm_xspace_stencils(const vpm_xspace* xs, double* mass, double* stiffness);
 
 /* projection!(potential, distribution): src/projections/potential.jl:2-22.
- * x_dev, w_dev: device arrays of length n; rhs_host: n_basis doubles. */
+ * x_dev, w_dev: device arrays of length n; rhs_host: n_basis doubles, or NULL to leave the result on the device
+ * (it is the input of the next vpm_poisson_solve(xs, NULL, ...)). */
 int vpm_deposit_x(vpm_xspace* xs, const double* x_dev, const double* w_dev, int64_t n, double* rhs_host);
-/* PoissonSolvers.update!(potential) [call site src/models/vlasov_poisson.jl:14]: rhs -> phi */
+/* PoissonSolvers.update!(potential) [call site src/models/vlasov_poisson.jl:14]: rhs -> phi.  rhs_host == NULL: solve
+ * for the device-side rhs of the last deposit; phi_host may be NULL (the potential stays on the device for the kicks). */
 int vpm_poisson_solve(vpm_xspace* xs, const double* rhs_host, double* phi_host);
 /* potential.solver.Mfac \ potential.rhs (test/projections_tests.jl:27): rhs -> density coefficients */
 int vpm_mass_solve_x(vpm_xspace* xs, const double* rhs_host, double* rho_host);

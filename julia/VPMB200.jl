@@ -11,7 +11,10 @@ using VlasovMethods
 import VlasovMethods: projection!, projection, run!, initialize!, DistributionFunction,
                       SplittingMethod, GeometricIntegrator, VlasovPoisson,
                       LenardBernstein, ConservativeLenardBernstein, BumpOnTail, DoubleMaxwellian,
-                      UniformDistribution, ShiftedUniformDistribution, ShiftedNormalV
+                      UniformDistribution, ShiftedUniformDistribution, ShiftedNormalV,
+                      LB_rhs!, CLB_rhs!, LB_rhs_GI!, CLB_rhs_GI!, s_advection!, s_acceleration!,
+                      compute_f_densities, compute_df_densities, projection_density, projection_momentum, projection_energy
+using BSplineKit: Derivative
 
 const libvpm = get(ENV, "LIBVPM_B200", "libvpm_b200.so")
 
@@ -158,7 +161,94 @@ function projection(velocities::AbstractVector{Float64}, dist::DeviceParticleDis
     finally
         ccall((:vpm_dev_free, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx.h, dv[])
     end
-    final_dist
+    DeviceSpline(final_dist, false)     # aliases final_dist's coefficients, as Spline(basis, coefficients) does upstream
+end
+
+# with_device_vector(f, ctx, host): f(device pointer) on a temporary device copy of a host vector
+function with_device_vector(f::Function, ctx::Context, host::AbstractVector{Float64})
+    d = Ref{Ptr{Float64}}()
+    check(ccall((:vpm_dev_alloc, libvpm), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Float64}}), ctx.h, length(host), d))
+    try
+        check(ccall((:vpm_memcpy_h2d, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), ctx.h, d[], host, length(host)))
+        return f(d[])
+    finally
+        ccall((:vpm_dev_free, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx.h, d[])
+    end
+end
+
+# fs.(v) and (Derivative(1) * fs).(v): src/models/lenard_bernstein.jl:26-28, src/projections/density.jl:45-47
+struct DeviceSpline
+    sdist::DeviceSplineDistribution
+    derivative::Bool
+end
+Base.:*(::Derivative{1}, s::DeviceSpline) = DeviceSpline(s.sdist, true)
+function (s::DeviceSpline)(v::AbstractVector{Float64})
+    n, ctx = length(v), s.sdist.ctx
+    out = Vector{Float64}(undef, n)
+    with_device_vector(ctx, collect(v)) do dv
+        with_device_vector(ctx, out) do dout
+            f, df = s.derivative ? (Ptr{Float64}(C_NULL), dout) : (dout, Ptr{Float64}(C_NULL))
+            check(ccall((:vpm_gather_v, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}),
+                        s.sdist.h, C_NULL, dv, n, f, df))
+            check(ccall((:vpm_memcpy_d2h, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), ctx.h, out, dout, n))
+        end
+    end
+    out
+end
+(s::DeviceSpline)(v::Real) = s([Float64(v)])[1]
+
+# compute_f_densities / compute_df_densities / projection_*: src/projections/density.jl:6-52 (unweighted sums, one pass)
+function moments(sdist::DeviceSplineDistribution, vp::AbstractVector{Float64})
+    out5 = Vector{Float64}(undef, 5)
+    with_device_vector(sdist.ctx, collect(vp)) do dv
+        check(ccall((:vpm_moments, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
+                    sdist.h, C_NULL, dv, length(vp), out5))
+    end
+    out5      # Σf, Σvf, Σv²f, Σf', Σvf'
+end
+compute_f_densities(sdist::DeviceSplineDistribution, vp) = (m = moments(sdist, vp); (m[1], m[2], m[3]))
+compute_df_densities(sdist::DeviceSplineDistribution, vp) = (m = moments(sdist, vp); (m[4], m[5]))
+projection_density(sdist::DeviceSplineDistribution, vp; isDerivative = false) = moments(sdist, vp)[isDerivative ? 4 : 1]
+projection_momentum(sdist::DeviceSplineDistribution, vp; isDerivative = false) = moments(sdist, vp)[isDerivative ? 5 : 2]
+projection_energy(sdist::DeviceSplineDistribution, vp) = moments(sdist, vp)[3]
+
+# ϕ(x, Derivative(1)) for a host vector of positions: call sites src/models/vlasov_poisson.jl:27,48,65
+function (ϕ::DevicePotential)(x::AbstractVector{Float64}, ::Derivative{1})
+    n, ctx = length(x), getfield(ϕ, :ctx)
+    coef = ϕ.coefficients
+    out = Vector{Float64}(undef, n)
+    with_device_vector(ctx, collect(x)) do dx
+        with_device_vector(ctx, out) do dout
+            check(ccall((:vpm_gather_x, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Cint, Ptr{Float64}),
+                        getfield(ϕ, :h), coef, dx, n, 1, dout))
+            check(ccall((:vpm_memcpy_d2h, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), ctx.h, out, dout, n))
+        end
+    end
+    out
+end
+(ϕ::DevicePotential)(x::Real, d::Derivative{1}) = ϕ([Float64(x)], d)[1]
+
+# The splitting flows with the reference's callback signature (z, t, z̄, t̄, params) on host matrices
+# (src/models/vlasov_poisson.jl:53-67), for callers that keep GeometricIntegrators in charge of the time loop.
+# Every call moves the state over PCIe: for parity, not for speed (use run! for that).
+const DeviceVPParams = NamedTuple{(:ϕ, :model),<:Tuple{DevicePotential,Any}}
+function s_advection!(z, t, z̄, t̄, params::DeviceVPParams)
+    z[1, :] .= z̄[1, :] .+ (t - t̄) .* z̄[2, :]
+    z[2, :] .= z̄[2, :]
+    z
+end
+function s_acceleration!(z, t, z̄, t̄, params::DeviceVPParams)
+    VlasovMethods.update_potential!(params.model)            # deposits from model.distribution (SURVEY F4)
+    z[1, :] .= z̄[1, :]
+    z[2, :] .= z̄[2, :] .- (t - t̄) .* params.ϕ(z̄[1, :], Derivative(1))
+    z
+end
+# one whole Strang step of the host state through the device (the `e2e` path of bench.py)
+function strang_step!(z::Matrix{Float64}, z̄::Matrix{Float64}, m; selfconsistent::Bool = false)
+    check(ccall((:vpm_vp_strang_step_host, libvpm), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Cint),
+                m.model.potential.h, m.model.distribution.h, z̄, z, m.tstep, m.χ, selfconsistent ? 0 : 1))
+    z
 end
 
 # LB_rhs! / CLB_rhs!: src/models/lenard_bernstein.jl:20-30, lenard_bernstein_conservative.jl:24-36
@@ -181,6 +271,12 @@ function lb_rhs!(v̇::Vector{Float64}, v::Vector{Float64}, params, conservative:
     end
     v̇
 end
+# the reference's own signatures: DiffEq form (v̇, v, params, t) and GeometricIntegrators form (v, t, q, params)
+const DeviceLBParams = NamedTuple{(:ν, :idist, :fdist, :model),<:Tuple{Any,DeviceParticleDistribution,Any,Any}}
+LB_rhs!(v̇, v::AbstractArray{Float64}, params::DeviceLBParams, t) = lb_rhs!(v̇, collect(v), params, false)
+CLB_rhs!(v̇, v::AbstractArray{Float64}, params::DeviceLBParams, t) = lb_rhs!(v̇, collect(v), params, true)
+LB_rhs_GI!(v, t, q::AbstractArray{Float64}, params::DeviceLBParams) = LB_rhs!(v, q, params, t)
+CLB_rhs_GI!(v, t, q::AbstractArray{Float64}, params::DeviceLBParams) = CLB_rhs!(v, q, params, t)
 
 # ---------------------------------------------------------------------------------- whole-run drivers
 # SplittingMethod(model, tspan, tstep) + run!: src/models/vlasov_poisson.jl:73-89, src/methods/splitting.jl:23-52
