@@ -224,7 +224,8 @@ int vpm_h5_close(vpm_h5* f);
  * 0, save_stride, 2 save_stride, ..., nsteps goes to dataset "z" of h5path (save_stride = 1 is the reference's
  * every-step output) and the step numbers of the saved frames times dt to "t".  The state never leaves
  * the device between steps: a frame is snapshotted device-to-device, and its device-to-host copy and file write
- * run on a second stream / the host while the next steps compute.  *frames_out (optional) = frames written. */
+ * run on a second stream / the host while the next steps compute.  *frames_out (optional) = frames written.
+ * Multi-GPU: each rank writes the frames of its own slab, so every rank must pass its own file name. */
 int vpm_vp_run(vpm_xspace* xs, vpm_particles* p, double dt, double chi, int nsteps, int mode, int diag_mode,
                int save_stride, const char* h5path, double* diag_host, int* frames_out);
 /* run!(method::GeometricIntegrator, h5file) (src/methods/geometric_integrator.jl:12-44): RK438 steps as
