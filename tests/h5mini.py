@@ -35,6 +35,7 @@ class Dataset:
         self.raw = None          # compact data
         self.filters = False
         self.messages = []       # (type, size) of every header message, for inspection
+        self.payloads = {}       # message type -> raw payload bytes
         self.chunks = []         # (offsets, address, nbytes) of every chunk found in the B-tree
 
 
@@ -183,6 +184,7 @@ class File:
         ds = Dataset(name)
         for mtype, mflags, body, msize in self._messages(ohdr):
             ds.messages.append((mtype, msize))
+            ds.payloads[mtype] = bytes(self.buf[body:body + msize])
             if mtype == 0x01:
                 ver, rank, flags = self.buf[body], self.buf[body + 1], self.buf[body + 2]
                 if ver != 1:

@@ -42,6 +42,22 @@ def test_reader_is_pinned_on_a_file_written_by_libhdf5():
     assert f._u(free, 8) == 1 and heap["free_head"] + f._u(free + 8, 8) == heap["data_size"]
 
 
+def test_datatype_message_is_byte_identical_to_libhdf5(vpm, tmp_path):
+    """the IEEE-754 little-endian binary64 datatype message of our datasets equals, byte for byte, the one the real
+    library wrote for the float64 dataset of the sample file"""
+    import scipy.io
+    sample = os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data", "testhdf5_7.4_GLNX86.mat")
+    if not os.path.exists(sample):
+        pytest.skip("scipy's MATLAB sample file is not installed")
+    want = h5mini.File(sample).datasets["testdouble"].payloads[0x03]
+    path = tmp_path / "dt.h5"
+    vpm.H5Writer(path).create_dataset("z", (2, 5, 3)).commit().close()
+    ours = h5mini.File(path).datasets["z"]
+    assert ours.payloads[0x03] == want and len(want) == 24
+    # fill value: the library's "default value" encoding (defined, size 0), here in message version 2
+    assert ours.payloads[0x05] == bytes([2, 1, 2, 1, 0, 0, 0, 0])
+
+
 def test_splitting_layout_roundtrip(vpm, tmp_path):
     nd, npart, nt = 2, 7, 5
     rng = np.random.default_rng(1)

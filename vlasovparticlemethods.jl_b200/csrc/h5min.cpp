@@ -263,9 +263,10 @@ int vpm_h5_commit(vpm_h5* f)
         o.u8(0x11); o.u8(0x20); o.u8(63); o.u8(0); o.u32(8);
         o.u16(0); o.u16(64); o.u8(52); o.u8(11); o.u8(0); o.u8(52); o.u32(1023);
         o.zeros(4);
-        // fill value: version 2, early allocation (every chunk exists), written on allocation, undefined value
-        o.u16(0x05); o.u16(8); o.u8(0); o.zeros(3);
-        o.u8(2); o.u8(1); o.u8(0); o.u8(0); o.zeros(4);
+        // fill value: version 2, early allocation (every chunk exists), fill time "if set", default value (defined, size 0)
+        // -- the combination libhdf5 itself writes for a dataset without a user fill value; unwritten frames read as 0
+        o.u16(0x05); o.u16(8); o.u8(1); o.zeros(3);
+        o.u8(2); o.u8(1); o.u8(2); o.u8(1); o.u32(0);
         // data layout: version 3, chunked, B-tree address, chunk dimensions + element size
         o.u16(0x08); o.u16(layout); o.u8(0); o.zeros(3);
         const size_t lstart = o.size();
