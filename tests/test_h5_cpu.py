@@ -181,3 +181,23 @@ def test_writer_fuzz(vpm, tmp_path):
             np.testing.assert_array_equal(f.read(name), a)
 
     run()
+
+
+def test_mapped_multithreaded_writes(vpm, tmp_path, monkeypatch):
+    """opt-in VPM_H5_THREADS > 1: the file is mapped and large pieces are copied by several threads; same bytes"""
+    monkeypatch.setenv("VPM_H5_THREADS", "4")
+    npart, nframes = 1_500_001, 3                           # 24 MB frames: pieces above and below the 1 MiB-per-thread cut
+    rng = np.random.default_rng(3)
+    z = rng.standard_normal((nframes, npart, 2))
+    path = tmp_path / "mapped.h5"
+    with vpm.H5Writer(path).create_dataset("z", (2, npart, nframes)).create_dataset("t", (nframes,)).commit() as w:
+        for n in range(nframes):
+            flat = z[n].ravel()
+            cuts = [0, 7, 7 + (5 << 17), 7 + (5 << 17) + (3 << 18) + 1, flat.size]
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                w.write_frame("z", n, flat[a:b], offset=a)
+            w.write_frame("t", n, [float(n)])
+    f = h5mini.File(path)
+    np.testing.assert_array_equal(f.read("z"), z)
+    np.testing.assert_array_equal(f.read("t"), np.arange(nframes, dtype=float))
+    assert f.eof_addr == os.path.getsize(path)
