@@ -685,6 +685,12 @@ class H5Writer:
     def __exit__(self, *exc):
         self.close()
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 class SplittingMethod:
     """SplittingMethod(model::VlasovPoisson{1,1}, tspan, tstep): Strang splitting (vlasov_poisson.jl:73-89).
