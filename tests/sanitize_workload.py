@@ -2,9 +2,10 @@
 """Small end-to-end workload for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): every particle
 pass variant of the library at sizes that exercise whole ring tiles plus a ragged remainder, both histogram
 fallbacks, the tiled large-grid deposit, the operators and the samplers.  Checks results against the oracle so
-that a sanitizer-clean run is also a correct one.
+that a sanitizer-clean run is also a correct one.  Lives under tests/ because it uses the oracle as its checker
+(only tests/, smoke() and bench.py's CPU arms may); it is a script, not a pytest module.
 
-    compute-sanitizer --tool racecheck python tools/sanitize_workload.py
+    compute-sanitizer --tool racecheck python tests/sanitize_workload.py
 """
 import os
 import sys
@@ -18,7 +19,7 @@ sys.path.insert(0, ROOT)
 def run_h5(vpm, orc, nrm):
     """run! drivers with trajectory output: snapshot passes, copy stream, pinned ring (several pieces), legs of steps"""
     import tempfile
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import h5mini
     n = (9 << 20) // 2 + 77      # frame = 2 n doubles > two 32 MiB ring pieces, with a ragged tail
     bot = vpm.BumpOnTail()
