@@ -80,3 +80,47 @@ def test_argument_errors_without_gpu(lib):
     assert b"bad arguments" in lib.vpm_last_error()
     assert lib.vpm_galerkin_periodic(1.0, 0.0, 4, 16, None, None, None) == -1
     assert lib.vpm_selftest_wrap(0) == -1
+
+
+def test_plotting_forms_of_the_rhs_compose_the_operators(monkeypatch):
+    """LB_rhs / CLB_rhs (the non-mutating "used for plotting" forms, lenard_bernstein.jl:37-44,
+    lenard_bernstein_conservative.jl:53-64) and the *_GI_ argument order are pure compositions of the device
+    operators; checked here with a host-side stand-in for the spline so that the composition itself is pinned
+    without a GPU (the operators are pinned on the GPU in tests/test_gpu_parity.py)."""
+    import vpm_b200 as vpm
+    from vpm_b200 import api
+
+    class FakeSplineDistribution:
+        def evaluate(self, v, coefficients=None, derivative=False):
+            v = np.asarray(v, dtype=float)
+            g = np.exp(-v * v / 2) / np.sqrt(2 * np.pi)
+            return -v * g if derivative else g
+
+    sd = FakeSplineDistribution()
+    fs = vpm.Spline(sd)
+    v = np.linspace(-3, 3, 13)
+    f, df = sd.evaluate(v), sd.evaluate(v, derivative=True)
+
+    class M:
+        pass
+    model = M()
+    model.ent = M()
+    model.ent.dist = sd
+    params = {"nu": 1.7, "idist": None, "fdist": sd, "model": model}
+    np.testing.assert_allclose(vpm.LB_rhs(v, params, fs), -1.7 * (df + v * f), rtol=1e-15)   # = 0 for the unit Maxwellian
+    assert np.abs(vpm.LB_rhs(v, params, fs)).max() < 1e-15
+    m5 = np.array([f.sum(), (v * f).sum(), (v * v * f).sum(), df.sum(), (v * df).sum()])
+    monkeypatch.setattr(api, "_moments", lambda dist, vp: tuple(m5))
+    n, nu, ne, B1, B2 = m5[0], m5[1], m5[2], -m5[3], -m5[4]
+    A1, A2 = (ne * B1 - nu * B2) / (n * ne - nu ** 2), -(nu * B1 - n * B2) / (n * ne - nu ** 2)
+    got = vpm.CLB_rhs(v, params, fs)
+    np.testing.assert_allclose(got, -1.7 * (df + (A1 + A2 * v) * f), rtol=1e-14, atol=1e-16)
+    # the conservative form has no net momentum / energy input over the points the moments were taken on
+    assert abs(got.sum()) < 1e-14 and abs((v * got).sum()) < 1e-14
+    # GI argument order
+    calls = []
+    monkeypatch.setattr(api, "LB_rhs_", lambda vd, q, p, t=0.0: calls.append(("lb", t)) or vd)
+    monkeypatch.setattr(api, "CLB_rhs_", lambda vd, q, p, t=0.0: calls.append(("clb", t)) or vd)
+    out = np.zeros(3)
+    assert vpm.LB_rhs_GI_(out, 0.25, np.ones(3), params) is out and vpm.CLB_rhs_GI_(out, 0.5, np.ones(3), params) is out
+    assert calls == [("lb", 0.25), ("clb", 0.5)]

@@ -641,6 +641,32 @@ def CLB_rhs_(vdot, v, params, t=0.0):
     return _lb_rhs(vdot, v, params, True)
 
 
+def LB_rhs_GI_(v, t, q, params):
+    """LB_rhs_GI!(v, t, q, params): the GeometricIntegrators argument order (lenard_bernstein.jl:32-34)"""
+    return LB_rhs_(v, q, params, t)
+
+
+def CLB_rhs_GI_(v, t, q, params):
+    """CLB_rhs_GI!(v, t, q, params): lenard_bernstein_conservative.jl:38-50"""
+    return CLB_rhs_(v, q, params, t)
+
+
+def LB_rhs(v, params, fs):
+    """LB_rhs(v, params, fs::Spline) -> v̇ for a GIVEN spline ("used for plotting", lenard_bernstein.jl:37-44):
+    no projection, v is any host grid"""
+    v = _f64(v).ravel()
+    dfdv = Derivative(1) * fs
+    return -float(params["nu"]) * (dfdv(v) + v * fs(v))
+
+
+def CLB_rhs(v, params, fs):
+    """CLB_rhs(v, params, fs::Spline) -> v̇ (lenard_bernstein_conservative.jl:53-64): A from the moments of fs over v"""
+    v = _f64(v).ravel()
+    dfdv = Derivative(1) * fs
+    A1, A2 = compute_coefficients(params["model"].ent.dist, params["idist"], v)
+    return -float(params["nu"]) * (dfdv(v) + (A1 + A2 * v) * fs(v))
+
+
 # ------------------------------------------------------------------------------------------------
 # methods (drivers)
 # ------------------------------------------------------------------------------------------------
