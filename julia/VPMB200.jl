@@ -273,8 +273,10 @@ function lb_rhs!(v̇::Vector{Float64}, v::Vector{Float64}, params, conservative:
 end
 # the reference's own signatures: DiffEq form (v̇, v, params, t) and GeometricIntegrators form (v, t, q, params)
 const DeviceLBParams = NamedTuple{(:ν, :idist, :fdist, :model),<:Tuple{Any,DeviceParticleDistribution,Any,Any}}
-LB_rhs!(v̇, v::AbstractArray{Float64}, params::DeviceLBParams, t) = lb_rhs!(v̇, collect(v), params, false)
-CLB_rhs!(v̇, v::AbstractArray{Float64}, params::DeviceLBParams, t) = lb_rhs!(v̇, collect(v), params, true)
+LB_rhs!(v̇, v::AbstractArray{Float64}, params::DeviceLBParams, t) =
+    (v̇ .= lb_rhs!(Vector{Float64}(undef, length(v)), collect(vec(v)), params, false))
+CLB_rhs!(v̇, v::AbstractArray{Float64}, params::DeviceLBParams, t) =
+    (v̇ .= lb_rhs!(Vector{Float64}(undef, length(v)), collect(vec(v)), params, true))
 LB_rhs_GI!(v, t, q::AbstractArray{Float64}, params::DeviceLBParams) = LB_rhs!(v, q, params, t)
 CLB_rhs_GI!(v, t, q::AbstractArray{Float64}, params::DeviceLBParams) = CLB_rhs!(v, q, params, t)
 
