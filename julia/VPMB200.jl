@@ -109,6 +109,24 @@ function Base.getproperty(p::DevicePotential, s::Symbol)
     getfield(p, s)
 end
 
+# Models.  VlasovPoisson{XD,VD,DT,PT<:Potential} (src/models/vlasov_poisson.jl:1-8) constrains its potential to
+# PoissonSolvers' own Potential type and CollisionEntropy builds a SplineDistributionCache that only accepts the host
+# SplineDistribution (src/entropies/collision_entropy.jl:1-10, src/distributions/spline_distribution.jl:41-51), so the
+# device types get their own small holders, reached through more specific methods of the SAME constructor names: the
+# scripts keep writing VlasovPoisson(dist, potential) and CollisionEntropy(sdist).
+struct DeviceVlasovPoisson <: VlasovMethods.VlasovModel
+    distribution::DeviceParticleDistribution
+    potential::DevicePotential
+end
+VlasovMethods.VlasovPoisson(dist::DeviceParticleDistribution, potential::DevicePotential) = DeviceVlasovPoisson(dist, potential)
+
+struct DeviceCollisionEntropy <: VlasovMethods.Entropy
+    dist::DeviceSplineDistribution
+end
+VlasovMethods.CollisionEntropy(dist::DeviceSplineDistribution) = DeviceCollisionEntropy(dist)
+# LenardBernstein(dist, ent; ν) / ConservativeLenardBernstein(dist, ent; ν) take any DistributionFunction{1,1} and any
+# Entropy (src/models/lenard_bernstein.jl:1-9), so they work with the device types as they are.
+
 # every reference sampler gives equal weights: declaring it lets the steppers skip the w[] stream
 set_uniform_weight!(d::DeviceParticleDistribution, w::Real) =
     (check(ccall((:vpm_particles_set_uniform_weight, libvpm), Cint, (Ptr{Cvoid}, Float64), d.h, w)); d)
@@ -144,7 +162,7 @@ update!(potential::DevicePotential) =
     (check(ccall((:vpm_poisson_solve, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), potential.h, C_NULL, C_NULL)); potential)
 
 # update_potential!(model): src/models/vlasov_poisson.jl:12-15
-VlasovMethods.update_potential!(model::VlasovPoisson{1,1,DeviceParticleDistribution,DevicePotential}) =
+VlasovMethods.update_potential!(model::DeviceVlasovPoisson) =
     check(ccall((:vpm_update_potential, libvpm), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
                 model.potential.h, model.distribution.h, C_NULL, C_NULL))
 
@@ -273,12 +291,14 @@ function lb_rhs!(v̇::Vector{Float64}, v::Vector{Float64}, params, conservative:
 end
 # the reference's own signatures: DiffEq form (v̇, v, params, t) and GeometricIntegrators form (v, t, q, params)
 const DeviceLBParams = NamedTuple{(:ν, :idist, :fdist, :model),<:Tuple{Any,DeviceParticleDistribution,Any,Any}}
-LB_rhs!(v̇, v::AbstractArray{Float64}, params::DeviceLBParams, t) =
-    (v̇ .= lb_rhs!(Vector{Float64}(undef, length(v)), collect(vec(v)), params, false))
-CLB_rhs!(v̇, v::AbstractArray{Float64}, params::DeviceLBParams, t) =
-    (v̇ .= lb_rhs!(Vector{Float64}(undef, length(v)), collect(vec(v)), params, true))
-LB_rhs_GI!(v, t, q::AbstractArray{Float64}, params::DeviceLBParams) = LB_rhs!(v, q, params, t)
-CLB_rhs_GI!(v, t, q::AbstractArray{Float64}, params::DeviceLBParams) = CLB_rhs!(v, q, params, t)
+# (AbstractVector{Float64} + the params type make these strictly more specific than the package's own methods,
+#  LB_rhs!(v̇, v::AbstractArray{ST}, params, t) and CLB_rhs!(v̇, v::AbstractVector{ST}, params, t): no ambiguity)
+LB_rhs!(v̇, v::AbstractVector{Float64}, params::DeviceLBParams, t) =
+    (v̇ .= lb_rhs!(Vector{Float64}(undef, length(v)), collect(v), params, false))
+CLB_rhs!(v̇, v::AbstractVector{Float64}, params::DeviceLBParams, t) =
+    (v̇ .= lb_rhs!(Vector{Float64}(undef, length(v)), collect(v), params, true))
+LB_rhs_GI!(v, t, q::AbstractVector{Float64}, params::DeviceLBParams) = LB_rhs!(v, q, params, t)
+CLB_rhs_GI!(v, t, q::AbstractVector{Float64}, params::DeviceLBParams) = CLB_rhs!(v, q, params, t)
 
 # ---------------------------------------------------------------------------------- whole-run drivers
 # SplittingMethod(model, tspan, tstep) + run!: src/models/vlasov_poisson.jl:73-89, src/methods/splitting.jl:23-52
@@ -289,7 +309,7 @@ struct DeviceSplittingMethod{MT}
     field::Symbol          # :frozen == as shipped (SURVEY F4), :selfconsistent == legacy integrate_vp!
     χ::Float64
 end
-SplittingMethod(model::VlasovPoisson{1,1,DeviceParticleDistribution,DevicePotential}, tspan::Tuple, tstep::Real;
+SplittingMethod(model::DeviceVlasovPoisson, tspan::Tuple, tstep::Real;
                 field::Symbol = :frozen, χ::Real = 1.0) = DeviceSplittingMethod(model, Float64.(tspan), Float64(tstep), field, Float64(χ))
 
 # run!(method, h5file) as upstream (src/methods/splitting.jl:23-52): the trajectory goes to dataset "z" of h5file with the
