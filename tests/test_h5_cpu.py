@@ -201,3 +201,18 @@ def test_mapped_multithreaded_writes(vpm, tmp_path, monkeypatch):
     np.testing.assert_array_equal(f.read("z"), z)
     np.testing.assert_array_equal(f.read("t"), np.arange(nframes, dtype=float))
     assert f.eof_addr == os.path.getsize(path)
+
+
+def test_four_level_chunk_tree(vpm, tmp_path):
+    """more than 64^3 frames (e.g. the reference's every-step output of a very long run): a four-level chunk B-tree"""
+    n = 270_000
+    path = tmp_path / "deep.h5"
+    w = vpm.H5Writer(path).create_dataset("t", (n,)).commit()
+    idx = [0, 1, 63, 64, 65, 4095, 4096, 4097, 262143, 262144, 262145, n - 1]     # both sides of every node boundary
+    for i in idx:
+        w.write_frame("t", i, [i + 0.5])
+    w.close()
+    f = h5mini.File(path)
+    a = f.read("t")
+    assert max(x["level"] for x in f.group_info["chunk_nodes"]) == 3 and len(f.datasets["t"].chunks) == n
+    assert all(a[i] == i + 0.5 for i in idx) and a.sum() == sum(i + 0.5 for i in idx)
