@@ -61,6 +61,14 @@ int64_t vpm_launch_count(vpm_ctx* ctx);
  * (8 entries each): 0 = VP particle pass, 1 = VP field kernel, 2 = LB particle pass, 3 = LB field kernel. */
 int vpm_profile(vpm_ctx* ctx, int enable);
 int vpm_profile_get(vpm_ctx* ctx, double* ms_by_kind, int64_t* count_by_kind);
+/* the LB particle passes of the same recording split by pass kind (8 entries each): 0 = deposit only,
+ * 1..4 = RK438 stage passes, 5 = rhs output, 6 = CLB moments, 7 = f / f' gather */
+int vpm_profile_get_lb(vpm_ctx* ctx, double* ms_by_mode, int64_t* count_by_mode);
+/* Binds the calling host thread to the CPUs local to the ctx's GPU (sysfs local_cpulist of its PCI device), so that
+ * pinned buffers allocated afterwards (vpm_host_alloc: first touch) land on the GPU's NUMA node and the host-array
+ * entry points do not cross the socket interconnect.  cpulist_out (optional, cap bytes) receives the list, e.g.
+ * "0-31,64-95".  Returns VPM_ERR_UNSUPPORTED when the topology cannot be read (nothing is changed then). */
+int vpm_ctx_bind_numa(vpm_ctx* ctx, char* cpulist_out, int cap);
 /* pinned host buffers for the host-array entry points */
 int vpm_host_alloc(int64_t bytes, void** out);
 int vpm_host_free(void* p);

@@ -317,7 +317,7 @@ SplittingMethod(model::DeviceVlasovPoisson, tspan::Tuple, tstep::Real;
 # `z = h5read(h5file, "z")` in scripts/vlasov_poisson.jl:38 keeps working.  save_stride = k keeps every k-th step (plus the
 # last); the times of the saved frames are in dataset "t".  run!(method) without a file keeps everything on the device.
 function run!(m::DeviceSplittingMethod, h5file::Union{AbstractString,Nothing} = nothing; save_stride::Integer = 1, diag_mode::Integer = 1)
-    nt = round(Int, (m.tspan[2] - m.tspan[1]) / m.tstep)
+    nt = Int(abs(div(m.tspan[2] - m.tspan[1], m.tstep, RoundUp)))   # GeometricEquations' ntime
     diag = zeros(3, nt + 1)          # rows W, K, M (src/vlasov_poisson.jl:58-67)
     frames = Ref{Cint}(0)
     check(ccall((:vpm_vp_run, libvpm), Cint,
@@ -339,7 +339,7 @@ GeometricIntegrator(model::Union{LenardBernstein{1,1,DeviceParticleDistribution}
 
 # run!(method, h5file): datasets "z" (np, nt+1) chunk (np, 1) and "t" (nt+1) as src/methods/geometric_integrator.jl:21-35
 function run!(m::DeviceRK438, h5file::Union{AbstractString,Nothing} = nothing; save_stride::Integer = 1)
-    nt = round(Int, (m.tspan[2] - m.tspan[1]) / m.tstep)
+    nt = Int(abs(div(m.tspan[2] - m.tspan[1], m.tstep, RoundUp)))   # GeometricEquations' ntime
     diag = zeros(2, nt + 1)          # rows Σv, Σv² (scripts/lenard_bernstein_conservative.jl:49-50)
     frames = Ref{Cint}(0)
     check(ccall((:vpm_lb_run, libvpm), Cint,

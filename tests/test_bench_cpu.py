@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _run(rank, world):
     env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT="29555")
     return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", str(world), "--steps", "2",
-                           "--warmup", "1", "--cpu-sample", "200000"], env=env, capture_output=True, text=True, timeout=300)
+                           "--warmup", "1", "--particles", "200000", "--cpu-sample", "100000"], env=env, capture_output=True, text=True, timeout=300)
 
 
 def test_reference_arm_line():
@@ -28,6 +28,22 @@ def test_reference_arm_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
+    # the arm honours --particles / --steps / --warmup (same config as our arm) and reports the serial rate as well
+    assert d["config"]["particles_per_gpu"] == 200000 and "sample_particles" not in d["config"] and d["warmup"] == 1
+    assert 0 < cb["single_thread_value"] <= 1.5 * cb["value"]
+    for k in ("lb", "clb"):
+        w = d["workloads"][k]
+        assert w["value"] > 1e4 and w["cpu_baseline"]["kind"] == "port" and w["cpu_baseline"]["cores"] >= 1
+
+
+def test_config_is_shared_by_both_arms():
+    """the driver compares the two arms' `config`: both build it with the same function"""
+    sys.path.insert(0, ROOT)
+    import bench
+    class A: particles, workload, load, field, gpus = 1e8, "vp", "bump_on_tail", "selfconsistent", 1
+    cfg = bench.workload_config(A, 1)
+    assert cfg["workload"] == "vp_bump_on_tail_strang_selfconsistent" and cfg["particles_per_gpu"] == 100000000
+    assert cfg["n_basis"] == 16 and cfg["order"] == 4 and cfg["dt"] == 0.1 and "l2" in cfg
 
 
 def test_reference_arm_other_ranks_stay_silent():

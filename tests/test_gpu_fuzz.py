@@ -5,6 +5,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
+EPS = 2.220446049250313e-16
 
 
 def nrm(a, b):
@@ -20,7 +21,7 @@ def vpm():
 
 
 @pytest.mark.parametrize("seed", range(12))
-def test_fuzz_vlasov_poisson(vpm, oracle, seed):
+def test_fuzz_vlasov_poisson(vpm, oracle, perr, seed):
     rng = np.random.default_rng(1000 + seed)
     K = int(rng.integers(2, 7))
     nh = int(rng.choice([3, 5, 8, 16, 17, 31, 64, 129, 300]))
@@ -37,24 +38,32 @@ def test_fuzz_vlasov_poisson(vpm, oracle, seed):
     pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((lo, lo + L), K, nh))
     for field, dm in (("selfconsistent", 2), ("selfconsistent", 1), ("frozen", 0)):
         d = vpm.ParticleDistribution(1, 1, n).set(x, v, w)
-        m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, dt * ns), dt, field=field, chi=chi if field != "frozen" else 1.0)
+        m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(ns, dt), dt, field=field, chi=chi if field != "frozen" else 1.0)
         vpm.run_(m, diag_mode=dm)
         xg, vg, _ = d.get()
         if field == "frozen":
             xo, vo, _ = xs.strang_frozen(x, v, x, w, dt, ns)
         else:
             xo, vo, do, _ = xs.strang_selfconsistent(x, v, w, dt, ns, chi=chi)
-        tag = (seed, K, nh, n, field, dm)
-        assert nrm(xg, xo) < TOL, tag
-        assert np.linalg.norm(vg - vo) < TOL * max(np.linalg.norm(vo), 1e-3 * np.sqrt(n)), tag
+        tag = f"@seed{seed}_K{K}_nh{nh}_n{n}_{field}_dm{dm}"
+        perr("fuzz_strang_x" + tag, nrm(xg, xo), TOL)
+        perr("fuzz_strang_v" + tag, np.linalg.norm(vg - vo) / max(np.linalg.norm(vo), 1e-3 * np.sqrt(n)), TOL)
         if dm == 2:
-            scale = np.abs(do).max(axis=0) + 1e-300
-            assert (np.abs(m.diagnostics - do) / scale).max() < 1e-9, tag
+            # W = phi' S phi / 2 of the solved field: backward-error bound of the solve on this (random) grid;
+            # K relative to itself; M = sum w v relative to sum w |v|
+            M_, S_ = xs.matrices()
+            ev = np.linalg.eigvalsh(S_)
+            kS = ev[-1] / ev[1] if nh > 1 else 1.0
+            scale = np.array([np.abs(do[:, 0]).max(), np.abs(do[:, 1]).max(), np.abs(w * v).sum()]) + 1e-300
+            e = (np.abs(m.diagnostics - do) / scale).max(axis=0)
+            perr("fuzz_W_history" + tag, e[0], max(TOL, 64 * kS * EPS))
+            perr("fuzz_K_history" + tag, e[1], TOL)
+            perr("fuzz_M_history" + tag, e[2], TOL)
 
 
 @pytest.mark.parametrize("ring", ["-1", "0"])   # TMA ring passes (default) / register-prefetch passes
 @pytest.mark.parametrize("seed", range(8))
-def test_fuzz_lenard_bernstein(vpm, oracle, seed, ring, monkeypatch):
+def test_fuzz_lenard_bernstein(vpm, oracle, perr, seed, ring, monkeypatch):
     monkeypatch.setenv("VPM_TUNE_LBTMA", ring)
     rng = np.random.default_rng(2000 + seed)
     K = int(rng.integers(3, 7))
@@ -73,9 +82,11 @@ def test_fuzz_lenard_bernstein(vpm, oracle, seed, ring, monkeypatch):
     sd = vpm.SplineDistribution(1, 1, nk, K, (lo, hi), "Dirichlet")
     d = vpm.ParticleDistribution(1, 1, n).set(np.zeros(n), v, w)
     model = (vpm.ConservativeLenardBernstein if cons else vpm.LenardBernstein)(d, vpm.CollisionEntropy(sd), nu=nu)
-    gi = vpm.GeometricIntegrator(model, (0.0, dt * ns), dt)
+    gi = vpm.GeometricIntegrator(model, vpm.tspan_for(ns, dt), dt)
     vpm.run_(gi)
     vo, do = vs.rk438(v, w, nu, dt, ns, conservative=cons)
-    tag = (seed, K, nk, n, cons)
-    assert nrm(d.get("v"), vo) < 1e-10, tag
-    np.testing.assert_allclose(gi.diagnostics, do, rtol=1e-10, atol=1e-12 * n, err_msg=str(tag))
+    tag = f"@seed{seed}_K{K}_nk{nk}_n{n}_{'clb' if cons else 'lb'}_ring{ring}"
+    tol = max(TOL, 64 * np.linalg.cond(vs.mass()) * EPS)     # random stress grids: backward-error bound of the mass solve
+    perr("fuzz_rk438_v" + tag, nrm(d.get("v"), vo), tol)
+    dscale = np.array([np.abs(v).sum(), (v * v).sum()])
+    perr("fuzz_rk438_moment_history" + tag, (np.abs(gi.diagnostics[:, :2] - do) / dscale).max(), tol)

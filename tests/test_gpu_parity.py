@@ -12,7 +12,15 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-TOL = 1e-12
+TOL = 1e-12      # north star: deposited coefficients, solved field, pushed particles, normwise relative, fp64
+EPS = 2.220446049250313e-16
+
+
+def cond_bound(kappa, c=16.0):
+    """tolerance for the result of a linear solve compared with the oracle's DIFFERENT algorithm (circulant pseudo-inverse
+    vs Cholesky of S + 11'/n; banded vs dense Cholesky): the north star's 1e-12 on the BASELINE grids (kappa <= 60), the
+    backward-error bound c * kappa * eps on the stress grids."""
+    return max(TOL, c * kappa * EPS)
 
 
 def nrm(a, b):
@@ -35,7 +43,7 @@ def make_particles(vpm, x, v, w):
 # ------------------------------------------------------------------------------------- x-space operators
 @pytest.mark.parametrize("K", [2, 3, 4, 5, 6])
 @pytest.mark.parametrize("nh", [16, 11, 100])
-def test_deposit_solve_gather(vpm, oracle, K, nh):
+def test_deposit_solve_gather(vpm, oracle, perr, K, nh):
     rng = np.random.default_rng(100 * K + nh)
     n = 50001
     lo, hi = -1.3, 4.9
@@ -45,22 +53,27 @@ def test_deposit_solve_gather(vpm, oracle, K, nh):
     d = make_particles(vpm, x, v, w)
     pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((lo, hi), K, nh))
     xs = oracle.XSpace(lo, hi, K, nh)
+    M, S = xs.matrices()
+    evS, evM = np.linalg.eigvalsh(S), np.linalg.eigvalsh(M)
+    kS, kM = evS[-1] / evS[1], evM[-1] / evM[0]          # evS[0] = 0: the constant mode (zero-mean gauge)
+    base = nh == 16 and K in (3, 4)                      # the x-grids of BASELINE configs 1, 2, 5
+    tol_s, tol_m = (TOL if base else cond_bound(kS)), (TOL if base else cond_bound(kM))
+    tag = f"@K{K}_nh{nh}"
     vpm.projection_(pot, d)
     rhs_o = xs.deposit(x, w)
-    assert nrm(pot.rhs, rhs_o) < TOL
+    perr("x_deposit" + tag, nrm(pot.rhs, rhs_o), TOL)
     assert abs(pot.rhs.sum() - w.sum()) < 1e-13          # KAT-1 partition of unity
     vpm.update_(pot)
     phi_o = xs.poisson_solve(rhs_o)
-    assert nrm(pot.coefficients, phi_o) < 1e-11
+    perr("x_solved_field" + tag, nrm(pot.coefficients, phi_o), tol_s)
     assert abs(pot.coefficients.sum()) < 1e-12 * np.abs(phi_o).sum() + 1e-18
     # solve from a given rhs, gathers, energy, mass solve
-    assert nrm(pot.solve(rhs_o), phi_o) < 1e-11
+    perr("x_solve_given_rhs" + tag, nrm(pot.solve(rhs_o), phi_o), tol_s)
     xt = rng.uniform(lo - 10, hi + 10, 4097)
-    assert nrm(pot.evaluate(xt, 1, phi_o), xs.eval(phi_o, xt, 1)) < 1e-11
-    assert nrm(pot.evaluate(xt, 0, phi_o), xs.eval(phi_o, xt, 0)) < 1e-11
-    assert abs(pot.energy(phi_o) - xs.field_energy(phi_o)) < 1e-11 * abs(xs.field_energy(phi_o))
-    assert nrm(pot.mass_solve(rhs_o), xs.mass_solve(rhs_o)) < 1e-11
-    M, S = xs.matrices()
+    perr("x_gather_dphi" + tag, nrm(pot.evaluate(xt, 1, phi_o), xs.eval(phi_o, xt, 1)), TOL)
+    perr("x_gather_phi" + tag, nrm(pot.evaluate(xt, 0, phi_o), xs.eval(phi_o, xt, 0)), TOL)
+    perr("x_field_energy" + tag, abs(pot.energy(phi_o) - xs.field_energy(phi_o)) / abs(xs.field_energy(phi_o)), TOL)
+    perr("x_mass_solve" + tag, nrm(pot.mass_solve(rhs_o), xs.mass_solve(rhs_o)), tol_m)
     ms, ss = pot.stencils()
     for dd in range(-(K - 1), K):
         if nh > 2 * K:
@@ -90,8 +103,7 @@ def test_deposit_edge_cases(vpm, oracle):
         assert err <= 1e-13 * max(1.0, np.abs(ref).max()), (name, err)
 
 
-def test_push_operators(vpm, oracle):
-    rng = np.random.default_rng(7)
+def test_push_operators(vpm, oracle, perr):
     n, K, nh, L = 30000, 4, 16, 2 * np.pi / 0.3
     x, v, w = oracle.sample_bump_on_tail(n)
     d = make_particles(vpm, x, v, w)
@@ -99,12 +111,12 @@ def test_push_operators(vpm, oracle):
     xs = oracle.XSpace(0.0, L, K, nh)
     vpm.s_advection_(d, pot, 0.37)
     xo = oracle.push_drift(x, v, 0.37)
-    assert nrm(d.get("x"), xo) < TOL
+    perr("drift_x", nrm(d.get("x"), xo), TOL)
     vpm.s_acceleration_(d, pot, 0.21)              # update_potential! + kick
     phi = xs.poisson_solve(xs.deposit(xo, w))
     vo = xs.push_kick(phi, xo, v, 0.21)
-    assert nrm(d.get("v"), vo) < TOL
-    assert nrm(pot.coefficients, phi) < 1e-11
+    perr("kick_v", nrm(d.get("v"), vo), TOL)
+    perr("kick_solved_field", nrm(pot.coefficients, phi), TOL)
     # AoS round trip (Julia 3 x N and 2 x N matrices)
     z3 = np.vstack([x, v, w])
     d.upload_aos(z3)
@@ -113,40 +125,57 @@ def test_push_operators(vpm, oracle):
 
 
 # ------------------------------------------------------------------------------------- Strang steppers
+def diag_err(dg, ref, w, v):
+    """W, K relative to their own maximum; M = sum w v relative to sum w |v| (it cancels to ~0 for symmetric loads)"""
+    scale = np.array([np.abs(ref[:, 0]).max(), np.abs(ref[:, 1]).max(), np.abs(w * v).sum()]) + 1e-300
+    return (np.abs(dg - ref) / scale).max(axis=0)
+
+
 @pytest.mark.parametrize("name", ["vp_k4_n16", "vp_k3_n16_cfg1", "vp_k5_n11_chi"])
-def test_strang_golden(vpm, name):
+def test_strang_golden(vpm, perr, name):
+    """tests/golden/*.npz are ORACLE outputs (tests/golden/make_golden.py), not reference outputs: parity unpinned"""
     g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     K, nh, L, dt, ns, chi = int(g["K"]), int(g["nh"]), float(g["L"]), float(g["dt"]), int(g["nsteps"]), float(g["chi"])
     pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), K, nh))
+    tag = "@" + name
     # self-consistent, exact legacy diagnostics
     d = make_particles(vpm, g["x"], g["v"], g["w"])
-    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, dt * ns), dt, field="selfconsistent", chi=chi)
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(ns, dt), dt, field="selfconsistent", chi=chi)
     vpm.run_(m, diag_mode=2)
     x1, v1, _ = d.get()
-    assert nrm(x1, g["x1"]) < TOL and nrm(v1, g["v1"]) < TOL
-    assert np.abs(m.diagnostics - g["diag"]).max() < 1e-11 * np.abs(g["diag"]).max()
+    perr("strang_x" + tag, nrm(x1, g["x1"]), TOL)
+    perr("strang_v" + tag, nrm(v1, g["v1"]), TOL)
+    eW, eK, eM = diag_err(m.diagnostics, g["diag"], g["w"], g["v"])
+    perr("strang_W_history" + tag, eW, TOL)
+    perr("strang_K_history" + tag, eK, TOL)
+    perr("strang_M_history" + tag, eM, TOL)
     # fused one-pass-per-step path (diag_mode 1 and 0) gives the same particles
     for dm in (1, 0):
         d2 = make_particles(vpm, g["x"], g["v"], g["w"])
-        m2 = vpm.SplittingMethod(vpm.VlasovPoisson(d2, pot), (0.0, dt * ns), dt, field="selfconsistent", chi=chi)
+        m2 = vpm.SplittingMethod(vpm.VlasovPoisson(d2, pot), vpm.tspan_for(ns, dt), dt, field="selfconsistent", chi=chi)
         vpm.run_(m2, diag_mode=dm)
         x2, v2, _ = d2.get()
-        assert nrm(x2, g["x1"]) < TOL and nrm(v2, g["v1"]) < TOL
+        perr(f"strang_x_fused_dm{dm}" + tag, nrm(x2, g["x1"]), TOL)
+        perr(f"strang_v_fused_dm{dm}" + tag, nrm(v2, g["v1"]), TOL)
         if dm == 1:
-            np.testing.assert_allclose(m2.diagnostics[:, 1:], g["diag"][:, 1:], rtol=1e-11)   # K, M exact
-            np.testing.assert_allclose(m2.diagnostics[0, 0], g["diag"][0, 0], rtol=1e-10)     # W(0) exact
+            _, eK, eM = diag_err(m2.diagnostics, g["diag"], g["w"], g["v"])
+            perr("strang_K_history_fused" + tag, eK, TOL)                                       # K, M exact
+            perr("strang_M_history_fused" + tag, eM, TOL)
+            perr("strang_W0_fused" + tag, abs(m2.diagnostics[0, 0] - g["diag"][0, 0]) / g["diag"][0, 0], TOL)   # W(0) exact
             assert np.all(m2.diagnostics[:, 0] > 0)
     # frozen field == the shipped SplittingMethod behaviour (SURVEY F4)
     d3 = make_particles(vpm, g["x"], g["v"], g["w"])
-    m3 = vpm.SplittingMethod(vpm.VlasovPoisson(d3, pot), (0.0, dt * ns), dt, field="frozen")
+    m3 = vpm.SplittingMethod(vpm.VlasovPoisson(d3, pot), vpm.tspan_for(ns, dt), dt, field="frozen")
     vpm.run_(m3)
     x3, v3, _ = d3.get()
-    assert nrm(x3, g["xf"]) < TOL and nrm(v3, g["vf"]) < TOL
-    assert nrm(pot.coefficients, g["phif"]) < 1e-11
+    perr("frozen_x" + tag, nrm(x3, g["xf"]), TOL)
+    perr("frozen_v" + tag, nrm(v3, g["vf"]), TOL)
+    perr("frozen_solved_field" + tag, nrm(pot.coefficients, g["phif"]), TOL)
 
 
-def test_strang_vs_oracle_long(vpm, oracle):
-    """40 steps, N=2e5: error growth stays far below the tolerance; bitwise run-to-run determinism."""
+def test_strang_vs_oracle_long(vpm, oracle, perr):
+    """40 steps, N=2e5 (the largest direct oracle comparison; beyond it parity is property-based, see
+    test_large_properties): error growth stays far below the tolerance; bitwise run-to-run determinism."""
     n, K, nh, L = 200001, 4, 16, 2 * np.pi / 0.3
     x, v, w = oracle.sample_bump_on_tail(n)
     oracle.set_threads(min(8, oracle.max_threads()))
@@ -160,8 +189,11 @@ def test_strang_vs_oracle_long(vpm, oracle):
         m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 4.0), 0.1, field="selfconsistent")
         vpm.run_(m, diag_mode=1)
         res.append(d.get() + (m.diagnostics,))
-    assert nrm(res[0][0], xo) < TOL and nrm(res[0][1], vo) < TOL
-    np.testing.assert_allclose(res[0][3][:, 1:], do[:, 1:], rtol=1e-10)
+    perr("strang40_x", nrm(res[0][0], xo), TOL)
+    perr("strang40_v", nrm(res[0][1], vo), TOL)
+    _, eK, eM = diag_err(res[0][3], do, w, v)
+    perr("strang40_K_history", eK, TOL)
+    perr("strang40_M_history", eM, TOL)
     for a, b in zip(res[0], res[1]):
         np.testing.assert_array_equal(a, b)     # fixed-order reductions: bitwise reproducible
 
@@ -205,9 +237,20 @@ def test_large_properties(vpm):
 
 
 # ------------------------------------------------------------------------------------- v-space / LB
+def clb_coefficient_scale(n, nu, ne, f, df, v):
+    """error scale of A1, A2 (lenard_bernstein_conservative.jl:11-21): each is a quotient whose numerator is a difference
+    of products of moment sums; B1 = -sum f' cancels to ~0 for symmetric loads, so the error of the numerator is judged
+    relative to the sums of absolute terms (SURVEY 8a note), not relative to A itself"""
+    s_df, s_vdf = np.abs(df).sum(), np.abs(v * df).sum()
+    det = abs(n * ne - nu * nu)
+    return np.array([(abs(ne) * s_df + abs(nu) * s_vdf) / det, (abs(nu) * s_df + abs(n) * s_vdf) / det])
+
+
 @pytest.mark.parametrize("ring", ["-1", "0"])   # TMA ring passes (default) / register-prefetch passes
 @pytest.mark.parametrize("name", ["lb_k4_n41", "lb_k5_n12"])
-def test_lb_golden(vpm, name, ring, monkeypatch):
+def test_lb_golden(vpm, perr, name, ring, monkeypatch):
+    """tests/golden/*.npz are ORACLE outputs (tests/golden/make_golden.py), not reference outputs: parity unpinned.
+    lb_k4_n41 is the v-grid of BASELINE configs 3, 4 (north-star tolerance); lb_k5_n12 is a stress grid."""
     monkeypatch.setenv("VPM_TUNE_LBTMA", ring)
     g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     K, nk, dt, ns, nu = int(g["K"]), int(g["nknots"]), float(g["dt"]), int(g["nsteps"]), float(g["nu"])
@@ -215,19 +258,21 @@ def test_lb_golden(vpm, name, ring, monkeypatch):
     sd = vpm.SplineDistribution(1, 1, nk, K, (-10.0, 10.0), "Dirichlet")
     assert len(sd) == nk + K - 4
     np.testing.assert_allclose(sd.mass_matrix, g["mass"], atol=1e-14)
+    tol_c = TOL if name == "lb_k4_n41" else cond_bound(np.linalg.cond(g["mass"]))
+    tag = f"@{name}_ring{ring}"
     d = make_particles(vpm, np.zeros(v.size), v, w)
     fs = vpm.projection(v, d, sd)
-    assert nrm(sd.rhs, g["rhs"]) < TOL
-    assert nrm(fs.coefficients, g["coef"]) < 1e-11
-    assert nrm(sd.mass_solve(g["rhs"]), g["coef"]) < 1e-11
-    assert nrm(fs(v), g["f"]) < 1e-11
-    assert nrm((vpm.Derivative(1) * fs)(v), g["df"]) < 1e-11
+    perr("v_deposit" + tag, nrm(sd.rhs, g["rhs"]), TOL)
+    perr("v_spline_coefficients" + tag, nrm(fs.coefficients, g["coef"]), tol_c)
+    perr("v_mass_solve" + tag, nrm(sd.mass_solve(g["rhs"]), g["coef"]), tol_c)
+    perr("v_gather_f" + tag, nrm(fs(v), g["f"]), tol_c)
+    perr("v_gather_df" + tag, nrm((vpm.Derivative(1) * fs)(v), g["df"]), tol_c)
     # f, f' of boundary cells, end points and out-of-domain particles individually
     np.testing.assert_allclose(fs(v[:6]), g["f"][:6], atol=1e-13 * np.abs(g["f"]).max())
     m5 = np.array(vpm.compute_f_densities(sd, v) + vpm.compute_df_densities(sd, v))
     scale = np.array([np.abs(g["f"]).sum(), np.abs(v * g["f"]).sum(), np.abs(v * v * g["f"]).sum(),
                       np.abs(g["df"]).sum(), np.abs(v * g["df"]).sum()])
-    assert np.all(np.abs(m5 - g["m5"]) < 1e-12 * scale)   # judged relative to sum |.| (SURVEY 8a note)
+    perr("v_moments" + tag, (np.abs(m5 - g["m5"]) / scale).max(), tol_c)   # judged relative to sum |.| (SURVEY 8a note)
     params = {"nu": nu, "idist": d, "fdist": sd}
     ent = vpm.CollisionEntropy(sd)
     for cons, key in ((False, "vdot_lb"), (True, "vdot_clb")):
@@ -235,21 +280,23 @@ def test_lb_golden(vpm, name, ring, monkeypatch):
         params["model"] = model
         vdot = np.zeros(v.size)
         (vpm.CLB_rhs_ if cons else vpm.LB_rhs_)(vdot, v, params, 0.0)
-        assert nrm(vdot, g[key]) < 1e-10, (cons, nrm(vdot, g[key]))
-    A = vpm.compute_coefficients(sd, d, v)
-    np.testing.assert_allclose(A, g["A"], rtol=1e-8, atol=1e-10)
+        perr(("clb" if cons else "lb") + "_rhs_vdot" + tag, nrm(vdot, g[key]), tol_c)
+    A = np.array(vpm.compute_coefficients(sd, d, v))
+    perr("clb_A1_A2" + tag, (np.abs(A - g["A"]) / clb_coefficient_scale(g["m5"][0], g["m5"][1], g["m5"][2], g["f"], g["df"], v)).max(), tol_c)
     # RK438 steppers
     for cons, kv, kd in ((False, "v_lb", "d_lb"), (True, "v_clb", "d_clb")):
         d2 = make_particles(vpm, np.zeros(v.size), v, w)
         model = (vpm.ConservativeLenardBernstein if cons else vpm.LenardBernstein)(d2, ent, nu=nu)
-        gi = vpm.GeometricIntegrator(model, (0.0, dt * ns), dt)
+        gi = vpm.GeometricIntegrator(model, vpm.tspan_for(ns, dt), dt)
         vpm.run_(gi)
-        assert nrm(d2.get("v"), g[kv]) < 1e-11, (cons, nrm(d2.get("v"), g[kv]))
-        np.testing.assert_allclose(gi.diagnostics, g[kd], rtol=1e-11)
+        mdl = "clb" if cons else "lb"
+        perr(mdl + "_rk438_v" + tag, nrm(d2.get("v"), g[kv]), tol_c)
+        dscale = np.array([np.abs(v).sum(), (v * v).sum()])          # sum v cancels: relative to sum |v|
+        perr(mdl + "_rk438_moment_history" + tag, (np.abs(gi.diagnostics[:, :2] - g[kd]) / dscale).max(), TOL)
 
 
 @pytest.mark.parametrize("n", [0, 1, 2, 511, 512, 513, 1024, 1537])
-def test_lb_edge_sizes(vpm, oracle, n):
+def test_lb_edge_sizes(vpm, oracle, perr, n):
     """Empty and ragged inputs around the 512-particle tile of the ring passes (whole tiles through the TMA ring,
     the remainder through plain loads), both models, against the oracle."""
     rng = np.random.default_rng(100 + n)
@@ -267,12 +314,14 @@ def test_lb_edge_sizes(vpm, oracle, n):
         gi = vpm.GeometricIntegrator(model, (0.0, 0.04), 0.02)
         vpm.run_(gi)
         vo, do = vs.rk438(v, w, 0.9, 0.02, 2, conservative=cons)
-        assert gi.diagnostics.shape == (3, 2)
+        assert gi.diagnostics.shape[0] == 3
         if n == 0:
             assert np.all(gi.diagnostics == 0.0)
             continue
-        assert np.abs(d.get("v") - vo).max() <= 1e-11 * max(1.0, np.abs(vo).max()), (n, cons)
-        np.testing.assert_allclose(gi.diagnostics, do, rtol=1e-10, atol=1e-12)
+        mdl = "clb" if cons else "lb"
+        perr(f"{mdl}_rk438_v_ragged@n{n}", np.abs(d.get("v") - vo).max() / max(1.0, np.abs(vo).max()), TOL)
+        dscale = np.array([np.abs(v).sum(), (v * v).sum()])
+        perr(f"{mdl}_rk438_moment_history_ragged@n{n}", (np.abs(gi.diagnostics[:, :2] - do) / dscale).max(), TOL)
 
 
 def test_lb_large_properties(vpm, monkeypatch):
@@ -362,7 +411,7 @@ def test_errors_are_reported(vpm):
 
 # ------------------------------------------------------------------------------------- large grids
 @pytest.mark.parametrize("hm", ["1", "2", "3"])
-def test_histogram_fallback_modes(vpm, oracle, hm, monkeypatch):
+def test_histogram_fallback_modes(vpm, oracle, perr, hm, monkeypatch):
     """Grids too large for per-thread histogram copies fall back to per-warp / per-CTA copies with
     shared-memory atomics; VPM_TUNE_HM forces those code paths on a small grid."""
     monkeypatch.setenv("VPM_TUNE_HM", hm)
@@ -370,21 +419,22 @@ def test_histogram_fallback_modes(vpm, oracle, hm, monkeypatch):
     K, nh, L, dt, ns = int(g["K"]), int(g["nh"]), float(g["L"]), float(g["dt"]), int(g["nsteps"])
     pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), K, nh))
     d = make_particles(vpm, g["x"], g["v"], g["w"])
-    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, dt * ns), dt, field="selfconsistent")
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(ns, dt), dt, field="selfconsistent")
     vpm.run_(m, diag_mode=2)
     x1, v1, _ = d.get()
-    assert nrm(x1, g["x1"]) < TOL and nrm(v1, g["v1"]) < TOL
-    assert np.abs(m.diagnostics - g["diag"]).max() < 1e-11 * np.abs(g["diag"]).max()
+    perr(f"strang_x@hm{hm}", nrm(x1, g["x1"]), TOL)
+    perr(f"strang_v@hm{hm}", nrm(v1, g["v1"]), TOL)
+    perr(f"strang_WKM_history@hm{hm}", diag_err(m.diagnostics, g["diag"], g["w"], g["v"]).max(), TOL)
     gl = np.load(os.path.join(ROOT, "tests", "golden", "lb_k4_n41.npz"))
     sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
     d2 = make_particles(vpm, np.zeros(gl["v"].size), gl["v"], gl["w"])
     gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d2, vpm.CollisionEntropy(sd), nu=float(gl["nu"])),
-                                 (0.0, float(gl["dt"]) * int(gl["nsteps"])), float(gl["dt"]))
+                                 vpm.tspan_for(int(gl["nsteps"]), float(gl["dt"])), float(gl["dt"]))
     vpm.run_(gi)
-    assert nrm(d2.get("v"), gl["v_clb"]) < 1e-11
+    perr(f"clb_rk438_v@hm{hm}", nrm(d2.get("v"), gl["v_clb"]), TOL)
 
 
-def test_large_grids_natural(vpm, oracle):
+def test_large_grids_natural(vpm, oracle, perr):
     rng = np.random.default_rng(3)
     n, K, nh, lo, hi = 60000, 4, 400, 0.0, 50.0       # 403 bins: per-warp copies
     x, v, w = rng.uniform(lo - 100, hi + 100, n), rng.standard_normal(n), rng.uniform(0.5, 1.5, n) / n
@@ -395,7 +445,8 @@ def test_large_grids_natural(vpm, oracle):
     vpm.run_(m, diag_mode=0)
     xo, vo, _, _ = xs.strang_selfconsistent(x, v, w, 0.1, 2, diag=False)
     xg, vg, _ = d.get()
-    assert nrm(xg, xo) < TOL and nrm(vg, vo) < TOL
+    perr("strang_x@nh400", nrm(xg, xo), TOL)
+    perr("strang_v@nh400", nrm(vg, vo), TOL)
     # v-space with 300 breakpoints
     vs = oracle.VSpace(-10.0, 10.0, 300, 4)
     sd = vpm.SplineDistribution(1, 1, 300, 4, (-10.0, 10.0), "Dirichlet")
@@ -405,7 +456,7 @@ def test_large_grids_natural(vpm, oracle):
     model = vpm.ConservativeLenardBernstein(d2, vpm.CollisionEntropy(sd), nu=1.0)
     vpm.CLB_rhs_(vdot, vv, {"nu": 1.0, "idist": d2, "fdist": sd, "model": model}, 0.0)
     ref, _, _ = vs.lb_rhs(vv, w, 1.0, True)
-    assert nrm(vdot, ref) < 1e-9
+    perr("clb_rhs_vdot@nknots300", nrm(vdot, ref), cond_bound(np.linalg.cond(vs.mass()), 64.0))
     # beyond the shared-memory capacity the library refuses instead of falling back
     with pytest.raises(vpm.VpmError):
         big = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, 1.0), 4, 20000))

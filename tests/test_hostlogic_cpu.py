@@ -124,3 +124,15 @@ def test_plotting_forms_of_the_rhs_compose_the_operators(monkeypatch):
     out = np.zeros(3)
     assert vpm.LB_rhs_GI_(out, 0.25, np.ones(3), params) is out and vpm.CLB_rhs_GI_(out, 0.5, np.ones(3), params) is out
     assert calls == [("lb", 0.25), ("clb", 0.5)]
+
+
+def test_ntime_is_a_ceiling_like_upstream():
+    """GeometricEquations: ntime = Int(abs(div(tend - tbegin, tstep, RoundUp))) -- a tspan that is not a multiple of
+    tstep gets the extra (partial-interval) step, and so does floating-point noise above an integer quotient"""
+    from vpm_b200 import api
+    assert api._ntime((0.0, 20.0), 0.1) == 200 and api._ntime((0.0, 500.0), 1e-2) == 50000 and api._ntime((0.0, 10.0), 0.1) == 100
+    assert api._ntime((0.0, 1.05), 0.1) == 11                 # non-divisible: rounded UP (round() gave 10)
+    assert api._ntime((0.0, 0.9), 0.3) == 4                   # 0.9 / 0.3 = 3.0000000000000004: as upstream
+    assert api._ntime((1.0, 0.0), 0.25) == 4
+    for ns, dt in ((3, 0.1), (7, 0.013), (1, 0.29), (4, 0.05), (0, 0.1), (200, 0.1)):
+        assert api._ntime(api.tspan_for(ns, dt), dt) == ns

@@ -53,7 +53,7 @@ def run_vp(vpm, n, kappa, eps, alpha, sigma, v0, nh, order, dt, nsteps, seed=0x5
     d = vpm.ParticleDistribution(1, 1, n)
     vpm.initialize_(d, vpm.BumpOnTail(eps=eps, kappa=kappa, alpha=alpha, sigma=sigma, v0=v0), seed=seed)
     pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), order, nh))
-    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, dt * nsteps), dt, field="selfconsistent")
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(nsteps, dt), dt, field="selfconsistent")
     vpm.run_(m, diag_mode=1)
     return m.diagnostics
 

@@ -28,6 +28,8 @@ SIGNATURES = {
     "vpm_launch_count": (_i64, [_vp]),
     "vpm_profile": (_i32, [_vp, _i32]),
     "vpm_profile_get": (_i32, [_vp, _vp, _vp]),
+    "vpm_profile_get_lb": (_i32, [_vp, _vp, _vp]),
+    "vpm_ctx_bind_numa": (_i32, [_vp, C.c_char_p, _i32]),
     "vpm_host_alloc": (_i32, [_i64, C.POINTER(_vp)]),
     "vpm_host_free": (_i32, [_vp]),
     "vpm_dev_alloc": (_i32, [_vp, _i64, C.POINTER(_vp)]),

@@ -671,7 +671,18 @@ def CLB_rhs(v, params, fs):
 # methods (drivers)
 # ------------------------------------------------------------------------------------------------
 def _ntime(tspan, tstep):
-    return int(round((tspan[1] - tspan[0]) / tstep))
+    """number of steps of a tspan: GeometricEquations' ntime = Int(abs(div(tend - tbegin, tstep, RoundUp))) -- a ceiling of
+    the floating-point quotient (0.9 / 0.3 = 3.0000000000000004 gives 4 steps, as upstream; tspan_for avoids that)"""
+    return int(abs(math.ceil((tspan[1] - tspan[0]) / tstep)))
+
+
+def tspan_for(nsteps, tstep, t0=0.0):
+    """a tspan (t0, t1) for which ntime is exactly nsteps (t0 + nsteps * tstep can round to a quotient just above
+    nsteps, which the upstream ceiling turns into one more step)"""
+    t1 = t0 + nsteps * tstep
+    while nsteps > 0 and _ntime((t0, t1), tstep) > nsteps:
+        t1 = math.nextafter(t1, t0)
+    return (t0, t1)
 
 
 class H5Writer:

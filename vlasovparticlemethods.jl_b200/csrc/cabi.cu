@@ -1,6 +1,7 @@
 // extern "C" surface of libvpm_b200.so (declared in include/vpm_b200.h): contexts, particle storage,
 // spaces, operator-level entry points and the whole-step device-resident steppers.
 #include <dlfcn.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <cmath>
@@ -127,7 +128,7 @@ int comm_allreduce(vpm_ctx* ctx, double* buf, size_t count)
     return VPM_OK;
 }
 
-void prof_begin(vpm_ctx* ctx, int kind)
+void prof_begin(vpm_ctx* ctx, int kind, int sub)
 {
     if (!ctx->profile) return;
     cudaEvent_t e0, e1;
@@ -136,6 +137,7 @@ void prof_begin(vpm_ctx* ctx, int kind)
     ctx->prof_events.push_back(e0);
     ctx->prof_events.push_back(e1);
     ctx->prof_kinds.push_back(kind);
+    ctx->prof_subs.push_back(sub);
     cudaEventRecord(e0, ctx->stream);
 }
 
@@ -174,6 +176,17 @@ using namespace vpm;
     do {                       \
         if (!(cond)) return fail(VPM_ERR_INVALID, msg); \
     } while (0)
+
+// A peer that never showed up in a fused all-reduce leaves its sequence number in the local mailbox's error word
+// (p2p.cuh).  Called by the synchronous steppers after their stream synchronisation.
+static int p2p_status(vpm_ctx* ctx)
+{
+    if (!ctx->p2p_local || ctx->p2p.nranks <= 1) return VPM_OK;
+    unsigned long long e = 0;
+    VPM_CUDA(cudaMemcpy(&e, &ctx->p2p_local->error, sizeof(e), cudaMemcpyDeviceToHost));
+    if (e) return fail(VPM_ERR_COMM, "peer-memory all-reduce timed out waiting for a rank (sequence " + std::to_string(e) + "); results are invalid");
+    return VPM_OK;
+}
 
 extern "C" {
 
@@ -256,6 +269,7 @@ int vpm_profile(vpm_ctx* ctx, int enable)
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     ctx->prof_events.clear();
     ctx->prof_kinds.clear();
+    ctx->prof_subs.clear();
     ctx->profile = enable != 0;
     return VPM_OK;
 }
@@ -270,6 +284,66 @@ int vpm_profile_get(vpm_ctx* ctx, double* ms_by_kind, int64_t* count_by_kind)
         VPM_CUDA(cudaEventElapsedTime(&ms, ctx->prof_events[2 * i], ctx->prof_events[2 * i + 1]));
         ms_by_kind[ctx->prof_kinds[i]] += ms;
         count_by_kind[ctx->prof_kinds[i]] += 1;
+    }
+    return VPM_OK;
+}
+
+int vpm_profile_get_lb(vpm_ctx* ctx, double* ms_by_mode, int64_t* count_by_mode)
+{
+    VPM_REQUIRE(ctx && ms_by_mode && count_by_mode, "vpm_profile_get_lb: NULL argument");
+    VPM_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 8; k++) { ms_by_mode[k] = 0.0; count_by_mode[k] = 0; }
+    for (size_t i = 0; i < ctx->prof_kinds.size(); i++) {
+        if (ctx->prof_kinds[i] != PROF_LB_PASS) continue;
+        const int m = ctx->prof_subs[i] & 7;
+        float ms = 0.f;
+        VPM_CUDA(cudaEventElapsedTime(&ms, ctx->prof_events[2 * i], ctx->prof_events[2 * i + 1]));
+        ms_by_mode[m] += ms;
+        count_by_mode[m] += 1;
+    }
+    return VPM_OK;
+}
+
+int vpm_ctx_bind_numa(vpm_ctx* ctx, char* cpulist_out, int cap)
+{
+    VPM_REQUIRE(ctx, "vpm_ctx_bind_numa: ctx is NULL");
+    if (cpulist_out && cap > 0) cpulist_out[0] = 0;
+    char bus[32] = {0};
+    VPM_CUDA(cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), ctx->device));
+    for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return fail(VPM_ERR_UNSUPPORTED, "vpm_ctx_bind_numa: cannot read " + path);
+    char buf[1024] = {0};
+    const bool got = fgets(buf, sizeof(buf), f) != nullptr;
+    fclose(f);
+    if (!got) return fail(VPM_ERR_UNSUPPORTED, "vpm_ctx_bind_numa: empty " + path);
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int ncpu = 0;
+    for (const char* c = buf; *c && *c != '\n';) {   // "a-b,c,d-e"
+        char* end = nullptr;
+        const long a = strtol(c, &end, 10);
+        if (end == c) break;
+        long b = a;
+        c = end;
+        if (*c == '-') {
+            b = strtol(c + 1, &end, 10);
+            c = end;
+        }
+        for (long k = a; k <= b && k < CPU_SETSIZE; k++) {
+            CPU_SET((int)k, &set);
+            ncpu++;
+        }
+        if (*c == ',') c++;
+    }
+    if (ncpu == 0) return fail(VPM_ERR_UNSUPPORTED, "vpm_ctx_bind_numa: no CPUs listed in " + path);
+    if (sched_setaffinity(0, sizeof(set), &set) != 0) return fail(VPM_ERR_UNSUPPORTED, "vpm_ctx_bind_numa: sched_setaffinity failed");
+    if (cpulist_out && cap > 0) {
+        size_t len = strcspn(buf, "\n");
+        if (len >= (size_t)cap) len = (size_t)cap - 1;
+        memcpy(cpulist_out, buf, len);
+        cpulist_out[len] = 0;
     }
     return VPM_OK;
 }
@@ -366,7 +440,10 @@ int vpm_particles_ptrs(vpm_particles* p, double** x, double** v, double** w)
     VPM_REQUIRE(p, "vpm_particles_ptrs: p is NULL");
     if (x) *x = p->x;
     if (v) *v = p->v;
-    if (w) *w = p->w;
+    if (w) {
+        *w = p->w;
+        p->uw = false;   // the caller may rewrite the weights through this pointer: the uniform-weight declaration ends here
+    }
     return VPM_OK;
 }
 
@@ -668,7 +745,7 @@ int vpm_xspace_get(vpm_xspace* xs, double* rhs_host, double* phi_host)
 // Strang stepping on SoA arrays (x, v evolve; w and the frozen-field deposit positions are inputs)
 static int vp_steps(vpm_xspace* xs, double* x, double* v, const double* w, int64_t n, const double* xdep,
                     const double* wdep, int64_t ndep, double dt, double chi, int nsteps, int mode, int diag_mode,
-                    bool uw = false, double wu = 0.0, bool keep_field = false)
+                    bool uw = false, double wu = 0.0, bool keep_field = false, bool later_leg = false)
 {
     vpm_ctx* ctx = xs->ctx;
     const double Dt = dt * chi, escale = -1.0 / (chi * chi), wscale = 1.0 / (chi * chi);
@@ -707,7 +784,7 @@ static int vp_steps(vpm_xspace* xs, double* x, double* v, const double* w, int64
 
     // self-consistent (legacy integrate_vp!): passes are staggered by half a drift so that one pass per
     // step does kick(n) + drift/2 + drift/2 + deposit(n+1)
-    if (diag_mode) {
+    if (diag_mode && !later_leg) {   // row 0 of a later leg of one run repeats the previous leg's last row: not recomputed
         VpPass p0 = ps;
         p0.flags = VP_DEPOSIT | VP_DIAG;
         VPM_CHECK(launch_vp_pass(ctx, xs, p0, &grid));
@@ -775,7 +852,7 @@ int vpm_vp_strang_steps(vpm_xspace* xs, vpm_particles* p, double dt, double chi,
     } else {
         VPM_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    return VPM_OK;
+    return p2p_status(ctx);
 }
 
 int vpm_vp_strang_step_host(vpm_xspace* xs, vpm_particles* p, const double* z_in, double* z_out, double dt, double chi, int mode)
@@ -796,7 +873,7 @@ int vpm_vp_strang_step_host(vpm_xspace* xs, vpm_particles* p, const double* z_in
     VPM_CHECK(launch_soa_to_aos(ctx, x, v, nullptr, 2, n, z));
     VPM_CUDA(cudaMemcpyAsync(z_out, z, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
     VPM_CUDA(cudaStreamSynchronize(ctx->stream));
-    return VPM_OK;
+    return p2p_status(ctx);
 }
 
 /* ---------------------------------------------------------------- v-space */
@@ -1027,9 +1104,9 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
 int vpm_lb_rk438_steps(vpm_vspace* vs, vpm_particles* p, double nu, double dt, int nsteps, int conservative, double* diag_host)
 {
     VPM_CHECK(vpm_lb_rk438_steps_async(vs, p, nu, dt, nsteps, conservative));
-    if (diag_host) return d2h(vs->ctx, diag_host, vs->diag, 2 * ((size_t)nsteps + 1));
-    VPM_CUDA(cudaStreamSynchronize(vs->ctx->stream));
-    return VPM_OK;
+    if (diag_host) VPM_CHECK(d2h(vs->ctx, diag_host, vs->diag, 2 * ((size_t)nsteps + 1)));
+    else VPM_CUDA(cudaStreamSynchronize(vs->ctx->stream));
+    return p2p_status(vs->ctx);
 }
 
 int vpm_vspace_get(vpm_vspace* vs, double* rhs_host, double* coef_host)
@@ -1180,7 +1257,7 @@ int vpm_vp_run(vpm_xspace* xs, vpm_particles* p, double dt, double chi, int nste
         if (done < nsteps) {
             // enqueue the next leg and its snapshot before draining frame f, so the GPU computes while the host writes
             const int leg = std::min(save_stride, nsteps - done);
-            VPM_CHECK(vp_steps(xs, p->x, p->v, p->w, p->n, p->x, p->w, p->n, dt, chi, leg, mode, diag_mode, p->uw, p->wu, done > 0));
+            VPM_CHECK(vp_steps(xs, p->x, p->v, p->w, p->n, p->x, p->w, p->n, dt, chi, leg, mode, diag_mode, p->uw, p->wu, done > 0, done > 0));
             if (diag_mode) {
                 const int skip = done > 0 ? 1 : 0;   // row 0 of a later leg repeats the previous leg's last row
                 VPM_CUDA(cudaMemcpyAsync(hist.p + 3 * (size_t)(done + skip), xs->diag + 3 * skip,
@@ -1201,7 +1278,7 @@ int vpm_vp_run(vpm_xspace* xs, vpm_particles* p, double dt, double chi, int nste
         VPM_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     if (frames_out) *frames_out = (int)nframes;
-    return VPM_OK;
+    return p2p_status(ctx);
 }
 
 int vpm_lb_run(vpm_vspace* vs, vpm_particles* p, double nu, double dt, double t0, int nsteps, int conservative, int save_stride,
@@ -1249,7 +1326,7 @@ int vpm_lb_run(vpm_vspace* vs, vpm_particles* p, double nu, double dt, double t0
     if (diag_host) VPM_CHECK(d2h(ctx, diag_host, hist.p, 2 * ((size_t)nsteps + 1)));
     else VPM_CUDA(cudaStreamSynchronize(ctx->stream));
     if (frames_out) *frames_out = (int)nframes;
-    return VPM_OK;
+    return p2p_status(ctx);
 }
 
 /* ---------------------------------------------------------------- host-side operators */
@@ -1398,6 +1475,11 @@ int vpm_p2p_attach(vpm_ctx* ctx, int nranks, int rank, const void* ipc_handles)
         }
         ctx->p2p_opened[r] = ptr;
         d.mbox[r] = (P2PMailbox*)ptr;
+    }
+    {
+        double ms = 20000.0;   // ~20 s at 2 GHz
+        if (const char* e = getenv("VPM_P2P_TIMEOUT_MS")) ms = std::max(1.0, atof(e));
+        d.timeout_cycles = (long long)(ms * 2.0e6);
     }
     ctx->p2p = d;
     ctx->p2p_seq = 0;

@@ -805,7 +805,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
     if (rc) return rc;
     P.partials = ctx->partials;
     P.red_partials = ctx->partials + (size_t)grid * vs->nbfull;
-    prof_begin(ctx, PROF_LB_PASS);
+    prof_begin(ctx, PROF_LB_PASS, p.mode);
     VPM_CUDA(launch_pdl(kern, (unsigned)grid, (unsigned)block, smem, ctx->stream, P));
     prof_end(ctx);
     ctx->launches++;

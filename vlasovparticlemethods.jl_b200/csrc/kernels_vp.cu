@@ -510,8 +510,8 @@ __global__ void __launch_bounds__(kVpFieldThreads) vp_field_kernel(const FieldDe
                 if (lane == 0) s_ru[b] = s;
             }
         }
-        if (F.has_kin && warp < 2) {
-            const double s = warp_sum(strided_sum(F.kin_partials + warp, 2, F.nparts, lane));
+        if (warp < 2) {   // K, M slots: always rewritten, so that the all-reduce below never sums stale values
+            const double s = F.has_kin ? warp_sum(strided_sum(F.kin_partials + warp, 2, F.nparts, lane)) : 0.0;
             if (lane == 0) F.rhs[nh + warp] = s;
         }
         __syncthreads();

@@ -7,8 +7,9 @@
 // The payload is 18 doubles (VP) to ~50 doubles (LB/CLB): pure latency, which is why it is a handful of
 // stores and a flag instead of a ring.  Mailboxes are double-buffered by the parity of the sequence number:
 // a rank can only run one collective ahead of the slowest rank (it needs that rank's flag to finish), so two
-// buffers are enough.  A bounded spin (about 20 s of SM clocks) turns a dead peer into an error flag
-// instead of a hung GPU.
+// buffers are enough.  A bounded spin (about 20 s of SM clocks; VPM_P2P_TIMEOUT_MS) turns a dead peer into an
+// error instead of a hung GPU: the mailbox's error word is set (the synchronous steppers check it and return
+// VPM_ERR_COMM) and the reduced vector is poisoned with NaN so that nothing downstream can pass for a result.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -27,6 +28,7 @@ struct P2PDev {
     P2PMailbox* mbox[kP2PMaxRanks];  // mbox[rank] is local, the others are IPC-mapped peer memory
     int nranks, rank;
     unsigned long long seq;          // 0 = inactive
+    long long timeout_cycles;        // spin bound of one collective (SM clocks)
 };
 
 #ifdef __CUDACC__
@@ -47,6 +49,8 @@ __device__ __forceinline__ void p2p_allreduce(const P2PDev& c, double* buf, int 
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int par = (int)(c.seq & 1ull);
+    __shared__ int s_dead;
+    if (tid == 0) s_dead = 0;
     for (int r = 0; r < c.nranks; r++) {
         double* dst = c.mbox[r]->data[par][c.rank];
         for (int i = tid; i < count; i += nt) dst[i] = buf[i];
@@ -58,8 +62,9 @@ __device__ __forceinline__ void p2p_allreduce(const P2PDev& c, double* buf, int 
         const unsigned long long* f = &c.mbox[c.rank]->flag[par][tid];
         const long long t0 = clock64();
         while (ld_acquire_sys(f) < c.seq) {
-            if (clock64() - t0 > 40000000000ll) {  // ~20 s: a peer died; flag it and fall through
+            if (clock64() - t0 > c.timeout_cycles) {  // a peer died: flag it, poison the sum below
                 c.mbox[c.rank]->error = c.seq;
+                s_dead = 1;
                 break;
             }
         }
@@ -69,7 +74,7 @@ __device__ __forceinline__ void p2p_allreduce(const P2PDev& c, double* buf, int 
     for (int i = tid; i < count; i += nt) {
         double s = 0.0;
         for (int r = 0; r < c.nranks; r++) s += __ldcv(&mine->data[par][r][i]);  // fixed rank order
-        buf[i] = s;
+        buf[i] = s_dead ? __longlong_as_double(0x7ff8000000000000ll) : s;
     }
     __syncthreads();
 }

@@ -70,6 +70,7 @@ struct vpm_ctx {
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;
     std::vector<int> prof_kinds;
+    std::vector<int> prof_subs;   // LB passes: the pass mode (LbMode), so that stages and moments passes are timed separately
 };
 
 struct vpm_particles {
@@ -128,7 +129,7 @@ int ensure_red(vpm_ctx* ctx, size_t doubles);
 int ensure_staging(vpm_ctx* ctx, size_t doubles);
 int comm_allreduce(vpm_ctx* ctx, double* buf, size_t count);
 enum ProfKind : int { PROF_VP_PASS = 0, PROF_VP_FIELD = 1, PROF_LB_PASS = 2, PROF_LB_FIELD = 3, PROF_OTHER = 4, PROF_NKIND = 8 };
-void prof_begin(vpm_ctx* ctx, int kind);   // no-ops unless ctx->profile
+void prof_begin(vpm_ctx* ctx, int kind, int sub = 0);   // no-ops unless ctx->profile
 void prof_end(vpm_ctx* ctx);
 
 // Launch with programmatic stream serialization (PDL): the kernel may start its prologue while the previous
