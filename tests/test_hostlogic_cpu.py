@@ -132,7 +132,7 @@ def test_ntime_is_a_ceiling_like_upstream():
     from vpm_b200 import api
     assert api._ntime((0.0, 20.0), 0.1) == 200 and api._ntime((0.0, 500.0), 1e-2) == 50000 and api._ntime((0.0, 10.0), 0.1) == 100
     assert api._ntime((0.0, 1.05), 0.1) == 11                 # non-divisible: rounded UP (round() gave 10)
-    assert api._ntime((0.0, 0.9), 0.3) == 4                   # 0.9 / 0.3 = 3.0000000000000004: as upstream
+    assert api._ntime((0.0, 2.1), 0.3) == 8                   # 2.1 / 0.3 = 7.000000000000001: as upstream
     assert api._ntime((1.0, 0.0), 0.25) == 4
     for ns, dt in ((3, 0.1), (7, 0.013), (1, 0.29), (4, 0.05), (0, 0.1), (200, 0.1)):
         assert api._ntime(api.tspan_for(ns, dt), dt) == ns

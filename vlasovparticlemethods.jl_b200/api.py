@@ -672,7 +672,7 @@ def CLB_rhs(v, params, fs):
 # ------------------------------------------------------------------------------------------------
 def _ntime(tspan, tstep):
     """number of steps of a tspan: GeometricEquations' ntime = Int(abs(div(tend - tbegin, tstep, RoundUp))) -- a ceiling of
-    the floating-point quotient (0.9 / 0.3 = 3.0000000000000004 gives 4 steps, as upstream; tspan_for avoids that)"""
+    the floating-point quotient (2.1 / 0.3 = 7.000000000000001 gives 8 steps, as upstream; tspan_for avoids that)"""
     return int(abs(math.ceil((tspan[1] - tspan[0]) / tstep)))
 
 
