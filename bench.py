@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip sustained / workloads / parity_check (tuning runs)")
+    ap.add_argument("--sustained", action="store_true", help="with --no-extras: still run the sustained window")
     ap.add_argument("--sustained-seconds", type=float, default=5.5)
     ap.add_argument("--lb-steps", type=int, default=30, help="RK438 steps of the lb / clb blocks of the default line")
     ap.add_argument("--ref-budget-seconds", type=float, default=150.0,
@@ -649,7 +650,7 @@ def main():
         line["passes_in_timed_region"] = vp["passes"]
         line.update({"value": vp["value"], "ms_per_step": vp["ms_per_step"], "config": cfg, "roofline": vp["roofline"],
                      "gpu_launches": vp["launches"], "clocks": vp["clocks"]})
-        if extras and args.load == "bump_on_tail" and args.field == "selfconsistent":
+        if (extras or args.sustained) and args.load == "bump_on_tail" and args.field == "selfconsistent":
             line["sustained"] = B.sustained(B.vp_run_steps, vp["ms_per_step"], BYTES_PER_STEP)
             # the fused pass alone, timed while the clocks are still at their sustained level
             kms, kcnt, _, _ = B.profile(B.vp_run_steps, 20)
@@ -668,7 +669,7 @@ def main():
             line["workloads"] = wl
     else:
         cons = args.workload == "clb"
-        r = B.bench_lb(cons, args.steps, sustained=extras)
+        r = B.bench_lb(cons, args.steps, sustained=extras or args.sustained)
         line["passes_in_timed_region"] = 4 * args.steps * (2 if cons else 1) + 1
         line.update({"value": r["value"], "ms_per_step": r["ms_per_step"], "config": cfg, "roofline": r["roofline"],
                      "gpu_launches": r["gpu_launches"], "clocks": r["clocks"], "passes": r["passes"],

@@ -204,6 +204,20 @@ int vpm_lb_rk438_steps(vpm_vspace* vs, vpm_particles* p, double nu, double dt, i
                        double* diag_host);
 int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double dt, int nsteps, int conservative);
 int vpm_vspace_get(vpm_vspace* vs, double* rhs_host, double* coef_host);
+/* Collision entropy -- NON-REFERENCE diagnostic.  The reference holds the entropy's spline (CollisionEntropy,
+ * src/entropies/collision_entropy.jl:1-10) but computing it is a TODO upstream (compute_entropy!, :12-15); the north star
+ * asks for entropy histories.  Definition used here, the particle form of -int f ln f dv with f given by its spline
+ * projection f_s:     S = - sum_p w_p ln max(f_s(v_p), f_floor),
+ * where the floor (> 0, e.g. 1e-14) keeps S continuous where f_s is at round-off level or negative (deep tails, outside
+ * the knots).  coef_host == NULL: the spline of the last projection.  *nfloored_host (optional): particles at the floor. */
+int vpm_entropy_v(vpm_vspace* vs, const double* coef_host, const double* v_dev, const double* w_dev, int64_t n, double f_floor,
+                  double* S_host, double* nfloored_host);
+/* enable != 0: every following RK438 stepper call on vs (vpm_lb_rk438_steps{,_async}, vpm_lb_run) also records the entropy
+ * of the states at steps 0..nsteps, each with the spline projected from that state (one extra gather pass of 16 B per
+ * particle and step; off by default).  vpm_vspace_entropy_get copies the first `rows` rows of the last call
+ * (rows <= nsteps + 1) after synchronising the stream. */
+int vpm_vspace_entropy_history(vpm_vspace* vs, int enable, double f_floor);
+int vpm_vspace_entropy_get(vpm_vspace* vs, double* S_host, double* nfloored_host, int rows);
 /* projection!(init::SplineDistribution, final::ParticleDistribution) -- an empty TODO upstream
  * (src/projections/distribution.jl:57-61): draw the velocities of p from the spline f_s by stratified inverse-CDF
  * sampling (quantile (offset + i + r) / ntotal of the cell-wise clipped CDF; r = 1/2, or a counter-based uniform when

@@ -15,6 +15,7 @@ import VlasovMethods: projection!, projection, run!, initialize!, DistributionFu
                       LB_rhs!, CLB_rhs!, LB_rhs_GI!, CLB_rhs_GI!, s_advection!, s_acceleration!,
                       compute_f_densities, compute_df_densities, projection_density, projection_momentum, projection_energy
 using BSplineKit: Derivative
+import PoissonSolvers   # a direct dependency of VlasovMethods (Project.toml:42); the model calls PoissonSolvers.update!
 
 const libvpm = get(ENV, "LIBVPM_B200", "libvpm_b200.so")
 
@@ -127,6 +128,19 @@ VlasovMethods.CollisionEntropy(dist::DeviceSplineDistribution) = DeviceCollision
 # LenardBernstein(dist, ent; ν) / ConservativeLenardBernstein(dist, ent; ν) take any DistributionFunction{1,1} and any
 # Entropy (src/models/lenard_bernstein.jl:1-9), so they work with the device types as they are.
 
+# compute_entropy!(entropy, dist): a TODO upstream (src/entropies/collision_entropy.jl:12-15) -- NON-REFERENCE diagnostic:
+# S = -sum_p w_p ln max(f_s(v_p), f_floor) with f_s the spline projection of the particles (vpm_entropy_v)
+const ENTROPY_FLOOR = 1e-14
+function compute_entropy!(entropy::DeviceCollisionEntropy, dist::DeviceParticleDistribution; f_floor::Float64 = ENTROPY_FLOOR)
+    _, v, w = ptrs(dist)
+    check(ccall((:vpm_project_v, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
+                entropy.dist.h, v, w, dist.n, C_NULL))
+    S = Ref{Float64}(); nf = Ref{Float64}()
+    check(ccall((:vpm_entropy_v, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Float64, Ref{Float64}, Ref{Float64}),
+                entropy.dist.h, C_NULL, v, w, dist.n, f_floor, S, nf))
+    S[]
+end
+
 # every reference sampler gives equal weights: declaring it lets the steppers skip the w[] stream
 set_uniform_weight!(d::DeviceParticleDistribution, w::Real) =
     (check(ccall((:vpm_particles_set_uniform_weight, libvpm), Cint, (Ptr{Cvoid}, Float64), d.h, w)); d)
@@ -157,9 +171,12 @@ function projection!(potential::DevicePotential, distribution::DeviceParticleDis
     potential
 end
 
-# PoissonSolvers.update!(potential): call site src/models/vlasov_poisson.jl:14
-update!(potential::DevicePotential) =
+# PoissonSolvers.update!(potential): call site src/models/vlasov_poisson.jl:14.  A METHOD OF PoissonSolvers' OWN GENERIC
+# FUNCTION, so that update_potential!(model) -- which calls PoissonSolvers.update!(model.potential) -- dispatches here
+# for a DevicePotential instead of raising a MethodError.
+PoissonSolvers.update!(potential::DevicePotential) =
     (check(ccall((:vpm_poisson_solve, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), potential.h, C_NULL, C_NULL)); potential)
+const update! = PoissonSolvers.update!
 
 # update_potential!(model): src/models/vlasov_poisson.jl:12-15
 VlasovMethods.update_potential!(model::DeviceVlasovPoisson) =
@@ -338,15 +355,25 @@ GeometricIntegrator(model::Union{LenardBernstein{1,1,DeviceParticleDistribution}
                     tspan::Tuple, tstep::Real) = DeviceRK438(model, Float64.(tspan), Float64(tstep))
 
 # run!(method, h5file): datasets "z" (np, nt+1) chunk (np, 1) and "t" (nt+1) as src/methods/geometric_integrator.jl:21-35
-function run!(m::DeviceRK438, h5file::Union{AbstractString,Nothing} = nothing; save_stride::Integer = 1)
+# entropy = true also returns the history of the (non-reference) collision entropy S(t_n), see compute_entropy!
+function run!(m::DeviceRK438, h5file::Union{AbstractString,Nothing} = nothing; save_stride::Integer = 1, entropy::Bool = false,
+              f_floor::Float64 = ENTROPY_FLOOR)
     nt = Int(abs(div(m.tspan[2] - m.tspan[1], m.tstep, RoundUp)))   # GeometricEquations' ntime
     diag = zeros(2, nt + 1)          # rows Σv, Σv² (scripts/lenard_bernstein_conservative.jl:49-50)
     frames = Ref{Cint}(0)
-    check(ccall((:vpm_lb_run, libvpm), Cint,
-                (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, Float64, Cint, Cint, Cint, Cstring, Ptr{Float64}, Ref{Cint}),
-                m.model.ent.dist.h, m.model.dist.h, m.model.ν, m.tstep, m.tspan[1], nt, m.model isa ConservativeLenardBernstein,
-                h5file === nothing ? 0 : save_stride, h5file === nothing ? C_NULL : h5file, diag, frames))
-    m.model.dist, diag
+    sh = m.model.ent.dist.h
+    check(ccall((:vpm_vspace_entropy_history, libvpm), Cint, (Ptr{Cvoid}, Cint, Float64), sh, entropy, f_floor))
+    S = entropy ? zeros(nt + 1) : nothing
+    try
+        check(ccall((:vpm_lb_run, libvpm), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, Float64, Cint, Cint, Cint, Cstring, Ptr{Float64}, Ref{Cint}),
+                    sh, m.model.dist.h, m.model.ν, m.tstep, m.tspan[1], nt, m.model isa ConservativeLenardBernstein,
+                    h5file === nothing ? 0 : save_stride, h5file === nothing ? C_NULL : h5file, diag, frames))
+        entropy && check(ccall((:vpm_vspace_entropy_get, libvpm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint), sh, S, C_NULL, nt + 1))
+    finally
+        ccall((:vpm_vspace_entropy_history, libvpm), Cint, (Ptr{Cvoid}, Cint, Float64), sh, 0, f_floor)
+    end
+    entropy ? (m.model.dist, diag, S) : (m.model.dist, diag)
 end
 
 # ---------------------------------------------------------------------------------- initial conditions

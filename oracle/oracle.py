@@ -75,6 +75,8 @@ def lib():
             "vpo_clb_coefficients": (None, [_D, _D]),
             "vpo_lb_rhs": (None, [vp, i64, _D, _D, f64, i32, _D, _D, _D]),
             "vpo_lb_rk438": (None, [vp, i64, _D, _D, f64, f64, i32, i32, _D]),
+            "vpo_entropy_v": (f64, [vp, _D, i64, _D, _D, f64, C.POINTER(C.c_double)]),
+            "vpo_lb_rk438_entropy": (None, [vp, i64, _D, _D, f64, f64, i32, i32, f64, _D, _D, _D]),
             "vpo_uniform": (f64, [u64, u64, u32]),
             "vpo_norminv": (f64, [f64]),
             "vpo_sample_bump_on_tail": (None, [i64, i64, i64, u64, f64, f64, f64, f64, f64, _D, _D, _D]),
@@ -254,6 +256,20 @@ class VSpace:
         v, w = np.empty(N), np.empty(N)
         mass = lib().vpo_resample_v(self._h, _dp(coef), N, offset, Ntotal, seed, int(jitter), _dp(v), _dp(w))
         return v, w, mass
+
+    def entropy(self, coef, v, w, f_floor=1e-14):
+        """S = -sum w ln max(f_s(v), f_floor) (non-reference diagnostic, see vpo_entropy_v); returns (S, n_floored)"""
+        coef, v, w = _f64(coef), _f64(v), _f64(w)
+        nf = C.c_double()
+        S = lib().vpo_entropy_v(self._h, _dp(coef), v.size, _dp(v), _dp(w), float(f_floor), C.byref(nf))
+        return float(S), int(nf.value)
+
+    def rk438_entropy(self, v, w, nu, dt, nsteps, conservative=False, f_floor=1e-14):
+        v, w = _f64(v).copy(), _f64(w)
+        d, e, nf = np.zeros((nsteps + 1, 2)), np.zeros(nsteps + 1), np.zeros(nsteps + 1)
+        lib().vpo_lb_rk438_entropy(self._h, v.size, _dp(v), _dp(w), float(nu), float(dt), int(conservative), int(nsteps),
+                                   float(f_floor), _dp(d), _dp(e), _dp(nf))
+        return v, d, e, nf
 
     def rk438(self, v, w, nu, dt, nsteps, conservative=False, diag=True):
         v, w = _f64(v).copy(), _f64(w)

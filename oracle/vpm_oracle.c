@@ -691,6 +691,47 @@ VPO_API void vpo_lb_rk438(const vpo_vspace *s, int64_t N, double *v, const doubl
     free(k1); free(k2); free(k3); free(k4); free(q);
 }
 
+/* ---- collision entropy (NON-REFERENCE diagnostic) ------------------------------
+ * The reference only holds the entropy's spline (CollisionEntropy, src/entropies/collision_entropy.jl:1-10); computing
+ * it is a TODO upstream (:12-15).  The north star asks for entropy histories, so this defines the particle form of the
+ * Boltzmann functional -int f ln f dv with f represented by its spline projection f_s:
+ *      S = - sum_p w_p ln max(f_s(v_p), f_floor)
+ * The floor makes S continuous in f_s where the projected spline is at round-off level or negative (deep tails, outside
+ * the knots): a sign flip of a 1e-17 value must not move S.  *nfloored counts the particles at or below the floor. */
+VPO_API double vpo_entropy_v(const vpo_vspace *s, const double *coef, int64_t N, const double *v, const double *w,
+                             double f_floor, double *nfloored)
+{
+    double S = 0.0, nf = 0.0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) reduction(+ : S, nf) if (g_threads > 1 && N > 4096)
+#endif
+    for (int64_t p = 0; p < N; p++) {
+        double f = vpo_veval(s, coef, v[p], 0);
+        if (!(f > f_floor)) { f = f_floor; nf += 1.0; }
+        S -= w[p] * log(f);
+    }
+    if (nfloored) *nfloored = nf;
+    return S;
+}
+
+/* vpo_lb_rk438 with the entropy history: ent[it] = S(v(t_it)) with f_s = projection of v(t_it), it = 0..nsteps */
+VPO_API void vpo_lb_rk438_entropy(const vpo_vspace *s, int64_t N, double *v, const double *w, double nu, double dt,
+                                  int conservative, int nsteps, double f_floor, double *diag, double *ent, double *nfloored)
+{
+    double *coef = (double *)malloc(s->nv * sizeof(double));
+    for (int it = 0; it <= nsteps; it++) {
+        if (it > 0) vpo_lb_rk438(s, N, v, w, nu, dt, conservative, 1, NULL);
+        if (diag) {
+            double s1 = 0, s2 = 0;
+            for (int64_t p = 0; p < N; p++) { s1 += v[p]; s2 += v[p] * v[p]; }
+            diag[2 * it] = s1; diag[2 * it + 1] = s2;
+        }
+        vpo_project_v(s, N, v, w, coef);
+        ent[it] = vpo_entropy_v(s, coef, N, v, w, f_floor, nfloored ? nfloored + it : NULL);
+    }
+    free(coef);
+}
+
 /* ---- spline -> particles: stratified inverse-CDF sampling of f_s --------------
  * projection!(init::SplineDistribution, final::ParticleDistribution) is an empty TODO upstream
  * (src/projections/distribution.jl:57-61); this is the checker for the library's vpm_resample_v, by an

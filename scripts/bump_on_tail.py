@@ -11,7 +11,7 @@ import argparse
 import numpy as np
 
 import _common  # noqa: F401
-from vpm_b200 import (BumpOnTail, ParticleDistribution, PeriodicBasisBSplineKit, Potential, SplittingMethod, VlasovPoisson,
+from vpm_b200 import (BumpOnTail, tspan_for, ParticleDistribution, PeriodicBasisBSplineKit, Potential, SplittingMethod, VlasovPoisson,
                       initialize_, run_)
 
 ap = argparse.ArgumentParser()
@@ -38,7 +38,7 @@ potential = Potential(PeriodicBasisBSplineKit((0.0, L), p + 1, nh))
 model = VlasovPoisson(dist, potential)
 
 # integrate all time steps                                            :58-60
-integrator = SplittingMethod(model, (0.0, nt * dt), dt, field="selfconsistent", chi=chi)
+integrator = SplittingMethod(model, tspan_for(nt, dt), dt, field="selfconsistent", chi=chi)
 run_(integrator, diag_mode=2)          # W, K, M exactly as save_timestep! (src/vlasov_poisson.jl:58-67)
 
 W, K, M = integrator.diagnostics.T

@@ -43,14 +43,14 @@ def _worker(rank, world, port, nper, out_dir, comm):
     d = vpm.ParticleDistribution(1, 1, nper, ctx)
     vpm.initialize_(d, vpm.BumpOnTail(), offset=rank * nper, ntotal=world * nper)
     pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), 4, 16), ctx)
-    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 0.5), 0.1, field="selfconsistent")
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(5, 0.1), 0.1, field="selfconsistent")
     vpm.run_(m, diag_mode=2)
     x, v, _ = d.get()
     # conservative Lenard-Bernstein RK438
     d2 = vpm.ParticleDistribution(1, 1, nper, ctx)
     vpm.initialize_(d2, vpm.DoubleMaxwellian((-10.0, 10.0), 2.0), offset=rank * nper, ntotal=world * nper)
     sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet", ctx)
-    gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d2, vpm.CollisionEntropy(sd)), (0.0, 0.03), 0.01)
+    gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d2, vpm.CollisionEntropy(sd)), vpm.tspan_for(3, 0.01), 0.01)
     vpm.run_(gi)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), x=x, v=v, diag=m.diagnostics, phi=pot.coefficients,
              vlb=d2.get("v"), dlb=gi.diagnostics, coef=sd.coefficients)
@@ -80,7 +80,7 @@ def test_two_rank_slabs_match_single_gpu(tmp_path, perr, comm):
     d = vpm.ParticleDistribution(1, 1, world * nper)
     vpm.initialize_(d, vpm.BumpOnTail())
     pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), 4, 16))
-    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 0.5), 0.1, field="selfconsistent")
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(5, 0.1), 0.1, field="selfconsistent")
     vpm.run_(m, diag_mode=2)
     x, v, _ = d.get()
     tag = "@" + comm
@@ -93,7 +93,7 @@ def test_two_rank_slabs_match_single_gpu(tmp_path, perr, comm):
     d2 = vpm.ParticleDistribution(1, 1, world * nper)
     vpm.initialize_(d2, vpm.DoubleMaxwellian((-10.0, 10.0), 2.0))
     sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
-    gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d2, vpm.CollisionEntropy(sd)), (0.0, 0.03), 0.01)
+    gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d2, vpm.CollisionEntropy(sd)), vpm.tspan_for(3, 0.01), 0.01)
     vpm.run_(gi)
     v2 = d2.get("v")
     perr("two_rank_clb_v" + tag, nrm(np.concatenate([r[0]["vlb"], r[1]["vlb"]]), v2), 1e-12)

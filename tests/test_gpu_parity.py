@@ -186,7 +186,7 @@ def test_strang_vs_oracle_long(vpm, oracle, perr):
     for rep in range(2):
         d = make_particles(vpm, x, v, w)
         pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), K, nh))
-        m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 4.0), 0.1, field="selfconsistent")
+        m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(40, 0.1), 0.1, field="selfconsistent")
         vpm.run_(m, diag_mode=1)
         res.append(d.get() + (m.diagnostics,))
     perr("strang40_x", nrm(res[0][0], xo), TOL)
@@ -227,7 +227,7 @@ def test_large_properties(vpm):
     pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, bot.L), 4, 16))
     vpm.projection_(pot, d)
     assert abs(pot.rhs.sum() - bot.L) < 1e-12 * bot.L
-    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 0.3), 0.1, field="selfconsistent")
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(3, 0.1), 0.1, field="selfconsistent")
     vpm.run_(m, diag_mode=1)
     dg = m.diagnostics
     assert np.all(np.isfinite(dg))
@@ -311,7 +311,7 @@ def test_lb_edge_sizes(vpm, oracle, perr, n):
             continue                                       # the CLB coefficients are 0/0 for a handful of particles
         d = vpm.ParticleDistribution(1, 1, n).set(np.zeros(n), v, w)
         model = (vpm.ConservativeLenardBernstein if cons else vpm.LenardBernstein)(d, vpm.CollisionEntropy(sd), nu=0.9)
-        gi = vpm.GeometricIntegrator(model, (0.0, 0.04), 0.02)
+        gi = vpm.GeometricIntegrator(model, vpm.tspan_for(2, 0.02), 0.02)
         vpm.run_(gi)
         vo, do = vs.rk438(v, w, 0.9, 0.02, 2, conservative=cons)
         assert gi.diagnostics.shape[0] == 3
@@ -346,7 +346,7 @@ def test_lb_large_properties(vpm, monkeypatch):
     for ring in ("-1", "0"):
         monkeypatch.setenv("VPM_TUNE_LBTMA", ring)
         d.set(v=v0)
-        gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d, ent, nu=1.0), (0.0, 0.04), 1e-2)
+        gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d, ent, nu=1.0), vpm.tspan_for(4, 1e-2), 1e-2)
         vpm.run_(gi)
         res[ring] = (d.get("v"), gi.diagnostics.copy())
     assert nrm(res["-1"][0], res["0"][0]) < 1e-13
@@ -354,7 +354,7 @@ def test_lb_large_properties(vpm, monkeypatch):
     monkeypatch.setenv("VPM_TUNE_LBTMA", "-1")
     d.set(v=v0)
     for _ in range(2):                                    # 2 + 2 steps in two calls
-        gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d, ent, nu=1.0), (0.0, 0.02), 1e-2)
+        gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d, ent, nu=1.0), vpm.tspan_for(2, 1e-2), 1e-2)
         vpm.run_(gi)
     assert nrm(d.get("v"), res["-1"][0]) < 1e-13
     dg = res["-1"][1]
@@ -373,7 +373,7 @@ def test_lb_relaxation_physics(vpm):
         d = vpm.ParticleDistribution(1, 1, n)
         vpm.initialize_(d, vpm.DoubleMaxwellian((-10.0, 10.0), 2.0))
         model = (vpm.ConservativeLenardBernstein if cons else vpm.LenardBernstein)(d, ent, nu=1.0)
-        gi = vpm.GeometricIntegrator(model, (0.0, 0.5), 1e-2)
+        gi = vpm.GeometricIntegrator(model, vpm.tspan_for(50, 1e-2), 1e-2)
         vpm.run_(gi)
         out[cons] = gi.diagnostics
     dc, dl = out[True], out[False]
@@ -441,7 +441,7 @@ def test_large_grids_natural(vpm, oracle, perr):
     d = make_particles(vpm, x, v, w)
     pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((lo, hi), K, nh))
     xs = oracle.XSpace(lo, hi, K, nh)
-    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 0.2), 0.1, field="selfconsistent")
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(2, 0.1), 0.1, field="selfconsistent")
     vpm.run_(m, diag_mode=0)
     xo, vo, _, _ = xs.strang_selfconsistent(x, v, w, 0.1, 2, diag=False)
     xg, vg, _ = d.get()

@@ -38,7 +38,7 @@ def test_vp_selfconsistent_trajectory(vpm, oracle, tmp_path, stride):
     n, nt, dt = 20011, 7, 0.1
     bot, x, v, w, pot = _vp_setup(vpm, oracle, n)
     d = vpm.ParticleDistribution(1, 1, n).set(x, v, w)
-    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, nt * dt), dt, field="selfconsistent")
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(nt, dt), dt, field="selfconsistent")
     path = tmp_path / "vp.h5"
     vpm.run_(m, str(path), save_stride=stride, diag_mode=1)
     steps = sorted(set(list(range(0, nt, stride)) + [nt]))
@@ -56,7 +56,7 @@ def test_vp_selfconsistent_trajectory(vpm, oracle, tmp_path, stride):
     np.testing.assert_array_equal(z[-1], np.stack([xg, vg], axis=1))    # the last frame is the final device state
     # the same run without output: legs of `stride` steps must not change the arithmetic or the history
     d2 = vpm.ParticleDistribution(1, 1, n).set(x, v, w)
-    m2 = vpm.SplittingMethod(vpm.VlasovPoisson(d2, pot), (0.0, nt * dt), dt, field="selfconsistent")
+    m2 = vpm.SplittingMethod(vpm.VlasovPoisson(d2, pot), vpm.tspan_for(nt, dt), dt, field="selfconsistent")
     vpm.run_(m2, diag_mode=1)
     x2, v2, _ = d2.get()
     assert nrm(xg, x2) < 1e-14 and nrm(vg, v2) < 1e-14
@@ -72,7 +72,7 @@ def test_vp_frozen_field_stays_frozen_across_legs(vpm, oracle, tmp_path):
     out = []
     for h5 in (None, str(tmp_path / "frozen.h5")):
         d = vpm.ParticleDistribution(1, 1, n).set(x, v, w)
-        m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, nt * dt), dt, field="frozen")
+        m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(nt, dt), dt, field="frozen")
         vpm.run_(m, h5, save_stride=2, diag_mode=1)
         out.append((d.get(), m.diagnostics))
     (xa, va, _), da = out[0]
@@ -96,7 +96,7 @@ def test_lb_trajectory(vpm, oracle, tmp_path, cons):
     sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
     d = vpm.ParticleDistribution(1, 1, n).set(np.zeros(n), v, w)
     model = (vpm.ConservativeLenardBernstein if cons else vpm.LenardBernstein)(d, vpm.CollisionEntropy(sd), nu=nu)
-    gi = vpm.GeometricIntegrator(model, (t0, t0 + nt * dt), dt)
+    gi = vpm.GeometricIntegrator(model, vpm.tspan_for(nt, dt, t0), dt)
     path = tmp_path / "lb.h5"
     vpm.run_(gi, str(path), save_stride=2)
     f = h5mini.File(path)
@@ -122,7 +122,7 @@ def test_large_frames_stream_through_the_pinned_ring(vpm, tmp_path):
     pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, bot.L), 4, 16))
     d = vpm.initialize_(vpm.ParticleDistribution(1, 1, n), bot)
     x0, v0, _ = d.get()
-    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 2 * dt), dt, field="selfconsistent")
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(2, dt), dt, field="selfconsistent")
     path = tmp_path / "big.h5"
     vpm.run_(m, str(path), save_stride=1, diag_mode=0)
     assert os.path.getsize(path) > 3 * 16 * n
@@ -134,7 +134,7 @@ def test_large_frames_stream_through_the_pinned_ring(vpm, tmp_path):
     np.testing.assert_array_equal(z[2, :, 1], v2)
     # frame 1 = one step from the initial state
     d1 = vpm.initialize_(vpm.ParticleDistribution(1, 1, n), bot)
-    m1 = vpm.SplittingMethod(vpm.VlasovPoisson(d1, pot), (0.0, dt), dt, field="selfconsistent")
+    m1 = vpm.SplittingMethod(vpm.VlasovPoisson(d1, pot), vpm.tspan_for(1, dt), dt, field="selfconsistent")
     vpm.run_(m1, diag_mode=0)
     x1, v1, _ = d1.get()
     np.testing.assert_array_equal(z[1, :, 0], x1)

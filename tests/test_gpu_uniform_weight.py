@@ -29,7 +29,7 @@ def test_vp_uniform_weight(vpm, oracle, n):
         if uw:
             d.set_uniform_weight(w[0])
         for field in ("selfconsistent", "frozen"):
-            m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 0.3), 0.1, field=field)
+            m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(3, 0.1), 0.1, field=field)
             vpm.run_(m, diag_mode=1)
         out.append(d.get() + (m.diagnostics,))
     for a, b in zip(out[0], out[1]):
@@ -40,7 +40,7 @@ def test_vp_uniform_weight(vpm, oracle, n):
     assert nrm(out[1][0], xo) < 1e-12 and nrm(out[1][1], vo) < 1e-12
     # uploading weights clears the declaration
     d.set(w=np.linspace(0.5, 1.5, n) * w[0])
-    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, 0.1), 0.1, field="selfconsistent")
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(1, 0.1), 0.1, field="selfconsistent")
     vpm.run_(m, diag_mode=2)
     x2, v2, w2 = d.get()
     xo2, vo2, do2, _ = xs.strang_selfconsistent(out[1][0], out[1][1], w2, 0.1, 1)
@@ -58,7 +58,7 @@ def test_lb_uniform_weight(vpm, oracle):
         d = vpm.ParticleDistribution(1, 1, n).set(np.zeros(n), v, w)
         if uw:
             d.set_uniform_weight(1.0 / n)
-        gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d, vpm.CollisionEntropy(sd)), (0.0, 0.03), 0.01)
+        gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d, vpm.CollisionEntropy(sd)), vpm.tspan_for(3, 0.01), 0.01)
         vpm.run_(gi)
         res.append((d.get("v"), gi.diagnostics))
     # the w[] stream changes which pass variants fit (ring vs register prefetch), hence the summation order

@@ -216,3 +216,85 @@ def test_four_level_chunk_tree(vpm, tmp_path):
     a = f.read("t")
     assert max(x["level"] for x in f.group_info["chunk_nodes"]) == 3 and len(f.datasets["t"].chunks) == n
     assert all(a[i] == i + 0.5 for i in idx) and a.sum() == sum(i + 0.5 for i in idx)
+
+
+# ---------------------------------------------------------------------------------- structural validation
+def _sample():
+    import scipy.io
+    return os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data", "testhdf5_7.4_GLNX86.mat")
+
+
+def test_validator_accepts_a_file_written_by_libhdf5():
+    """the structural validator (tests/h5validate.py) is pinned on the real library's output first"""
+    import h5validate
+    if not os.path.exists(_sample()):
+        pytest.skip("scipy's MATLAB sample file is not installed")
+    rep = h5validate.validate(_sample())
+    assert rep["base"] == 512 and rep["eof"] == rep["file_size"]
+    assert rep["datasets"]["testdouble"]["layout"] == "contiguous" and rep["snods"] >= 1 and rep["allocations"] >= 6
+    assert all(h["free_bytes"] + 8 <= h["data_size"] for h in rep["heaps"])
+
+
+@pytest.mark.parametrize("nframes", [1, 6, 64, 65, 130, 5001])
+def test_written_files_pass_structural_validation(vpm, tmp_path, nframes):
+    """every address, size and key of our files: inside the file, disjoint, B-tree invariants (1, 2 and 3 levels), heap
+    free list, symbol-table caches, superblock EOF == file size -- what H5Fopen / H5Dread check before touching data"""
+    import h5validate
+    path = tmp_path / "v.h5"
+    npart = 3
+    w = vpm.H5Writer(path).create_dataset("z", (2, npart, nframes)).create_dataset("t", (nframes,)).commit()
+    for n in {0, nframes // 2, nframes - 1}:
+        w.write_frame("z", n, np.full((npart, 2), float(n)))
+        w.write_frame("t", n, [0.5 * n])
+    w.close()
+    rep = h5validate.validate(path)
+    dz, dt = rep["datasets"]["z"], rep["datasets"]["t"]
+    assert dz["chunks"] == dz["chunks_possible"] == nframes and dt["chunks"] == nframes
+    assert dz["btree_depth"] == (1 if nframes <= 64 else 2 if nframes <= 64 * 64 else 3)
+    assert rep["eof"] == rep["file_size"] == os.path.getsize(path)
+    # the validated structure holds the data the reader returns
+    f = h5mini.File(path)
+    assert f.read("t")[nframes - 1] == 0.5 * (nframes - 1) and f.read("z")[nframes // 2, 0, 0] == float(nframes // 2)
+
+
+def test_validator_rejects_corrupted_structures(vpm, tmp_path):
+    """the validator is not vacuous: single-field corruptions of a good file are caught"""
+    import h5validate
+    path = tmp_path / "good.h5"
+    w = vpm.H5Writer(path).create_dataset("z", (2, 3, 130)).create_dataset("t", (130,)).commit()
+    w.close()
+    good = open(path, "rb").read()
+    h5validate.validate(path)
+    f = h5mini.File(path)
+    f.read("z")
+    nodes = f.group_info["chunk_nodes"]
+    leaf = next(n for n in nodes if n["level"] == 0)
+    heap_addr, heap = next(iter(f.group_info["heaps"].items()))
+
+    def corrupt(off, data):
+        b = bytearray(good)
+        b[off:off + len(data)] = data
+        p = tmp_path / "bad.h5"
+        p.write_bytes(bytes(b))
+        return p
+
+    eof_field = 24 + 16                                      # superblock v0: base, free-space, EOF, driver addresses
+    cases = {
+        "eof beyond file": corrupt(eof_field, (len(good) + 8).to_bytes(8, "little")),
+        "eof short of file": corrupt(eof_field, (len(good) - 8).to_bytes(8, "little")),
+        "btree key order": corrupt(leaf["addr"] + 24 + 8, (10 ** 6).to_bytes(8, "little")),
+        "btree sibling": corrupt(leaf["addr"] + 16, (1234).to_bytes(8, "little")),
+        "chunk size field": corrupt(leaf["addr"] + 24, (7).to_bytes(4, "little")),
+        "heap free list": corrupt(heap_addr + 16, (heap["data_size"] + 64).to_bytes(8, "little")),
+        "heap free terminator": corrupt(heap["data_addr"] + heap["free_head"], (0xFFFFFFFFFFFFFFFF).to_bytes(8, "little")),
+        "object header count": corrupt(f.root_entry["ohdr"] + 2, (9).to_bytes(2, "little")),
+    }
+    for name, p in cases.items():
+        with pytest.raises((h5mini.H5FormatError, ValueError, IndexError, struct_error())):
+            h5validate.validate(p)
+            pytest.fail(f"corruption not detected: {name}")
+
+
+def struct_error():
+    import struct
+    return struct.error

@@ -44,7 +44,7 @@ def run(vpm, n, nsteps, conservative, chunk):
     done = 0
     while done < nsteps:
         k = min(chunk, nsteps - done)
-        gi = vpm.GeometricIntegrator(model, (0.0, dt * k), dt)
+        gi = vpm.GeometricIntegrator(model, vpm.tspan_for(k, dt), dt)
         vpm.run_(gi)
         diags.append(gi.diagnostics if not diags else gi.diagnostics[1:])
         done += k

@@ -42,7 +42,7 @@ def main():
 
     def run(h5, stride, steps):
         d = vpm.initialize_(vpm.ParticleDistribution(1, 1, n), bot)
-        m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), (0.0, steps * dt), dt, field="selfconsistent")
+        m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(steps, dt), dt, field="selfconsistent")
         d.ctx.sync()
         t0 = time.perf_counter()
         vpm.run_(m, h5, save_stride=stride, diag_mode=1)

@@ -78,6 +78,9 @@ SIGNATURES = {
     "vpm_lb_rk438_steps": (_i32, [_vp, _vp, _f64, _f64, _i32, _i32, _vp]),
     "vpm_lb_rk438_steps_async": (_i32, [_vp, _vp, _f64, _f64, _i32, _i32]),
     "vpm_vspace_get": (_i32, [_vp, _vp, _vp]),
+    "vpm_entropy_v": (_i32, [_vp, _vp, _vp, _vp, _i64, _f64, _D, _D]),
+    "vpm_vspace_entropy_history": (_i32, [_vp, _i32, _f64]),
+    "vpm_vspace_entropy_get": (_i32, [_vp, _vp, _vp, _i32]),
     "vpm_h5_create": (_i32, [C.c_char_p, C.POINTER(_vp)]),
     "vpm_h5_add_dataset": (_i32, [_vp, C.c_char_p, _i32, C.POINTER(_i64), C.POINTER(_i32)]),
     "vpm_h5_commit": (_i32, [_vp]),

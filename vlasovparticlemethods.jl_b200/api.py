@@ -604,6 +604,35 @@ class CollisionEntropy(Entropy):
     def __init__(self, dist):
         self.dist = dist
         self.cache = {np.float64: dist, float: dist}
+        self.value, self.floored = None, None   # set by compute_entropy_ (non-reference diagnostic)
+
+
+ENTROPY_FLOOR = 1e-14   # f_s below this is round-off of the fp64 projection (f_s = O(0.1) in the bulk)
+
+
+def compute_entropy_(entropy, dist, velocities=None, f_floor=ENTROPY_FLOOR, project=True):
+    """compute_entropy!(entropy, dist) -- a TODO upstream (src/entropies/collision_entropy.jl:12-15), so this is a
+    NON-REFERENCE diagnostic: S = -sum_p w_p ln max(f_s(v_p), f_floor), the particle form of -int f ln f dv with f given by
+    the spline projection of the particles (project=True re-projects dist first, as update_entropy! does,
+    lenard_bernstein.jl:15-17; False uses the spline currently held by entropy.dist).  `velocities`: evaluate at these
+    instead of the particles' own.  Sets entropy.value / entropy.floored and returns S."""
+    sd = entropy.dist
+    _, v, w = dist.ptrs()
+    dv = None
+    if velocities is not None:
+        vel = _f64(velocities).ravel()
+        if vel.size != dist.npart:
+            raise ValueError("velocities must have one entry per particle")
+        dv = DeviceVector(dist.ctx, vel.size, vel)
+        v = dv.ptr
+    if project:
+        check(_lib().vpm_project_v(sd._h, v, w, dist.npart, None))
+    S, nf = C.c_double(), C.c_double()
+    check(_lib().vpm_entropy_v(sd._h, None, v, w, dist.npart, float(f_floor), C.byref(S), C.byref(nf)))
+    if dv is not None:
+        dv.free()
+    entropy.value, entropy.floored = S.value, int(nf.value)
+    return S.value
 
 
 class LenardBernstein:
@@ -760,14 +789,16 @@ class GeometricIntegrator:
         self.diagnostics = None
 
 
-def run_(method, h5file=None, save_stride=None, diag_mode=1):
+def run_(method, h5file=None, save_stride=None, diag_mode=1, entropy=False, f_floor=ENTROPY_FLOOR):
     """run!(method, h5file): src/methods/splitting.jl:23-52, src/methods/geometric_integrator.jl:12-44.
 
     The state stays on the device between steps (vpm_vp_run / vpm_lb_run).  With h5file, the frames of steps
     0, k, 2k, ..., nt (k = save_stride, default 1 = the reference's every-step output) are written to an HDF5
     file in the reference's layout (dataset "z", plus "t"), copied off the device while the next steps compute.
     Without h5file no trajectory is kept.  Diagnostics (W,K,M) or (sum v, sum v^2) of every step are kept in
-    method.diagnostics; method.frames = number of frames written.
+    method.diagnostics; method.frames = number of frames written.  GeometricIntegrator runs with entropy=True also
+    record the collision entropy S(t_n) of every step (compute_entropy_: non-reference diagnostic, one extra gather pass
+    per step) in method.entropy, and the number of floored particles in method.entropy_floored.
     """
     nt = _ntime(method.tspan, method.tstep)
     stride = int(save_stride or 1) if h5file is not None else 0
@@ -785,8 +816,17 @@ def run_(method, h5file=None, save_stride=None, diag_mode=1):
         m = method.model
         d, sd = m.dist, m.ent.dist
         diag = np.zeros((nt + 1, 2))
-        check(_lib().vpm_lb_run(sd._h, d._h, m.nu, method.tstep, float(method.tspan[0]), nt, int(m.conservative), stride, path,
-                                _hp(diag), C.byref(frames)))
+        check(_lib().vpm_vspace_entropy_history(sd._h, int(bool(entropy)), float(f_floor)))
+        try:
+            check(_lib().vpm_lb_run(sd._h, d._h, m.nu, method.tstep, float(method.tspan[0]), nt, int(m.conservative), stride, path,
+                                    _hp(diag), C.byref(frames)))
+            method.entropy = method.entropy_floored = None
+            if entropy:
+                S, nf = np.zeros(nt + 1), np.zeros(nt + 1)
+                check(_lib().vpm_vspace_entropy_get(sd._h, _hp(S), _hp(nf), nt + 1))
+                method.entropy, method.entropy_floored = S, nf
+        finally:
+            _lib().vpm_vspace_entropy_history(sd._h, 0, float(f_floor))
         method.diagnostics, method.frames = diag, frames.value
         return d
     raise TypeError("run_ expects a SplittingMethod or a GeometricIntegrator")

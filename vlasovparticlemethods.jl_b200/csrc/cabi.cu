@@ -920,7 +920,7 @@ int vpm_vspace_destroy(vpm_vspace* vs)
     cudaSetDevice(vs->ctx->device);
     cudaStreamSynchronize(vs->ctx->stream);
     cudaFree(vs->pieces); cudaFree(vs->chol); cudaFree(vs->rhs); cudaFree(vs->coef); cudaFree(vs->ftab);
-    cudaFree(vs->scal); cudaFree(vs->diag);
+    cudaFree(vs->scal); cudaFree(vs->diag); cudaFree(vs->ent);
     delete vs;
     return VPM_OK;
 }
@@ -1050,6 +1050,62 @@ int vpm_lb_rhs(vpm_vspace* vs, const double* v_dev, const double* w_dev, int64_t
     return VPM_OK;
 }
 
+// one LB_ENTROPY pass over (q, w) with the device-side spline of vs; the two sums (S, floored count) are reduced
+// (all-reduced across ranks) into row `slot` of the entropy history
+static int lb_entropy_row(vpm_ctx* ctx, vpm_vspace* vs, const double* q, const double* w, int64_t n, bool uw, double wu, int slot)
+{
+    LbPass pe{};
+    pe.mode = LB_ENTROPY; pe.q = q; pe.w = w; pe.n = n; pe.f_floor = vs->f_floor;
+    pe.use_uw = uw; pe.w_uniform = wu;
+    int grid = 0;
+    VPM_CHECK(launch_lb_pass(ctx, vs, pe, &grid));
+    return launch_lb_field(ctx, vs, LBF_SCALRED | LBF_ENT, grid, 2, slot);
+}
+
+int vpm_entropy_v(vpm_vspace* vs, const double* coef_host, const double* v_dev, const double* w_dev, int64_t n, double f_floor,
+                  double* S_host, double* nfloored_host)
+{
+    VPM_REQUIRE(vs && v_dev && w_dev && n >= 0 && S_host && f_floor > 0.0, "vpm_entropy_v: bad arguments");
+    vpm_ctx* ctx = vs->ctx;
+    VPM_CUDA(cudaSetDevice(ctx->device));
+    VPM_CHECK(set_coef(vs, coef_host));
+    VPM_CHECK(grow_diag(ctx, &vs->ent, &vs->ent_cap, 2));
+    const double keep = vs->f_floor;
+    vs->f_floor = f_floor;
+    const int rc = lb_entropy_row(ctx, vs, v_dev, w_dev, n, false, 0.0, 0);
+    vs->f_floor = keep;
+    VPM_CHECK(rc);
+    double r[2];
+    VPM_CHECK(d2h(ctx, r, vs->ent, 2));
+    *S_host = r[0];
+    if (nfloored_host) *nfloored_host = r[1];
+    return VPM_OK;
+}
+
+int vpm_vspace_entropy_history(vpm_vspace* vs, int enable, double f_floor)
+{
+    VPM_REQUIRE(vs && (!enable || f_floor > 0.0), "vpm_vspace_entropy_history: bad arguments");
+    vs->want_entropy = enable != 0;
+    if (enable) vs->f_floor = f_floor;
+    vs->ent_rows = 0;
+    return VPM_OK;
+}
+
+int vpm_vspace_entropy_get(vpm_vspace* vs, double* S_host, double* nfloored_host, int rows)
+{
+    VPM_REQUIRE(vs && S_host && rows >= 0, "vpm_vspace_entropy_get: bad arguments");
+    VPM_REQUIRE(rows <= vs->ent_rows, "vpm_vspace_entropy_get: more rows requested than the last stepper call recorded");
+    if (rows == 0) return VPM_OK;
+    VPM_CUDA(cudaSetDevice(vs->ctx->device));
+    std::vector<double> tmp(2 * (size_t)rows);
+    VPM_CHECK(d2h(vs->ctx, tmp.data(), vs->ent, tmp.size()));
+    for (int i = 0; i < rows; i++) {
+        S_host[i] = tmp[2 * i];
+        if (nfloored_host) nfloored_host[i] = tmp[2 * i + 1];
+    }
+    return VPM_OK;
+}
+
 static int alloc_scratch(vpm_particles* p)
 {
     if (p->q) return VPM_OK;
@@ -1076,11 +1132,21 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
     ps.n = p->n; ps.w = p->w; ps.nu = nu; ps.dt = dt; ps.conservative = conservative;
     ps.use_uw = p->uw; ps.w_uniform = p->wu;
     ps.ka = p->ka; ps.kb = p->kb;
+    // entropy history (opt-in, vpm_vspace_entropy_history): one extra gather pass per row, right after the projection of
+    // that row's state; a leg of a longer run (vpm_lb_run) continues at row vs->ent_row0 and skips its row 0
+    const bool ent = vs->want_entropy != 0;
+    const int erow0 = ent ? vs->ent_row0 : 0;
+    if (ent) {
+        if (erow0 == 0) VPM_CHECK(grow_diag(ctx, &vs->ent, &vs->ent_cap, 2 * ((size_t)nsteps + 2)));
+        else VPM_REQUIRE(vs->ent_cap >= 2 * ((size_t)erow0 + nsteps + 1), "entropy history buffer too small for this leg");
+        vs->ent_rows = erow0 + nsteps + 1;
+    }
     {   // projection of the initial state + step-0 diagnostics
         LbPass p0 = ps;
         p0.mode = LB_DEPOSIT_ONLY; p0.q = p->v; p0.diag = 1;
         VPM_CHECK(launch_lb_pass(ctx, vs, p0, &grid));
         VPM_CHECK(launch_lb_field(ctx, vs, PROJ | LBF_SCALRED | LBF_DIAG, grid, 2, 0));
+        if (ent && erow0 == 0) VPM_CHECK(lb_entropy_row(ctx, vs, p->v, p->w, p->n, p->uw, p->wu, 0));
     }
     for (int it = 1; it <= nsteps; it++) {
         for (int s = 1; s <= 4; s++) {
@@ -1097,6 +1163,7 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
             if (s == 4) VPM_CHECK(launch_lb_field(ctx, vs, PROJ | LBF_SCALRED | LBF_DIAG, grid, 2, it));
             else VPM_CHECK(launch_lb_field(ctx, vs, PROJ, grid, 0, -1));
         }
+        if (ent) VPM_CHECK(lb_entropy_row(ctx, vs, p->v, p->w, p->n, p->uw, p->wu, erow0 + it));
     }
     return VPM_OK;
 }
@@ -1303,6 +1370,14 @@ int vpm_lb_run(vpm_vspace* vs, vpm_particles* p, double nu, double dt, double t0
     VPM_CUDA(cudaMemcpyAsync(fw.snap[0], p->v, vbytes, cudaMemcpyDeviceToDevice, ctx->stream));
     VPM_CHECK(fw.mark_ready(0));
     int done = 0;
+    if (vs->want_entropy) {   // rows of the whole run; the legs below continue at row `done`
+        VPM_CHECK(grow_diag(ctx, &vs->ent, &vs->ent_cap, 2 * ((size_t)nsteps + 2)));
+        vs->ent_row0 = 0;
+    }
+    struct EntRowReset {
+        vpm_vspace* v;
+        ~EntRowReset() { v->ent_row0 = 0; }
+    } ent_reset{vs};
     if (nsteps == 0 && diag_host) {
         VPM_CHECK(vpm_lb_rk438_steps_async(vs, p, nu, dt, 0, conservative));
         VPM_CUDA(cudaMemcpyAsync(hist.p, vs->diag, sizeof(double) * 2, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1310,6 +1385,7 @@ int vpm_lb_run(vpm_vspace* vs, vpm_particles* p, double nu, double dt, double t0
     for (int64_t f = 0; f < nframes; f++) {
         if (done < nsteps) {
             const int leg = std::min(save_stride, nsteps - done);
+            vs->ent_row0 = done;
             VPM_CHECK(vpm_lb_rk438_steps_async(vs, p, nu, dt, leg, conservative));
             if (diag_host) {
                 const int skip = done > 0 ? 1 : 0;
@@ -1369,11 +1445,12 @@ int vpm_selftest_wrap(int d)
 {
     VPM_REQUIRE(d >= 1 && d <= (1 << 20), "vpm_selftest_wrap: divisor out of range");
     const FastMod fm = make_fastmod(d);
-    auto wrap = [&](int ci) -> int {
-        if (fm.d <= 1u) return 0;
+    auto wrap = [&](int ci) -> int {   // the device code of splines.cuh, instruction for instruction
+        if ((d & (d - 1)) == 0 && (ci & (d - 1)) != (int)(((long long)ci % d + d) % d)) return -1;   // POW2 path
         const uint32_t n = (uint32_t)(ci + fm.bias);
         const uint32_t q = (uint32_t)(((uint64_t)n * fm.magic) >> 32) >> fm.shift;
-        return (int)(n - q * fm.d);
+        const uint32_t r = n - q * fm.d;
+        return (int)std::min(r, fm.d - 1u);
     };
     auto ref = [&](long long ci) -> int { long long r = ci % d; return (int)(r < 0 ? r + d : r); };
     const int lim = 1 << 30;

@@ -49,8 +49,10 @@ struct LbDev {
     double* red_partials;
     double w_uniform;
     int use_uw;
+    double f_floor;
     int stages;   // ring depth of lb_pass_ring_kernel
     int w_direct; // ring kernel: the weight stream bypasses the ring (register prefetch) so that a second stage fits
+    int late_release;  // ring kernel tuning (VPM_TUNE_LBREL=1): hand a stage back after the tile's compute and stores
 };
 
 constexpr int kRedW = 8;  // doubles per CTA row of scalar partial sums
@@ -181,6 +183,15 @@ __device__ __forceinline__ void lb_group(const LbDev& P, const int mode_rt, cons
             }
             return;
         }
+        if (mode == LB_ENTROPY) {   // S = -sum w ln max(f, floor): continuous where the projected spline is at round-off level
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                const bool low = !(f[p] > P.f_floor);
+                sums[0] = fma(-it[p].w, log(low ? P.f_floor : f[p]), sums[0]);
+                sums[1] += low ? 1.0 : 0.0;
+            }
+            return;
+        }
         if (mode == LB_MOMENTS) {
 #pragma unroll
             for (int p = 0; p < NP; p++) {
@@ -265,7 +276,7 @@ struct LbIo {
     static constexpr bool stage = MODE >= LB_STAGE1 && MODE <= LB_STAGE4;
     static constexpr bool dep = rt || MODE == LB_DEPOSIT_ONLY || stage;
     static constexpr bool rd_q = rt || !(MODE == LB_STAGE2 || MODE == LB_STAGE3);
-    static constexpr bool rd_w = dep;
+    static constexpr bool rd_w = dep || MODE == LB_ENTROPY;
     static constexpr bool rd_v0 = rt || MODE == LB_STAGE2 || MODE == LB_STAGE3;
     static constexpr bool rd_a = rt || MODE == LB_STAGE2 || MODE == LB_STAGE3 || MODE == LB_STAGE4;
     static constexpr bool rd_b = rt || MODE == LB_STAGE3;
@@ -310,7 +321,7 @@ __device__ __forceinline__ void lb_epilogue(const LbDev& P, const int mode, cons
             if (lane == 0) P.partials[(size_t)blockIdx.x * P.nbfull + b] = s;
         }
     }
-    const int nsum = mode == LB_MOMENTS ? 5 : ((P.diag && (mode == LB_DEPOSIT_ONLY || mode == LB_STAGE4)) ? 2 : 0);
+    const int nsum = mode == LB_MOMENTS ? 5 : ((mode == LB_ENTROPY || (P.diag && (mode == LB_DEPOSIT_ONLY || mode == LB_STAGE4))) ? 2 : 0);
     if (nsum) {
 #pragma unroll
         for (int k = 0; k < 5; k++) {
@@ -327,7 +338,7 @@ __device__ __forceinline__ void lb_epilogue(const LbDev& P, const int mode, cons
 }
 
 template <int K, int MODE, int VEC, int HM>
-__global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT) ? 4 : 2) lb_pass_kernel(const LbDev P)
+__global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT || MODE == LB_ENTROPY) ? 4 : 2) lb_pass_kernel(const LbDev P)
 {
     extern __shared__ __align__(16) double smem[];
     using Io = LbIo<MODE>;
@@ -356,7 +367,7 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
 
     // runtime-mode variants decide loads/stores from the mode; compile-time modes fold these
     const bool rd_q = Io::rd_q && !(mode == LB_STAGE2 || mode == LB_STAGE3);
-    const bool rd_w = Io::rd_w && dep && !P.use_uw;
+    const bool rd_w = Io::rd_w && (dep || mode == LB_ENTROPY) && !P.use_uw;
     const bool rd_v0 = Io::rd_v0 && (mode == LB_STAGE2 || mode == LB_STAGE3);
     const bool rd_a = Io::rd_a && (mode >= LB_STAGE2 && mode <= LB_STAGE4);
     const bool rd_b = Io::rd_b && mode == LB_STAGE3;
@@ -440,7 +451,7 @@ constexpr int kLbRingThreads = kBlock + 32;
 constexpr int kLbMaxStages = 8;
 
 template <int K, int MODE>
-__global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT) ? 3 : 2) lb_pass_ring_kernel(const LbDev P)
+__global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT || MODE == LB_ENTROPY) ? 3 : 2) lb_pass_ring_kernel(const LbDev P)
 {
     static_assert(MODE >= 0, "the ring variant is specialised per mode");
     extern __shared__ __align__(16) double smem[];
@@ -527,7 +538,7 @@ __global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE ==
         const double2 wa = rd_w ? *reinterpret_cast<const double2*>(src + iw * kLbTile) : wcur;
         LbItem it[2] = {{qa.x, wa.x, va.x, aa.x, ba.x}, {qa.y, wa.y, va.y, aa.y, ba.y}};
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[s]);   // this warp's operands are in registers: the stage may be refilled
+        if (lane == 0 && !P.late_release) mbar_arrive(&s_empty[s]);   // this warp's operands are in registers: the stage may be refilled
         double o1[2] = {0.0, 0.0}, o2[2] = {0.0, 0.0};
         lb_group<K, MODE, 0, 2>(P, MODE, s_tab, s_hist, it, o1, o2, sums, A1, A2);
         const long long i = g * kLbTile + 2 * tid;
@@ -536,6 +547,7 @@ __global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE ==
         if (Io::wr_b) st_stream2(P.kb + i, make_double2(it[0].b, it[1].b));
         if (wr_o1) st_stream2(P.out + i, make_double2(o1[0], o1[1]));
         if (wr_o2) st_stream2(P.out2 + i, make_double2(o2[0], o2[1]));
+        if (lane == 0 && P.late_release) mbar_arrive(&s_empty[s]);
         if (++s == P.stages) {
             s = 0;
             phase ^= 1u;
@@ -563,7 +575,7 @@ struct LbFieldDev {
     const double* partials;
     const double* red_partials;
     int nparts, phases, diag_slot, nred;
-    double *rhs, *coef, *ftab, *scal, *diag;
+    double *rhs, *coef, *ftab, *scal, *diag, *ent;
     const double *chol, *pieces;
     int nv, nbfull, ncell, K, off;
     double invh;
@@ -691,6 +703,10 @@ __global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbField
         F.diag[2 * F.diag_slot] = F.rhs[nv];
         F.diag[2 * F.diag_slot + 1] = F.rhs[nv + 1];
     }
+    if ((F.phases & LBF_ENT) && tid == 0 && F.ent && F.diag_slot >= 0) {
+        F.ent[2 * F.diag_slot] = F.rhs[nv];
+        F.ent[2 * F.diag_slot + 1] = F.rhs[nv + 1];
+    }
 }
 
 template <int K>
@@ -704,6 +720,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
     P.ftab = vs->ftab; P.scal = vs->scal; P.pieces = vs->pieces;
     P.use_uw = p.use_uw;
     P.w_uniform = p.use_uw ? p.w_uniform : 0.0;
+    P.f_floor = p.f_floor;
 
     const bool stage = p.mode >= LB_STAGE1 && p.mode <= LB_STAGE4;
     const bool dep = p.mode == LB_DEPOSIT_ONLY || stage;
@@ -726,7 +743,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
     const bool vec = al(p.q) && al(p.w) && al(p.v0) && al(p.ka) && al(p.kb) && al(p.qout) && al(p.out) && al(p.out2);
 
     void (*kern)(const LbDev) = nullptr;
-    if (p.mode < LB_DEPOSIT_ONLY || p.mode > LB_EVAL) return fail(VPM_ERR_INVALID, "bad LB pass mode");
+    if (p.mode < LB_DEPOSIT_ONLY || p.mode > LB_ENTROPY) return fail(VPM_ERR_INVALID, "bad LB pass mode");
 
     // Ring variant: size the ring to the shared memory left at the kernel's target occupancy (2 CTAs/SM beside
     // the histograms, 3 CTAs/SM for the gather-only modes).
@@ -743,7 +760,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
         if (p.mode == LB_STAGE2 || p.mode == LB_STAGE3) ns++;                    // v0
         if (p.mode >= LB_STAGE2 && p.mode <= LB_STAGE4) ns++;                    // ka
         if (p.mode == LB_STAGE3) ns++;                                           // kb
-        if (dep && !p.use_uw) ns++;                                              // w
+        if ((dep || p.mode == LB_ENTROPY) && !p.use_uw) ns++;                    // w
         const int target = dep ? 2 : 3;
         const size_t per_cta = ctx->smem_sm / target - ctx->smem_reserved;
         const size_t fixed = smem_reg + 2 * kLbMaxStages * sizeof(uint64_t);
@@ -766,6 +783,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
             smem = fixed + (size_t)stages * stage_bytes;
         }
     }
+    if (const char* e = getenv("VPM_TUNE_LBREL")) P.late_release = atoi(e);
     const int block = tma ? kLbRingThreads : kBlock;
     if (tma) switch (p.mode) {
         case LB_DEPOSIT_ONLY: kern = lb_pass_ring_kernel<K, LB_DEPOSIT_ONLY>; break;
@@ -776,6 +794,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
         case LB_RHS_OUT: kern = lb_pass_ring_kernel<K, LB_RHS_OUT>; break;
         case LB_MOMENTS: kern = lb_pass_ring_kernel<K, LB_MOMENTS>; break;
         case LB_EVAL: kern = lb_pass_ring_kernel<K, LB_EVAL>; break;
+        case LB_ENTROPY: kern = lb_pass_ring_kernel<K, LB_ENTROPY>; break;
     }
     else if (hm == 1) kern = vec ? lb_pass_kernel<K, -1, 2, 1> : lb_pass_kernel<K, -1, 1, 1>;
     else if (hm == 2) kern = vec ? lb_pass_kernel<K, -1, 2, 2> : lb_pass_kernel<K, -1, 1, 2>;
@@ -789,6 +808,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
         case LB_RHS_OUT: kern = lb_pass_kernel<K, LB_RHS_OUT, 2, 0>; break;
         case LB_MOMENTS: kern = lb_pass_kernel<K, LB_MOMENTS, 2, 0>; break;
         case LB_EVAL: kern = lb_pass_kernel<K, LB_EVAL, 2, 0>; break;
+        case LB_ENTROPY: kern = lb_pass_kernel<K, LB_ENTROPY, 2, 0>; break;
     }
     int occ = 0;
     {
@@ -834,7 +854,7 @@ int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nr
     F.partials = ctx->partials;
     F.red_partials = ctx->partials + (size_t)nparts * vs->nbfull;
     F.nparts = nparts; F.diag_slot = diag_slot; F.nred = nred;
-    F.rhs = vs->rhs; F.coef = vs->coef; F.ftab = vs->ftab; F.scal = vs->scal; F.diag = vs->diag;
+    F.rhs = vs->rhs; F.coef = vs->coef; F.ftab = vs->ftab; F.scal = vs->scal; F.diag = vs->diag; F.ent = vs->ent;
     F.chol = vs->chol; F.pieces = vs->pieces;
     F.nv = vs->nv; F.nbfull = vs->nbfull; F.ncell = vs->ncell; F.K = vs->K; F.off = vs->dirichlet ? 1 : 0;
     F.invh = vs->invh;

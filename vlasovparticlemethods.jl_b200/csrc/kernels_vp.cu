@@ -40,6 +40,7 @@ struct VpDev {
     int nbp;
     double w_uniform;
     int use_uw;
+    int late_release;   // ring kernel tuning: hand a stage back after the tile's compute and stores instead of right after the operand loads
 };
 
 template <int K>
@@ -57,7 +58,7 @@ struct HistCfg {
     static constexpr int copies = HM == 0 ? kBlock : (HM == 1 ? kBlock / 32 : 1);
 };
 
-template <int K, int FLAGS, int HM>
+template <int K, int FLAGS, int HM, bool P2 = false>
 __device__ __forceinline__ void vp_particle(const VpDev& P, const int flags_rt, const double* __restrict__ s_etab,
                                             double* __restrict__ s_hist, double& x, double& v, const double w,
                                             double& ksum, double& msum, int* dep_c = nullptr, double* dep_u = nullptr)
@@ -69,7 +70,7 @@ __device__ __forceinline__ void vp_particle(const VpDev& P, const int flags_rt, 
         int ci;
         double u;
         split_floor(x - P.lo, P.invh, ci, u);
-        const double* e = s_etab + wrap_index(ci, P.fm) * ES;
+        const double* e = s_etab + wrap_index<P2>(ci, P.fm) * ES;
         double E = e[K - 2];
 #pragma unroll
         for (int m = K - 3; m >= 0; m--) E = fma(E, u, e[m]);
@@ -88,7 +89,7 @@ __device__ __forceinline__ void vp_particle(const VpDev& P, const int flags_rt, 
         double u, b[K];
         split_floor(x - P.lo, P.invh, ci, u);
         if (HM == 3) {  // tile-sorted deposit: hand the cell and local coordinate back to the caller
-            *dep_c = wrap_index(ci, P.fm);
+            *dep_c = wrap_index<P2>(ci, P.fm);
             *dep_u = u;
             return;
         }
@@ -96,7 +97,7 @@ __device__ __forceinline__ void vp_particle(const VpDev& P, const int flags_rt, 
         // bins are unwrapped: cell c feeds bins c..c+K-1 (function c-K+1+j lives in bin c+j, folded
         // mod nh by the field kernel) -> one address computation, K immediate-offset RMWs
         constexpr int HS = HistCfg<HM>::copies;
-        double* hcell = s_hist + wrap_index(ci, P.fm) * HS;
+        double* hcell = s_hist + wrap_index<P2>(ci, P.fm) * HS;
 #pragma unroll
         for (int j = 0; j < K; j++) {
             if (HM == 0) hcell[j * HS] = fma(w, b[j], hcell[j * HS]);
@@ -305,6 +306,135 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_tma_kernel(const VpDev P
         s_red[2 * warp + 1] = msum;
     }
     __syncthreads();
+    if (tid == 0) {
+        double k = 0.0, m = 0.0;
+        for (int wi = 0; wi < kBlock / 32; wi++) {
+            k += s_red[2 * wi];
+            m += s_red[2 * wi + 1];
+        }
+        P.kin_partials[2 * blockIdx.x] = k;
+        P.kin_partials[2 * blockIdx.x + 1] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised ring variant of the fused main pass (default): kBlock worker threads plus ONE PRODUCER WARP.
+// Lane 0 of the producer waits on a stage's "empty" mbarrier (one arrival per worker warp) and re-arms it with
+// three bulk-async copies; a worker warp waits on the "full" mbarrier, copies its operands to registers, computes,
+// stores and hands the stage back -- there is no CTA-wide barrier in the loop (the __syncthreads of
+// vp_pass_tma_kernel made every tile as slow as its slowest warp) and no copy-issue code on the workers' path.
+// P2: the grid size is a power of two (periodic wrap by one AND).  Against vp_pass_tma_kernel the loop is
+// a third shorter in instructions per particle (107 -> 70 in SASS, 20 % fewer executed; profiles/r2_sass_vp_pass.txt),
+// which is what the pass needs to stay HBM-bound at the SM clock this pool's B200s sustain under load (sw_power_cap):
+// 0.621 instead of 0.651 ms per step over 5.5 s, and it draws less power, so the clock settles higher (1635 vs 1500 MHz).
+// ---------------------------------------------------------------------------------------------
+constexpr int kVpRingThreads = kBlock + 32;
+
+__device__ __forceinline__ void vp_worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory"); }
+
+template <int K, int FLAGS, int MINB, int STAGES, bool P2, bool UW>
+__global__ void __launch_bounds__(kVpRingThreads, MINB) vp_pass_ring_kernel(const VpDev P)
+{
+    extern __shared__ __align__(16) double smem[];
+    constexpr int ES = VpCfg<K>::ES;
+    constexpr bool DEP = (FLAGS & VP_DEPOSIT) != 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb = DEP ? P.nh + K - 1 : 0;
+    constexpr int nstream = UW ? 2 : 3;   // uniform weights (compile time): no w tile, a stage is two tiles
+    double* s_red = smem;
+    double* s_etab = smem + 2 * (kBlock / 32);
+    double* s_hbase = s_etab + ((P.nh * ES + 1) & ~1);
+    double* s_hist = s_hbase + tid;
+    double* s_stage = s_hbase + (size_t)nb * kBlock;                 // STAGES x {x, v, w} x kTmaTile
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_stage + (size_t)STAGES * nstream * kTmaTile);
+    uint64_t* s_empty = s_full + STAGES;
+
+    pdl_trigger();
+    for (int i = tid; i < nb * kBlock; i += kVpRingThreads) s_hbase[i] = 0.0;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], kBlock / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdl_wait();   // everything below reads what the previous kernels of the stream wrote (E table, particles)
+    for (int i = tid; i < P.nh * ES; i += kVpRingThreads) s_etab[i] = P.etab[i];
+    __syncthreads();
+
+    const long long ntiles = P.n / kTmaTile;
+    if (warp == kBlock / 32) {   // ---- producer warp
+        if (lane == 0) {
+            const uint32_t tile_bytes = kTmaTile * sizeof(double);
+            int s = 0;
+            uint32_t phase = 1;   // a fresh "empty" barrier passes a wait on parity 1: the first lap does not block
+            for (long long g = blockIdx.x; g < ntiles; g += gridDim.x) {
+                mbar_wait(&s_empty[s], phase);
+                double* dst = s_stage + (size_t)s * nstream * kTmaTile;
+                mbar_expect_tx(&s_full[s], (uint32_t)nstream * tile_bytes);
+                bulk_g2s(dst, P.x_in + g * kTmaTile, tile_bytes, &s_full[s]);
+                bulk_g2s(dst + kTmaTile, P.v_in + g * kTmaTile, tile_bytes, &s_full[s]);
+                if (!UW) bulk_g2s(dst + 2 * kTmaTile, P.w + g * kTmaTile, tile_bytes, &s_full[s]);
+                if (++s == STAGES) {
+                    s = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+        return;   // the workers synchronise among themselves (named barrier) from here on
+    }
+
+    // ---- worker warps
+    double ksum = 0.0, msum = 0.0;
+    const double2 wdef = make_double2(P.w_uniform, P.w_uniform);
+    {
+        int s = 0;
+        uint32_t phase = 0;
+        const double* src0 = s_stage + 2 * tid;
+        double* xo = P.x_out + 2 * tid;
+        double* vo = P.v_out + 2 * tid;
+        for (long long g = blockIdx.x; g < ntiles; g += gridDim.x) {
+            mbar_wait(&s_full[s], phase);
+            const double* src = src0 + (size_t)s * nstream * kTmaTile;
+            double2 xa = *reinterpret_cast<const double2*>(src);
+            double2 va = *reinterpret_cast<const double2*>(src + kTmaTile);
+            const double2 wa = UW ? wdef : *reinterpret_cast<const double2*>(src + 2 * kTmaTile);
+            __syncwarp();
+            if (lane == 0 && !P.late_release) mbar_arrive(&s_empty[s]);   // this warp's operands are in registers: the stage may be refilled
+            vp_particle<K, FLAGS, 0, P2>(P, FLAGS, s_etab, s_hist, xa.x, va.x, wa.x, ksum, msum);
+            vp_particle<K, FLAGS, 0, P2>(P, FLAGS, s_etab, s_hist, xa.y, va.y, wa.y, ksum, msum);
+            st_stream2(xo + g * kTmaTile, xa);
+            st_stream2(vo + g * kTmaTile, va);
+            if (lane == 0 && P.late_release) mbar_arrive(&s_empty[s]);
+            if (++s == STAGES) {
+                s = 0;
+                phase ^= 1u;
+            }
+        }
+    }
+    // remainder (< one tile): plain loads, spread over the grid
+    for (long long i = ntiles * kTmaTile + (long long)blockIdx.x * kBlock + tid; i < P.n; i += (long long)gridDim.x * kBlock) {
+        double x = P.x_in[i], v = P.v_in[i], w = UW ? P.w_uniform : P.w[i];
+        vp_particle<K, FLAGS, 0, P2>(P, FLAGS, s_etab, s_hist, x, v, w, ksum, msum);
+        P.x_out[i] = x;
+        P.v_out[i] = v;
+    }
+
+    vp_worker_sync();
+    for (int b = warp; b < nb; b += kBlock / 32) {  // nb == 0 without a deposit
+        double sum = 0.0;
+#pragma unroll
+        for (int t = lane; t < kBlock; t += 32) sum += s_hbase[b * kBlock + t];
+        sum = warp_sum(sum);
+        if (lane == 0) P.partials[(size_t)blockIdx.x * P.nbp + b] = sum;
+    }
+    ksum = warp_sum(ksum);
+    msum = warp_sum(msum);
+    if (lane == 0) {
+        s_red[2 * warp] = ksum;
+        s_red[2 * warp + 1] = msum;
+    }
+    vp_worker_sync();
     if (tid == 0) {
         double k = 0.0, m = 0.0;
         for (int wi = 0; wi < kBlock / 32; wi++) {
@@ -663,23 +793,44 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     }();
     void (*kern)(const VpDev) = nullptr;
     static const int tune_tma = [] {
-        const char* e = getenv("VPM_TUNE_TMA");  // 0: register-prefetch kernel, 1 (default): 2-stage bulk-async ring
-        return e ? atoi(e) : 1;
+        // 0: register-prefetch kernel; 1: two-stage bulk-async ring with a CTA barrier per tile (round 1);
+        // 5 (default): warp-specialised ring (producer warp, per-warp stage release)
+        const char* e = getenv("VPM_TUNE_TMA");
+        return e ? atoi(e) : 5;
     }();
     const bool tma = tune_tma && !tiled && hm == 0 && vec && (p.flags == kMainFlags || p.flags == kFrozenFlags);
-    if (tma && p.flags == kFrozenFlags) {  // no histograms: a deeper ring fits
-        smem += sizeof(double) * (size_t)4 * (p.use_uw ? 2 : 3) * kTmaTile + sizeof(uint64_t) * 4;
-        kern = vp_pass_tma_kernel<K, kFrozenFlags, 3, 4>;
-    } else if (tma && p.use_uw && tune_tma == 1) {
+    const bool ring = tma && tune_tma >= 5;
+    static const int tune_rel = [] {
+        // 1 (default): a worker warp hands a stage back after the tile's compute and stores; 0: right after its operand
+        // loads.  Early release keeps both stages of every CTA in flight all the time and measured SLOWER (0.631 vs 0.612
+        // ms per pass at 1e8 particles, profiles/r2_vp_pass_ab.json): the memory system is past its sweet spot there, as
+        // with deeper rings and larger carve-outs in round 1.
+        const char* e = getenv("VPM_TUNE_VPREL");
+        return e ? atoi(e) : 1;
+    }();
+    P.late_release = tune_rel;
+    const bool p2 = (xs->nh & (xs->nh - 1)) == 0;
+    const size_t tile_b = sizeof(double) * kTmaTile;
+    if (ring && p.flags == kFrozenFlags) {  // no histograms: a deeper ring fits
+        smem += 4 * (p.use_uw ? 2 : 3) * tile_b + sizeof(uint64_t) * 2 * 4;
+        kern = p.use_uw ? (p2 ? vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, true, true> : vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, false, true>)
+                        : (p2 ? vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, true, false> : vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, false, false>);
+    } else if (ring && p.use_uw) {
         // uniform weights: two tiles per stage, so a third stage fits in the shared memory of the 3-CTA/SM configuration
-        smem += sizeof(double) * (size_t)3 * 2 * kTmaTile + sizeof(uint64_t) * 3;
+        smem += 3 * 2 * tile_b + sizeof(uint64_t) * 2 * 3;
+        kern = p2 ? vp_pass_ring_kernel<K, kMainFlags, 3, 3, true, true> : vp_pass_ring_kernel<K, kMainFlags, 3, 3, false, true>;
+    } else if (ring) {
+        smem += 2 * 3 * tile_b + sizeof(uint64_t) * 2 * 2;
+        kern = p2 ? vp_pass_ring_kernel<K, kMainFlags, 3, 2, true, false> : vp_pass_ring_kernel<K, kMainFlags, 3, 2, false, false>;
+    } else if (tma && p.flags == kFrozenFlags) {
+        smem += 4 * (p.use_uw ? 2 : 3) * tile_b + sizeof(uint64_t) * 4;
+        kern = vp_pass_tma_kernel<K, kFrozenFlags, 3, 4>;
+    } else if (tma && p.use_uw) {
+        smem += 3 * 2 * tile_b + sizeof(uint64_t) * 3;
         kern = vp_pass_tma_kernel<K, kMainFlags, 3, 3>;
     } else if (tma) {
-        const int stages = (tune_tma == 2 || tune_tma == 4) ? 3 : (tune_tma == 3 ? 4 : 2);
-        smem += sizeof(double) * (size_t)stages * (p.use_uw ? 2 : 3) * kTmaTile + sizeof(uint64_t) * stages;
-        kern = tune_tma == 2 ? vp_pass_tma_kernel<K, kMainFlags, 2, 3>
-             : tune_tma == 3 ? vp_pass_tma_kernel<K, kMainFlags, 2, 4>
-             : tune_tma == 4 ? vp_pass_tma_kernel<K, kMainFlags, 3, 3> : vp_pass_tma_kernel<K, kMainFlags, 3, 2>;
+        smem += 2 * 3 * tile_b + sizeof(uint64_t) * 2;
+        kern = vp_pass_tma_kernel<K, kMainFlags, 3, 2>;
     } else if (tiled) kern = tune_tile == 1 ? vp_pass_tiled_kernel<K, 8, 2> : (tune_tile == 2 ? vp_pass_tiled_kernel<K, 4, 2> : vp_pass_tiled_kernel<K, 4, 3>);
     else if (hm == 1) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 1> : vp_pass_kernel<K, -1, 1, 3, 1>;
     else if (hm == 2) kern = vec ? vp_pass_kernel<K, -1, 2, 3, 2> : vp_pass_kernel<K, -1, 1, 3, 2>;
@@ -692,7 +843,7 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
 
     int occ = 0;
     {
-        const int rc_occ = kernel_occupancy(ctx, (const void*)kern, kBlock, smem, &occ);
+        const int rc_occ = kernel_occupancy(ctx, (const void*)kern, ring ? kVpRingThreads : kBlock, smem, &occ);
         if (rc_occ) return rc_occ;
     }
     if (occ < 1) return fail(VPM_ERR_UNSUPPORTED, "vp pass kernel does not fit on an SM");
@@ -707,7 +858,7 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     P.kin_partials = ctx->partials + (size_t)grid * nb;
 
     prof_begin(ctx, PROF_VP_PASS);
-    VPM_CUDA(launch_pdl(kern, (unsigned)grid, (unsigned)kBlock, smem, ctx->stream, P));
+    VPM_CUDA(launch_pdl(kern, (unsigned)grid, (unsigned)(ring ? kVpRingThreads : kBlock), smem, ctx->stream, P));
     prof_end(ctx);
     ctx->launches++;
     VPM_CUDA(cudaGetLastError());

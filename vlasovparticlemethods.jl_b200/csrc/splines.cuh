@@ -70,10 +70,14 @@ __device__ __forceinline__ void split_floor(double d, double invh, int& ci, doub
     u = fma(d, invh, -(tm - M));
 }
 
-// ci mod d for possibly negative ci (|ci| < 2^30), result clamped into [0,d) for safety
+// ci mod d for possibly negative ci (|ci| < 2^30), result clamped into [0,d) for safety (garbage positions -- NaN,
+// overflow -- must still index inside the shared-memory tables; d = 1 has magic 0 and relies on the clamp).
+// POW2: d is a power of two (the 16-function grid of the BASELINE configs): one AND on the two's-complement index
+// instead of the six-instruction invariant-divisor sequence; exact for every int, in range by construction.
+template <bool POW2 = false>
 __device__ __forceinline__ int wrap_index(int ci, const FastMod& fm)
 {
-    if (fm.d <= 1u) return 0;
+    if (POW2) return ci & (int)(fm.d - 1u);
     const uint32_t n = (uint32_t)(ci + fm.bias);
     const uint32_t q = __umulhi(n, fm.magic) >> fm.shift;
     const uint32_t r = n - q * fm.d;

@@ -117,6 +117,11 @@ struct vpm_vspace {
     double* scal = nullptr;    // [8] A1, A2, moments...
     double* diag = nullptr;
     size_t diag_cap = 0;
+    // entropy history (vpm_vspace_entropy_history): rows (S, floored count) of the last stepper call
+    double* ent = nullptr;
+    size_t ent_cap = 0;
+    int want_entropy = 0, ent_row0 = 0, ent_rows = 0;
+    double f_floor = 1e-14;
 };
 
 namespace vpm {
@@ -197,6 +202,7 @@ enum LbMode : int {
     LB_RHS_OUT = 5,       // write vdot to out (operator-level LB_rhs!/CLB_rhs!)
     LB_MOMENTS = 6,       // five unweighted sums of f, f' (density.jl)
     LB_EVAL = 7,          // write f(q) to out and f'(q) to out2 (gather operator)
+    LB_ENTROPY = 8,       // sums of -w ln max(f(q), f_floor) and of the floored particles (non-reference diagnostic)
 };
 
 struct LbPass {
@@ -210,13 +216,15 @@ struct LbPass {
     int diag;   // stage 4: accumulate sum v, sum v^2
     double w_uniform;
     int use_uw;
+    double f_floor;   // LB_ENTROPY
 };
 
 int launch_lb_pass(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* grid_out);
 // REDUCE: partial rows -> vs->rhs[0..nv); SCALRED: nred scalar partial sums -> vs->rhs[nv..nv+nred)
 // (both all-reduced across ranks when a communicator is attached); SOLVE: banded Cholesky rhs -> coef;
-// TABLE: coef -> per-cell f / f' polynomials; COEFF: CLB A1, A2 from the five moments; DIAG: sums -> diag row
-enum LbFieldPhase : int { LBF_REDUCE = 1, LBF_SOLVE = 2, LBF_TABLE = 4, LBF_COEFF = 8, LBF_DIAG = 16, LBF_SCALRED = 32 };
+// TABLE: coef -> per-cell f / f' polynomials; COEFF: CLB A1, A2 from the five moments; DIAG: sums -> diag row;
+// ENT: the two sums of an LB_ENTROPY pass -> entropy history row diag_slot
+enum LbFieldPhase : int { LBF_REDUCE = 1, LBF_SOLVE = 2, LBF_TABLE = 4, LBF_COEFF = 8, LBF_DIAG = 16, LBF_SCALRED = 32, LBF_ENT = 64 };
 int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nred, int diag_slot);
 
 // ---------------- misc kernels (kernels_misc.cu) ----------------
