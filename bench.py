@@ -68,6 +68,7 @@ def parse():
                          "all particles in one cell (worst case for atomics-based deposits) / cell-sorted x")
     ap.add_argument("--n-basis", type=int, default=16, help="x-space basis size (headline config: 16)")
     ap.add_argument("--order", type=int, default=4, help="spline order (headline config: 4 = cubic)")
+    ap.add_argument("--lb-nknots", type=int, default=41, help="lb / clb: knots of the v-grid (BASELINE configs: 41)")
     ap.add_argument("--field", default="selfconsistent", choices=["selfconsistent", "frozen"],
                     help="vp: self-consistent Strang loop (headline) or the frozen field of the shipped SplittingMethod")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
@@ -626,9 +627,9 @@ class Bench:
 
 
 def main():
-    global NH, ORDER
+    global NH, ORDER, LB_NKNOTS
     args = parse()
-    NH, ORDER = args.n_basis, args.order
+    NH, ORDER, LB_NKNOTS = args.n_basis, args.order, args.lb_nknots
     if args.impl == "reference":
         return run_reference(args)
 

@@ -56,7 +56,12 @@ def test_entropy_history_vs_oracle(vpm, oracle, perr, cons, tmp_path):
     assert gi.entropy.shape == (ns + 1,) and np.array_equal(gi.entropy_floored, nfo) and nfo.max() <= 5
     perr("entropy_history" + tag, np.abs(gi.entropy - eo).max() / np.abs(eo).max(), TOL)
     perr("entropy_history_v" + tag, np.linalg.norm(d.get("v") - vo) / np.linalg.norm(vo), TOL)
-    assert np.all(np.diff(gi.entropy) > 0)                  # H-theorem: the relaxation produces entropy
+    if cons:
+        assert np.all(np.diff(gi.entropy) > 0)              # H-theorem: the energy-conserving relaxation produces entropy
+    else:
+        # the plain operator, as coded upstream (lenard_bernstein.jl:28), relaxes towards the UNIT Maxwellian: the ensemble
+        # (variance 5) cools, and S falls towards ln sqrt(2 pi e) = 1.419
+        assert np.all(np.diff(gi.entropy) < 0) and gi.entropy[-1] > 0.5 * np.log(2 * np.pi * np.e)
     # the same history through the trajectory-writing driver split into legs (save_stride 3: legs of 3 + 1 steps)
     d2 = vpm.ParticleDistribution(1, 1, n).set(np.zeros(n), v, w)
     gi2 = vpm.GeometricIntegrator(model_t(d2, vpm.CollisionEntropy(sd), nu=nu), vpm.tspan_for(ns, dt), dt)

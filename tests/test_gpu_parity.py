@@ -461,3 +461,31 @@ def test_large_grids_natural(vpm, oracle, perr):
     with pytest.raises(vpm.VpmError):
         big = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, 1.0), 4, 20000))
         vpm.projection_(big, d)
+
+
+@pytest.mark.parametrize("nknots", [300, 1000])
+@pytest.mark.parametrize("cons", [False, True])
+def test_large_v_grids_tiled_deposit(vpm, oracle, perr, nknots, cons):
+    """v-grids beyond the per-thread histogram copies (> ~110 functions) deposit through lb_pass_tiled_kernel: particles
+    binned by cell inside shared memory, one owner thread per cell -- no fp64 atomics.  RK438 steps against the oracle
+    (src/distributions/spline_distribution.jl:23-36 with 300 / 1000 knots), domain ends and outside particles included."""
+    rng = np.random.default_rng(nknots)
+    n, K, ns, dt, nu = 40_003, 4, 2, 5e-3, 0.8
+    v = np.r_[rng.standard_normal(n // 2) * 0.9 + 1.5, rng.standard_normal(n - n // 2) * 1.1 - 1.2]
+    v[:6] = [-10.0, 10.0, -10.5, 11.0, -9.999, 9.999]
+    w = rng.uniform(0.5, 1.5, n) / n
+    vs = oracle.VSpace(-10.0, 10.0, nknots, K)
+    sd = vpm.SplineDistribution(1, 1, nknots, K, (-10.0, 10.0), "Dirichlet")
+    d = make_particles(vpm, np.zeros(n), v, w)
+    fs = vpm.projection(v, d, sd)
+    tag = f"@nknots{nknots}_{'clb' if cons else 'lb'}"
+    perr("v_deposit_tiled" + tag, nrm(sd.rhs, vs.deposit(v, w)), TOL)
+    tol = cond_bound(np.linalg.cond(vs.mass()), 64.0)
+    perr("v_spline_coefficients_tiled" + tag, nrm(fs.coefficients, vs.project(v, w)), tol)
+    model = (vpm.ConservativeLenardBernstein if cons else vpm.LenardBernstein)(d, vpm.CollisionEntropy(sd), nu=nu)
+    gi = vpm.GeometricIntegrator(model, vpm.tspan_for(ns, dt), dt)
+    vpm.run_(gi)
+    vo, do = vs.rk438(v, w, nu, dt, ns, conservative=cons)
+    perr("rk438_v_tiled" + tag, nrm(d.get("v"), vo), tol)
+    dscale = np.array([np.abs(v).sum(), (v * v).sum()])
+    perr("rk438_moment_history_tiled" + tag, (np.abs(gi.diagnostics[:, :2] - do) / dscale).max(), tol)

@@ -68,7 +68,15 @@ struct TabCfg {
     static constexpr int even = (K + 1) & ~1;
     static constexpr int TSP = ((even / 2) & 1) ? even : even + 2;         // padded shared-memory row stride
     static constexpr int NV2 = (K + 1) / 2;                                // double2 loads per row
+    // Gather-only passes (moments, rhs, eval, entropy) have no histograms beside the table and are bound by the
+    // bank conflicts of its look-ups (32 lanes, ~30 different cells): there the table is REPLICATED eight times,
+    // interleaved in 16-byte units by lane & 7, so that the eight lanes of every quarter-warp phase of a 16-byte
+    // load own four banks each -- conflict-free for any combination of cells (10.5 KB instead of 2 KB at 41 knots).
+    static constexpr int REP = 8;
+    static __host__ __device__ constexpr int doubles(int ncell, bool rep) { return rep ? (ncell + 1) * NV2 * REP * 2 : (ncell + 1) * TSP; }
 };
+
+constexpr bool lb_mode_gather(int mode) { return mode == LB_RHS_OUT || mode == LB_MOMENTS || mode == LB_EVAL || mode == LB_ENTROPY; }
 
 // Cell index and local coordinate of q on the clamped grid.  Fast path (0 <= t < ncell, t = (q - lo) / h): one
 // round-toward-zero fma against 2^52 leaves floor(t) in the low mantissa word, so ci and u = t - ci cost four
@@ -120,11 +128,12 @@ __device__ __forceinline__ double rk_q4(double v0, double k1, double k2, double 
 // block in which the compiler can interleave the particles' dependent fp64 chains.
 template <int K, int MODE, int HM, int NP>
 __device__ __forceinline__ void lb_group(const LbDev& P, const int mode_rt, const double* __restrict__ s_tab, double* __restrict__ s_hist,
-                                         LbItem (&it)[NP], double (&o1)[NP], double (&o2)[NP], double (&sums)[5], const double A1,
-                                         const double A2)
+                                         LbItem (&it)[NP], double (&o1)[NP], double (&o2)[NP], double (&sums)[5], const double nA1,
+                                         const double nA2, const double nuh, int* dep_c = nullptr, double* dep_u = nullptr)
 {
     constexpr int TSP = TabCfg<K>::TSP, NV2 = TabCfg<K>::NV2;
-    constexpr int HS = HistCfg<HM>::copies;
+    constexpr bool REP = lb_mode_gather(MODE);   // compile-time gather-only modes: replicated, conflict-free table
+    constexpr int HS = HM == 3 ? 1 : HistCfg<HM>::copies;
     const int mode = MODE >= 0 ? MODE : mode_rt;
     int ci[NP];
     double u[NP], qn[NP];
@@ -154,32 +163,35 @@ __device__ __forceinline__ void lb_group(const LbDev& P, const int mode_rt, cons
 #pragma unroll
             for (int p = 0; p < NP; p++) v_locate_fix(P, qe[p], ci[p], u[p]);  // outside -> zero row of the ghost cell
         }
-        double f[NP], df[NP];
+        // f and its derivative with respect to the local coordinate, dfu = h f', by Horner's rule with synthetic division
+        // (2K - 3 fused multiply-adds for both; the factor 1/h is folded into the constants of whatever consumes dfu)
+        double f[NP], dfu[NP];
 #pragma unroll
         for (int p = 0; p < NP; p++) {
-            const double2* e2 = reinterpret_cast<const double2*>(s_tab + ci[p] * TSP);
+            const double2* e2 = REP ? reinterpret_cast<const double2*>(s_tab) + ci[p] * (NV2 * TabCfg<K>::REP) + (threadIdx.x & (TabCfg<K>::REP - 1))
+                                    : reinterpret_cast<const double2*>(s_tab + ci[p] * TSP);
             double e[2 * NV2];
 #pragma unroll
             for (int i = 0; i < NV2; i++) {
-                const double2 t = e2[i];
+                const double2 t = e2[REP ? i * TabCfg<K>::REP : i];
                 e[2 * i] = t.x;
                 e[2 * i + 1] = t.y;
             }
-            double a = e[K - 1];
+            double a = e[K - 1], g = e[K - 1];
 #pragma unroll
-            for (int m = K - 2; m >= 0; m--) a = fma(a, u[p], e[m]);
-            double g = (double)(K - 1) * e[K - 1];   // f'(u) h = sum_m m f_m u^(m-1)
-#pragma unroll
-            for (int m = K - 2; m >= 1; m--) g = fma(g, u[p], (double)m * e[m]);
-            g *= P.invh;
+            for (int m = K - 2; m >= 1; m--) {
+                a = fma(a, u[p], e[m]);
+                g = fma(g, u[p], a);
+            }
+            a = fma(a, u[p], e[0]);
             f[p] = a;
-            df[p] = g;
+            dfu[p] = g;
         }
         if (mode == LB_EVAL) {
 #pragma unroll
             for (int p = 0; p < NP; p++) {
                 o1[p] = f[p];
-                o2[p] = df[p];
+                o2[p] = dfu[p] * P.invh;
             }
             return;
         }
@@ -198,15 +210,16 @@ __device__ __forceinline__ void lb_group(const LbDev& P, const int mode_rt, cons
                 sums[0] += f[p];
                 sums[1] = fma(qe[p], f[p], sums[1]);
                 sums[2] = fma(qe[p] * qe[p], f[p], sums[2]);
-                sums[3] += df[p];
-                sums[4] = fma(qe[p], df[p], sums[4]);
+                sums[3] += dfu[p];                       // both f' sums are scaled by 1/h once, in lb_epilogue
+                sums[4] = fma(qe[p], dfu[p], sums[4]);
             }
             return;
         }
 #pragma unroll
         for (int p = 0; p < NP; p++) {
-            // LB: vdot = -nu (f' + v f)    CLB: vdot = -nu (f' + (A1 + A2 v) f)    (A1 = 0, A2 = 1 for the plain model)
-            const double k = -P.nu * fma(fma(A2, qe[p], A1), f[p], df[p]);
+            // LB: vdot = -nu (f' + v f)    CLB: vdot = -nu (f' + (A1 + A2 v) f)    (A1 = 0, A2 = 1 for the plain model),
+            // with nA = -nu A and nuh = -nu / h folded by the caller: three fp64 instructions
+            const double k = fma(fma(nA2, qe[p], nA1), f[p], nuh * dfu[p]);
             if (mode == LB_RHS_OUT) {
                 o1[p] = k;
             } else if (mode == LB_STAGE1) {   // q2 = v0 + dt (k1/3)
@@ -230,6 +243,16 @@ __device__ __forceinline__ void lb_group(const LbDev& P, const int mode_rt, cons
         if (mode == LB_RHS_OUT) return;
     }
 
+    if (HM == 3) {   // tile-sorted deposit (lb_pass_tiled_kernel): hand the cell and local coordinate back; -1 = outside, deposits nothing
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            bool in = true;
+            if (v_locate_fast(P, qn[p], ci[p], u[p])) in = v_locate_fix(P, qn[p], ci[p], u[p]);
+            dep_c[p] = in ? ci[p] : -1;
+            dep_u[p] = u[p];
+        }
+        return;
+    }
     // deposit w B_j(qn) into this thread's histogram copy
     bool edge = false;
 #pragma unroll
@@ -294,14 +317,22 @@ __device__ __forceinline__ void lb_cta_sync()
     else __syncthreads();
 }
 
-// stage the f rows of the table in shared memory with the padded row stride; ghost row ncell = 0
-template <int K>
+// stage the f rows of the table in shared memory with the padded row stride (or replicated, TabCfg); ghost row ncell = 0
+template <int K, bool REP>
 __device__ __forceinline__ void lb_stage_table(const LbDev& P, double* __restrict__ s_tab, int tid, int nthreads)
 {
-    constexpr int TS = TabCfg<K>::TS, TSP = TabCfg<K>::TSP;
-    for (int i = tid; i < (P.ncell + 1) * TSP; i += nthreads) {
-        const int r = i / TSP, m = i - r * TSP;
-        s_tab[i] = (r < P.ncell && m < K) ? P.ftab[r * TS + m] : 0.0;
+    constexpr int TS = TabCfg<K>::TS, TSP = TabCfg<K>::TSP, NV2 = TabCfg<K>::NV2, R = TabCfg<K>::REP;
+    if (REP) {
+        for (int i = tid; i < (P.ncell + 1) * NV2 * R * 2; i += nthreads) {
+            const int d = i & 1, g = i / (2 * R);          // double within the 16-byte unit; unit index = row * NV2 + j
+            const int r = g / NV2, m = 2 * (g - r * NV2) + d;
+            s_tab[i] = (r < P.ncell && m < K) ? P.ftab[r * TS + m] : 0.0;
+        }
+    } else {
+        for (int i = tid; i < (P.ncell + 1) * TSP; i += nthreads) {
+            const int r = i / TSP, m = i - r * TSP;
+            s_tab[i] = (r < P.ncell && m < K) ? P.ftab[r * TS + m] : 0.0;
+        }
     }
 }
 
@@ -320,6 +351,10 @@ __device__ __forceinline__ void lb_epilogue(const LbDev& P, const int mode, cons
             s = warp_sum(s);
             if (lane == 0) P.partials[(size_t)blockIdx.x * P.nbfull + b] = s;
         }
+    }
+    if (mode == LB_MOMENTS) {
+        sums[3] *= P.invh;
+        sums[4] *= P.invh;
     }
     const int nsum = mode == LB_MOMENTS ? 5 : ((mode == LB_ENTROPY || (P.diag && (mode == LB_DEPOSIT_ONLY || mode == LB_STAGE4))) ? 2 : 0);
     if (nsum) {
@@ -348,18 +383,19 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
     const bool dep = mode == LB_DEPOSIT_ONLY || stage;
     const bool ev = mode != LB_DEPOSIT_ONLY;
     double* s_red = smem;                        // 5 * warps
-    double* s_tab = smem + 5 * (kBlock / 32);    // (ncell + 1) * TSP
+    double* s_tab = smem + 5 * (kBlock / 32);    // (ncell + 1) * TSP, or the replicated layout for the gather-only modes
     constexpr int HS = HistCfg<HM>::copies;
-    double* s_hbase = s_tab + (P.ncell + 1) * TabCfg<K>::TSP;
+    double* s_hbase = s_tab + TabCfg<K>::doubles(P.ncell, lb_mode_gather(MODE));
     double* s_hist = s_hbase + (HM == 0 ? tid : (HM == 1 ? (tid >> 5) : 0));
 
     pdl_trigger();
     if (dep)
         for (int i = tid; i < P.nbfull * HS; i += kBlock) s_hbase[i] = 0.0;
     pdl_wait();   // everything below reads what the previous kernels of the stream wrote (f table, A, stage vectors)
-    if (ev) lb_stage_table<K>(P, s_tab, tid, kBlock);
+    if (ev) lb_stage_table<K, lb_mode_gather(MODE)>(P, s_tab, tid, kBlock);
     __syncthreads();
     const double A1 = P.conservative && ev ? P.scal[0] : 0.0, A2 = P.conservative && ev ? P.scal[1] : 1.0;
+    const double nA1 = -P.nu * A1, nA2 = -P.nu * A2, nuh = -P.nu * P.invh;
 
     double sums[5] = {0, 0, 0, 0, 0};
     const long long stride = (long long)gridDim.x * kBlock;
@@ -404,7 +440,7 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
             }
             LbItem it[2] = {{qa.x, wa.x, va.x, aa.x, ba.x}, {qa.y, wa.y, va.y, aa.y, ba.y}};
             double o1[2] = {0.0, 0.0}, o2[2] = {0.0, 0.0};
-            lb_group<K, MODE, HM, 2>(P, mode, s_tab, s_hist, it, o1, o2, sums, A1, A2);
+            lb_group<K, MODE, HM, 2>(P, mode, s_tab, s_hist, it, o1, o2, sums, nA1, nA2, nuh);
             if (wr_q) st_stream2(P.qout + 2 * i, make_double2(it[0].q, it[1].q));
             if (wr_a) st_stream2(P.ka + 2 * i, make_double2(it[0].a, it[1].a));
             if (wr_b) st_stream2(P.kb + 2 * i, make_double2(it[0].b, it[1].b));
@@ -421,7 +457,7 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
         for (long long i = i0; i < P.n; i += stride) {
             LbItem it[1] = {{rd_q ? P.q[i] : 0.0, rd_w ? P.w[i] : P.w_uniform, rd_v0 ? P.v0[i] : 0.0, rd_a ? P.ka[i] : 0.0, rd_b ? P.kb[i] : 0.0}};
             double o1[1] = {0.0}, o2[1] = {0.0};
-            lb_group<K, MODE, HM, 1>(P, mode, s_tab, s_hist, it, o1, o2, sums, A1, A2);
+            lb_group<K, MODE, HM, 1>(P, mode, s_tab, s_hist, it, o1, o2, sums, nA1, nA2, nuh);
             if (wr_q) P.qout[i] = it[0].q;
             if (wr_a) P.ka[i] = it[0].a;
             if (wr_b) P.kb[i] = it[0].b;
@@ -469,8 +505,8 @@ __global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE ==
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* s_red = smem;                        // 5 * warps
-    double* s_tab = smem + 5 * (kBlock / 32);    // (ncell + 1) * TSP
-    double* s_hbase = s_tab + (P.ncell + 1) * TabCfg<K>::TSP;
+    double* s_tab = smem + 5 * (kBlock / 32);    // (ncell + 1) * TSP, or the replicated layout for the gather-only modes
+    double* s_hbase = s_tab + TabCfg<K>::doubles(P.ncell, lb_mode_gather(MODE));
     double* s_hist = s_hbase + tid;
     double* s_stage = s_hbase + (dep ? (size_t)P.nbfull * kBlock : 0);      // stages x ns x kLbTile
     uint64_t* s_full = reinterpret_cast<uint64_t*>(s_stage + (size_t)P.stages * ns * kLbTile);
@@ -487,7 +523,7 @@ __global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE ==
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     pdl_wait();   // everything below reads what the previous kernels of the stream wrote (f table, A, stage vectors)
-    if (ev) lb_stage_table<K>(P, s_tab, tid, kLbRingThreads);
+    if (ev) lb_stage_table<K, lb_mode_gather(MODE)>(P, s_tab, tid, kLbRingThreads);
     __syncthreads();
 
     const long long ntiles = P.n / kLbTile;
@@ -517,6 +553,7 @@ __global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE ==
 
     // ---- worker warps
     const double A1 = P.conservative && ev ? P.scal[0] : 0.0, A2 = P.conservative && ev ? P.scal[1] : 1.0;
+    const double nA1 = -P.nu * A1, nA2 = -P.nu * A2, nuh = -P.nu * P.invh;
     const bool wr_q = Io::wr_q && stage && P.qout != nullptr;
     const bool wr_o1 = Io::wr_o1 && P.out != nullptr;
     const bool wr_o2 = Io::wr_o2 && P.out2 != nullptr;
@@ -540,7 +577,7 @@ __global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE ==
         __syncwarp();
         if (lane == 0 && !P.late_release) mbar_arrive(&s_empty[s]);   // this warp's operands are in registers: the stage may be refilled
         double o1[2] = {0.0, 0.0}, o2[2] = {0.0, 0.0};
-        lb_group<K, MODE, 0, 2>(P, MODE, s_tab, s_hist, it, o1, o2, sums, A1, A2);
+        lb_group<K, MODE, 0, 2>(P, MODE, s_tab, s_hist, it, o1, o2, sums, nA1, nA2, nuh);
         const long long i = g * kLbTile + 2 * tid;
         if (wr_q) st_stream2(P.qout + i, make_double2(it[0].q, it[1].q));
         if (Io::wr_a) st_stream2(P.ka + i, make_double2(it[0].a, it[1].a));
@@ -557,7 +594,7 @@ __global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE ==
     for (long long i = ntiles * kLbTile + (long long)blockIdx.x * kBlock + tid; i < P.n; i += (long long)gridDim.x * kBlock) {
         LbItem it[1] = {{rd_q ? P.q[i] : 0.0, (rd_w || ld_w) ? P.w[i] : P.w_uniform, rd_v0 ? P.v0[i] : 0.0, rd_a ? P.ka[i] : 0.0, rd_b ? P.kb[i] : 0.0}};
         double o1[1] = {0.0}, o2[1] = {0.0};
-        lb_group<K, MODE, 0, 1>(P, MODE, s_tab, s_hist, it, o1, o2, sums, A1, A2);
+        lb_group<K, MODE, 0, 1>(P, MODE, s_tab, s_hist, it, o1, o2, sums, nA1, nA2, nuh);
         if (wr_q) P.qout[i] = it[0].q;
         if (Io::wr_a) P.ka[i] = it[0].a;
         if (Io::wr_b) P.kb[i] = it[0].b;
@@ -565,6 +602,164 @@ __global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE ==
         if (wr_o2) P.out2[i] = o2[0];
     }
     lb_epilogue<kBlock, true>(P, MODE, dep, s_hbase, s_red, sums);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Large v-grids (more than ~110 basis functions): per-thread histogram copies no longer fit in shared memory and fp64
+// shared-memory atomics are CAS loops (the per-warp / per-CTA fallbacks below measured ~5x slower).  Like
+// vp_pass_tiled_kernel, this variant bins each tile of particles by cell inside shared memory (counting sort on
+// native 32-bit shared atomics) and lets exactly one thread reduce each cell's segment into per-cell accumulators
+// acc[c][j] (the K basis functions alive on cell c): a segmented reduction over cell-binned particles without fp64
+// atomics.  The K-1 cells at either end of the clamped knot vector use the per-cell piece table, the interior the
+// closed-form uniform pieces; the choice is per CELL, so the owner thread never diverges inside a segment.
+// Runtime mode (deposit-only and the four RK438 stages), plain loads: this is the path of exotic grids, not of the
+// BASELINE configs.
+// ---------------------------------------------------------------------------------------------
+template <int K, int kTilePPT>
+__global__ void __launch_bounds__(kBlock, 2) lb_pass_tiled_kernel(const LbDev P)
+{
+    constexpr int kTile = kBlock * kTilePPT;
+    extern __shared__ __align__(16) double smem[];
+    const int mode = P.mode, ncell = P.ncell;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool ev = mode != LB_DEPOSIT_ONLY;
+    double* s_red = smem;                                        // 5 * warps
+    double* s_tab = smem + 5 * (kBlock / 32);                    // (ncell + 1) * TSP
+    double* s_acc = s_tab + (ncell + 1) * TabCfg<K>::TSP;        // ncell * K
+    double* s_u = s_acc + (size_t)ncell * K;                     // kTile
+    double* s_w = s_u + kTile;                                   // kTile
+    int* s_cnt = reinterpret_cast<int*>(s_w + kTile);            // ncell
+    int* s_off = s_cnt + ncell;                                  // ncell + 1
+    __shared__ int s_wsum[kBlock / 32];
+
+    pdl_trigger();
+    for (int i = tid; i < ncell * K; i += kBlock) s_acc[i] = 0.0;
+    for (int i = tid; i < ncell; i += kBlock) s_cnt[i] = 0;
+    pdl_wait();
+    if (ev) lb_stage_table<K, false>(P, s_tab, tid, kBlock);
+    __syncthreads();
+    const double A1 = P.conservative && ev ? P.scal[0] : 0.0, A2 = P.conservative && ev ? P.scal[1] : 1.0;
+    const double nA1 = -P.nu * A1, nA2 = -P.nu * A2, nuh = -P.nu * P.invh;
+
+    const bool rd_q = !(mode == LB_STAGE2 || mode == LB_STAGE3);
+    const bool rd_w = !P.use_uw;
+    const bool rd_v0 = mode == LB_STAGE2 || mode == LB_STAGE3;
+    const bool rd_a = mode >= LB_STAGE2 && mode <= LB_STAGE4;
+    const bool rd_b = mode == LB_STAGE3;
+    const bool wr_q = mode >= LB_STAGE1 && mode <= LB_STAGE4 && P.qout != nullptr;
+    const bool wr_a = mode == LB_STAGE1 || mode == LB_STAGE3;
+    const bool wr_b = mode == LB_STAGE2;
+    const int chunk = (ncell + kBlock - 1) / kBlock;             // cells scanned per thread
+
+    double sums[5] = {0, 0, 0, 0, 0};
+    for (long long base = (long long)blockIdx.x * kTile; base < P.n; base += (long long)gridDim.x * kTile) {
+        int pc[kTilePPT], pr[kTilePPT];
+        double pu[kTilePPT], pw[kTilePPT];
+        // A: stage algebra of this thread's particles; take a ticket in the cell of the value to deposit
+#pragma unroll
+        for (int k = 0; k < kTilePPT; k++) {
+            const long long i = base + (long long)k * kBlock + tid;
+            pc[k] = -1;
+            pr[k] = 0;
+            if (i < P.n) {
+                LbItem it[1] = {{rd_q ? P.q[i] : 0.0, rd_w ? P.w[i] : P.w_uniform, rd_v0 ? P.v0[i] : 0.0, rd_a ? P.ka[i] : 0.0, rd_b ? P.kb[i] : 0.0}};
+                double o1[1] = {0.0}, o2[1] = {0.0};
+                lb_group<K, -1, 3, 1>(P, mode, s_tab, nullptr, it, o1, o2, sums, nA1, nA2, nuh, &pc[k], &pu[k]);
+                pw[k] = it[0].w;
+                if (wr_q) P.qout[i] = it[0].q;
+                if (wr_a) P.ka[i] = it[0].a;
+                if (wr_b) P.kb[i] = it[0].b;
+                if (pc[k] >= 0) pr[k] = atomicAdd(&s_cnt[pc[k]], 1);
+            }
+        }
+        __syncthreads();
+        // B: exclusive scan of the counts (chunk consecutive cells per thread, warp scan, cross-warp fix-up)
+        int local = 0;
+        for (int c = tid * chunk; c < min(ncell, (tid + 1) * chunk); c++) local += s_cnt[c];
+        int incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int wi = 0; wi < warp; wi++) wbase += s_wsum[wi];
+        int run = wbase + incl - local;
+        for (int c = tid * chunk; c < min(ncell, (tid + 1) * chunk); c++) {
+            s_off[c] = run;
+            run += s_cnt[c];
+        }
+        __syncthreads();
+        // C: scatter (u, w) into cell order
+#pragma unroll
+        for (int k = 0; k < kTilePPT; k++)
+            if (pc[k] >= 0) {
+                const int pos = s_off[pc[k]] + pr[k];
+                s_u[pos] = pu[k];
+                s_w[pos] = pw[k];
+            }
+        __syncthreads();
+        // D: every cell's segment is reduced by its single owner thread; reset the counters
+        for (int c = tid; c < ncell; c += kBlock) {
+            const int beg = s_off[c], end = beg + s_cnt[c];
+            s_cnt[c] = 0;
+            if (end > beg) {
+                double acc[K];
+#pragma unroll
+                for (int j = 0; j < K; j++) acc[j] = 0.0;
+                if (c < K - 1 || c > ncell - K) {   // repeated end knots: per-cell piece table
+                    const double* pcs = P.pieces + (size_t)c * K * K;
+                    for (int q = beg; q < end; q++) {
+                        const double uu = s_u[q], w = s_w[q];
+#pragma unroll
+                        for (int j = 0; j < K; j++) {
+                            double r = __ldg(pcs + j * K + K - 1);
+#pragma unroll
+                            for (int m = K - 2; m >= 0; m--) r = fma(r, uu, __ldg(pcs + j * K + m));
+                            acc[j] = fma(r, w, acc[j]);
+                        }
+                    }
+                } else {
+                    for (int q = beg; q < end; q++) {
+                        double b[K];
+                        basis_uniform<K>(s_u[q], b);
+                        const double w = s_w[q];
+#pragma unroll
+                        for (int j = 0; j < K; j++) acc[j] = fma(b[j], w, acc[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < K; j++) s_acc[c * K + j] += acc[j];
+            }
+        }
+        __syncthreads();
+    }
+
+    // bin b = c + j collects function j of cell c
+    for (int b = tid; b < P.nbfull; b += kBlock) {
+        double sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int c = b - j;
+            if (c >= 0 && c < ncell) sum += s_acc[c * K + j];
+        }
+        P.partials[(size_t)blockIdx.x * P.nbfull + b] = sum;
+    }
+    if (P.diag && (mode == LB_DEPOSIT_ONLY || mode == LB_STAGE4)) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const double t = warp_sum(sums[k]);
+            if (lane == 0) s_red[5 * warp + k] = t;
+        }
+        __syncthreads();
+        if (tid < 2) {
+            double t = 0.0;
+            for (int wi = 0; wi < kBlock / 32; wi++) t += s_red[5 * wi + tid];
+            P.red_partials[(size_t)blockIdx.x * kRedW + tid] = t;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -724,7 +919,12 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
 
     const bool stage = p.mode >= LB_STAGE1 && p.mode <= LB_STAGE4;
     const bool dep = p.mode == LB_DEPOSIT_ONLY || stage;
-    const size_t base = sizeof(double) * (5 * (kBlock / 32) + (size_t)(vs->ncell + 1) * TabCfg<K>::TSP);
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const bool vec = al(p.q) && al(p.w) && al(p.v0) && al(p.ka) && al(p.kb) && al(p.qout) && al(p.out) && al(p.out2);
+    // the gather-only modes run mode-specialised kernels (whenever the arrays are 16-byte aligned) with the replicated table
+    // (as long as that copy stays small: large v-grids keep the compact table and the runtime-mode kernel)
+    const bool rep = lb_mode_gather(p.mode) && vec && sizeof(double) * (size_t)TabCfg<K>::doubles(vs->ncell, true) <= 40 * 1024;
+    const size_t base = sizeof(double) * (5 * (kBlock / 32) + (size_t)TabCfg<K>::doubles(vs->ncell, rep));
     int hm = 0;
     if (dep) {
         if (base + sizeof(double) * (size_t)vs->nbfull * kBlock > ctx->smem_optin) hm = 1;  // shared-memory CAS atomics are ~5x slower
@@ -739,9 +939,6 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
     if (smem_reg > ctx->smem_optin)
         return fail(VPM_ERR_UNSUPPORTED, "v-space too large: the f/f' table and one histogram copy must fit in shared memory");
 
-    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    const bool vec = al(p.q) && al(p.w) && al(p.v0) && al(p.ka) && al(p.kb) && al(p.qout) && al(p.out) && al(p.out2);
-
     void (*kern)(const LbDev) = nullptr;
     if (p.mode < LB_DEPOSIT_ONLY || p.mode > LB_ENTROPY) return fail(VPM_ERR_INVALID, "bad LB pass mode");
 
@@ -754,7 +951,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
     size_t smem = smem_reg;
     bool tma = false;
     const bool want_ring = tune_tma < 0 ? dep : ((tune_tma >> (p.mode + 1)) & 1) != 0;
-    if (hm == 0 && vec && p.n >= kLbTile && want_ring) {
+    if (hm == 0 && vec && p.n >= kLbTile && want_ring && (rep || !lb_mode_gather(p.mode))) {
         int ns = 0;
         if (!(p.mode == LB_STAGE2 || p.mode == LB_STAGE3)) ns++;                 // q
         if (p.mode == LB_STAGE2 || p.mode == LB_STAGE3) ns++;                    // v0
@@ -784,6 +981,19 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
         }
     }
     if (const char* e = getenv("VPM_TUNE_LBREL")) P.late_release = atoi(e);
+    // grids beyond the per-thread copies: tile-sorted segmented reduction (no fp64 atomics).  VPM_TUNE_HM=3 forces it
+    // on a small grid (tests), 1 / 2 select the per-warp / per-CTA CAS fallbacks instead
+    constexpr int kTilePPT = 4;
+    const size_t smem_tiled = base + sizeof(double) * ((size_t)vs->ncell * K + 2 * (size_t)kBlock * kTilePPT) + sizeof(int) * (2 * (size_t)vs->ncell + 2);
+    bool tiled = dep && hm != 0 && smem_tiled <= ctx->smem_optin;
+    if (const char* e = getenv("VPM_TUNE_HM")) {
+        if (atoi(e) == 3 && dep && smem_tiled <= ctx->smem_optin) tiled = true;
+        else if (atoi(e) != 3 && atoi(e) > 0) tiled = false;
+    }
+    if (tiled) {
+        tma = false;
+        smem = smem_tiled;
+    }
     const int block = tma ? kLbRingThreads : kBlock;
     if (tma) switch (p.mode) {
         case LB_DEPOSIT_ONLY: kern = lb_pass_ring_kernel<K, LB_DEPOSIT_ONLY>; break;
@@ -796,9 +1006,11 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
         case LB_EVAL: kern = lb_pass_ring_kernel<K, LB_EVAL>; break;
         case LB_ENTROPY: kern = lb_pass_ring_kernel<K, LB_ENTROPY>; break;
     }
+    else if (tiled) kern = lb_pass_tiled_kernel<K, kTilePPT>;
     else if (hm == 1) kern = vec ? lb_pass_kernel<K, -1, 2, 1> : lb_pass_kernel<K, -1, 1, 1>;
     else if (hm == 2) kern = vec ? lb_pass_kernel<K, -1, 2, 2> : lb_pass_kernel<K, -1, 1, 2>;
     else if (!vec) kern = lb_pass_kernel<K, -1, 1, 0>;
+    else if (lb_mode_gather(p.mode) && !rep) kern = lb_pass_kernel<K, -1, 2, 0>;
     else switch (p.mode) {
         case LB_DEPOSIT_ONLY: kern = lb_pass_kernel<K, LB_DEPOSIT_ONLY, 2, 0>; break;
         case LB_STAGE1: kern = lb_pass_kernel<K, LB_STAGE1, 2, 0>; break;
@@ -816,7 +1028,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
         if (rc_occ) return rc_occ;
     }
     if (occ < 1) return fail(VPM_ERR_UNSUPPORTED, "lb pass kernel does not fit on an SM");
-    long long want = tma ? (p.n + kLbTile - 1) / kLbTile : (p.n / (vec ? 2 : 1) + kBlock - 1) / kBlock;
+    long long want = tiled ? (p.n + kBlock * kTilePPT - 1) / (kBlock * kTilePPT) : tma ? (p.n + kLbTile - 1) / kLbTile : (p.n / (vec ? 2 : 1) + kBlock - 1) / kBlock;
     if (want < 1) want = 1;
     long long grid = (long long)ctx->sm_count * occ;
     if (grid > want) grid = want;

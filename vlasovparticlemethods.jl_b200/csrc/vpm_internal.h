@@ -65,6 +65,9 @@ struct vpm_ctx {
     vpm::P2PMailbox* p2p_local = nullptr;
     void* p2p_opened[vpm::kP2PMaxRanks] = {};
     unsigned long long p2p_seq = 0;
+    // second stream + events of the host-array entry points: chunked copies overlap the layout passes
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_events;
     uint64_t launches = 0;     // kernels launched by this library (bench "gpu_launches")
     // optional per-launch CUDA-event timing (vpm_profile): pairs of events on the launching stream
     bool profile = false;
