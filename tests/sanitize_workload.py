@@ -62,7 +62,7 @@ def main():
     nrm = lambda a, b: np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
     if "--run-h5" in sys.argv:
         return run_h5(vpm, orc, nrm)
-    n = 3 * 512 + 77
+    n = 3 * 1024 + 77
     # ---- Vlasov-Poisson: TMA main pass, prologue/epilogue passes, field kernel, both modes
     bot = vpm.BumpOnTail()
     x, v, w = orc.sample_bump_on_tail(n)
@@ -90,9 +90,12 @@ def main():
     ww = np.full(n, 1.0 / n)
     vs = orc.VSpace(-10.0, 10.0, 41, 4)
     sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
-    for env in ({"VPM_TUNE_LBTMA": "-1"}, {"VPM_TUNE_LBTMA": "0"}, {"VPM_TUNE_LBTMA": "190"}, {"VPM_TUNE_HM": "1"}, {"VPM_TUNE_HM": "2"}):
-        os.environ.pop("VPM_TUNE_LBTMA", None)
-        os.environ.pop("VPM_TUNE_HM", None)
+    # (default ring, 512-worker "fat" ring forced at this small size, register passes, ring for every mode, per-warp /
+    # per-CTA CAS fallbacks, tile-sorted deposit)
+    for env in ({"VPM_TUNE_LBTMA": "-1"}, {"VPM_TUNE_LBFAT": "2"}, {"VPM_TUNE_LBTMA": "0"}, {"VPM_TUNE_LBTMA": "1022", "VPM_TUNE_LBFAT": "0"},
+                {"VPM_TUNE_HM": "1"}, {"VPM_TUNE_HM": "2"}, {"VPM_TUNE_HM": "3"}):
+        for k in ("VPM_TUNE_LBTMA", "VPM_TUNE_HM", "VPM_TUNE_LBFAT"):
+            os.environ.pop(k, None)
         os.environ.update(env)
         for cons in (False, True):
             for uw in (False, True):
@@ -104,8 +107,25 @@ def main():
                 vpm.run_(gi)
                 vo, _ = vs.rk438(vv, ww, 0.8, 0.02, 2, conservative=cons)
                 assert np.abs(d.get("v") - vo).max() < 1e-10, (env, cons, uw)
-    os.environ.pop("VPM_TUNE_LBTMA", None)
-    os.environ.pop("VPM_TUNE_HM", None)
+    for k in ("VPM_TUNE_LBTMA", "VPM_TUNE_HM", "VPM_TUNE_LBFAT"):
+        os.environ.pop(k, None)
+    # entropy history (gather pass with the replicated table + the ENT phase of the field kernel)
+    d = vpm.ParticleDistribution(1, 1, n).set(np.zeros(n), vv, ww)
+    gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d, vpm.CollisionEntropy(sd), nu=0.8), vpm.tspan_for(2, 0.02), 0.02)
+    vpm.run_(gi, entropy=True)
+    _, _, eo, _ = vs.rk438_entropy(vv, ww, 0.8, 0.02, 2, conservative=True, f_floor=vpm.ENTROPY_FLOOR)
+    assert np.abs(gi.entropy - eo).max() < 1e-11 * np.abs(eo).max()
+    # the round-1 VP pass (CTA barrier per tile) next to the default warp-specialised ring, general and power-of-two grids
+    for env, nh in (({"VPM_TUNE_TMA": "1"}, 16), ({"VPM_TUNE_TMA": "5", "VPM_TUNE_VPREL": "0"}, 16), ({}, 17)):
+        os.environ.update(env)
+        d = vpm.ParticleDistribution(1, 1, n).set(x, v, w)
+        pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, bot.L), 4, nh))
+        m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(3, 0.1), 0.1, field="selfconsistent")
+        vpm.run_(m, diag_mode=1)
+        xo, vo, _, _ = orc.XSpace(0.0, bot.L, 4, nh).strang_selfconsistent(x, v, w, 0.1, 3)
+        assert nrm(d.get("x"), xo) < 1e-12 and nrm(d.get("v"), vo) < 1e-12, (env, nh)
+        for k in env:
+            os.environ.pop(k, None)
     # operators and samplers
     d = vpm.ParticleDistribution(1, 1, n)
     vpm.initialize_(d, vpm.DoubleMaxwellian((-10.0, 10.0), 2.0))

@@ -872,9 +872,11 @@ int vpm_vp_strang_step_host(vpm_xspace* xs, vpm_particles* p, const double* z_in
     // The two PCIe copies dominate (3.2 GB per step at 1e8 particles) and cannot overlap each other: the kick of any
     // particle needs the deposit of all.  What can overlap is the layout work: the state travels in kChunks pieces on a
     // second stream, and the AoS -> SoA pass of piece c runs while piece c + 1 is on the wire (likewise on the way out).
-    constexpr int kChunks = 8;
+    constexpr int kMaxChunks = 8;
+    int kChunks = kMaxChunks;
+    if (const char* e = getenv("VPM_TUNE_E2E_CHUNKS")) kChunks = std::min(kMaxChunks, std::max(1, atoi(e)));   // 1: no overlap (A/B)
     if (!ctx->copy_stream) VPM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    while (ctx->copy_events.size() < 2 * kChunks + 1) {
+    while (ctx->copy_events.size() < 2 * kMaxChunks + 1) {
         cudaEvent_t e;
         VPM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->copy_events.push_back(e);
@@ -882,8 +884,8 @@ int vpm_vp_strang_step_host(vpm_xspace* xs, vpm_particles* p, const double* z_in
     const int64_t piece = ((n + kChunks - 1) / kChunks + 1) & ~(int64_t)1;   // even: keeps the 16-byte alignment of every piece
     cudaStream_t cs = ctx->copy_stream;
     // the staging buffer may still be read by work enqueued earlier on the compute stream
-    VPM_CUDA(cudaEventRecord(ctx->copy_events[2 * kChunks], ctx->stream));
-    VPM_CUDA(cudaStreamWaitEvent(cs, ctx->copy_events[2 * kChunks], 0));
+    VPM_CUDA(cudaEventRecord(ctx->copy_events[2 * kMaxChunks], ctx->stream));
+    VPM_CUDA(cudaStreamWaitEvent(cs, ctx->copy_events[2 * kMaxChunks], 0));
     int c = 0;
     for (int64_t o = 0; o < n; o += piece, c++) {
         const int64_t m = std::min(piece, n - o);
@@ -897,8 +899,8 @@ int vpm_vp_strang_step_host(vpm_xspace* xs, vpm_particles* p, const double* z_in
     for (int64_t o = 0; o < n; o += piece, c++) {
         const int64_t m = std::min(piece, n - o);
         VPM_CHECK(launch_soa_to_aos(ctx, x + o, v + o, nullptr, 2, m, z + 2 * o));
-        VPM_CUDA(cudaEventRecord(ctx->copy_events[kChunks + c], ctx->stream));
-        VPM_CUDA(cudaStreamWaitEvent(cs, ctx->copy_events[kChunks + c], 0));
+        VPM_CUDA(cudaEventRecord(ctx->copy_events[kMaxChunks + c], ctx->stream));
+        VPM_CUDA(cudaStreamWaitEvent(cs, ctx->copy_events[kMaxChunks + c], 0));
         VPM_CUDA(cudaMemcpyAsync(z_out + 2 * o, z + 2 * o, sizeof(double) * 2 * m, cudaMemcpyDeviceToHost, cs));
     }
     VPM_CUDA(cudaStreamSynchronize(cs));

@@ -56,6 +56,7 @@ struct LbDev {
 };
 
 constexpr int kRedW = 8;  // doubles per CTA row of scalar partial sums
+constexpr int kLbPf = 4;  // cp.async prefetch depth of the gather-only passes (16-byte loads per thread and stream in flight)
 
 // Shared-memory copy of the per-cell table: only the K monomial coefficients of f (the coefficients of f' are
 // m f_m / h and are formed in registers: the passes are co-limited by shared-memory wavefronts, and 4 loaded
@@ -126,14 +127,14 @@ __device__ __forceinline__ double rk_q4(double v0, double k1, double k2, double 
 // out-of-domain particles, the K-1 cells at either end that feel the repeated knots) are detected for the
 // group as a whole and repaired on one shared slow path, so that the common path is a single straight-line
 // block in which the compiler can interleave the particles' dependent fp64 chains.
-template <int K, int MODE, int HM, int NP>
+template <int K, int MODE, int HM, int NP, int NWK = kBlock, bool REP = lb_mode_gather(MODE)>
 __device__ __forceinline__ void lb_group(const LbDev& P, const int mode_rt, const double* __restrict__ s_tab, double* __restrict__ s_hist,
                                          LbItem (&it)[NP], double (&o1)[NP], double (&o2)[NP], double (&sums)[5], const double nA1,
                                          const double nA2, const double nuh, int* dep_c = nullptr, double* dep_u = nullptr)
 {
     constexpr int TSP = TabCfg<K>::TSP, NV2 = TabCfg<K>::NV2;
-    constexpr bool REP = lb_mode_gather(MODE);   // compile-time gather-only modes: replicated, conflict-free table
-    constexpr int HS = HM == 3 ? 1 : HistCfg<HM>::copies;
+    // REP: replicated, conflict-free table (gather-only modes; stages 1, 2, 4 of the 512-worker ring kernel)
+    constexpr int HS = HM == 3 ? 1 : (HM == 0 ? NWK : HistCfg<HM>::copies);
     const int mode = MODE >= 0 ? MODE : mode_rt;
     int ci[NP];
     double u[NP], qn[NP];
@@ -310,10 +311,10 @@ struct LbIo {
     static constexpr bool wr_o2 = rt || MODE == LB_EVAL;
 };
 
-template <bool NAMED>
+template <bool NAMED, int NW = kBlock>
 __device__ __forceinline__ void lb_cta_sync()
 {
-    if (NAMED) asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");   // the kBlock worker threads of a ring CTA
+    if (NAMED) asm volatile("bar.sync 1, %0;" ::"n"(NW) : "memory");   // the NW worker threads of a ring CTA
     else __syncthreads();
 }
 
@@ -337,14 +338,14 @@ __device__ __forceinline__ void lb_stage_table(const LbDev& P, double* __restric
 }
 
 // Fixed-order reduction of the CTA's private histograms into one partial row, and of the scalar sums.
-template <int HS, bool NAMED>
+template <int HS, bool NAMED, int NW = kBlock>
 __device__ __forceinline__ void lb_epilogue(const LbDev& P, const int mode, const bool dep, const double* __restrict__ s_hbase,
                                             double* __restrict__ s_red, double (&sums)[5])
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (dep) {
-        lb_cta_sync<NAMED>();
-        for (int b = warp; b < P.nbfull; b += kBlock / 32) {
+        lb_cta_sync<NAMED, NW>();
+        for (int b = warp; b < P.nbfull; b += NW / 32) {
             double s = 0.0;
 #pragma unroll
             for (int t = lane; t < HS; t += 32) s += s_hbase[b * HS + t];
@@ -363,10 +364,10 @@ __device__ __forceinline__ void lb_epilogue(const LbDev& P, const int mode, cons
             const double s = warp_sum(sums[k]);
             if (lane == 0) s_red[5 * warp + k] = s;
         }
-        lb_cta_sync<NAMED>();
+        lb_cta_sync<NAMED, NW>();
         if (tid < nsum) {
             double s = 0.0;
-            for (int wi = 0; wi < kBlock / 32; wi++) s += s_red[5 * wi + tid];
+            for (int wi = 0; wi < NW / 32; wi++) s += s_red[5 * wi + tid];
             P.red_partials[(size_t)blockIdx.x * kRedW + tid] = s;
         }
     }
@@ -413,7 +414,44 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
     const bool wr_o1 = Io::wr_o1 && (mode == LB_RHS_OUT || mode == LB_EVAL) && P.out != nullptr;
     const bool wr_o2 = Io::wr_o2 && mode == LB_EVAL && P.out2 != nullptr;
 
-    if (VEC == 2) {
+    if (VEC == 2 && lb_mode_gather(MODE)) {
+        // Gather-only passes read 8 (16 with weights) bytes per particle and are bound by memory-level parallelism: one
+        // 16-byte load per thread in flight leaves the warps on the long scoreboard (ncu: 8 of 14 stall cycles per issue,
+        // DRAM at 54 %).  Each thread keeps kPf loads in flight with cp.async into its own shared-memory slots -- no
+        // registers, no barriers (a thread only ever reads the slots it filled itself).
+        const long long nvec = P.n >> 1;
+        const double2 wdef = make_double2(P.w_uniform, P.w_uniform);
+        double2* s_pq = reinterpret_cast<double2*>(s_hbase) + tid;          // [kPf][kBlock] q pairs, then the same for w
+        double2* s_pw = s_pq + kLbPf * kBlock;
+#pragma unroll
+        for (int d = 0; d < kLbPf; d++) {
+            const long long j = gtid + d * stride;
+            if (j < nvec) {
+                cp_async16(s_pq + d * kBlock, P.q + 2 * j);
+                if (rd_w) cp_async16(s_pw + d * kBlock, P.w + 2 * j);
+            }
+            cp_async_commit();
+        }
+        int slot = 0;
+        for (long long i = gtid; i < nvec; i += stride) {
+            cp_async_wait<kLbPf - 1>();   // the oldest group -- this trip's operands -- has landed
+            const double2 qa = s_pq[slot * kBlock];
+            const double2 wa = rd_w ? s_pw[slot * kBlock] : wdef;
+            const long long j = i + kLbPf * stride;
+            if (j < nvec) {
+                cp_async16(s_pq + slot * kBlock, P.q + 2 * j);
+                if (rd_w) cp_async16(s_pw + slot * kBlock, P.w + 2 * j);
+            }
+            cp_async_commit();            // one group per trip, empty or not, keeps the wait count uniform
+            LbItem it[2] = {{qa.x, wa.x, 0.0, 0.0, 0.0}, {qa.y, wa.y, 0.0, 0.0, 0.0}};
+            double o1[2] = {0.0, 0.0}, o2[2] = {0.0, 0.0};
+            lb_group<K, MODE, HM, 2>(P, mode, s_tab, s_hist, it, o1, o2, sums, nA1, nA2, nuh);
+            if (wr_o1) st_stream2(P.out + 2 * i, make_double2(o1[0], o1[1]));
+            if (wr_o2) st_stream2(P.out2 + 2 * i, make_double2(o2[0], o2[1]));
+            slot = slot + 1 == kLbPf ? 0 : slot + 1;
+        }
+        cp_async_wait<0>();
+    } else if (VEC == 2) {
         const long long nvec = P.n >> 1;
         const double2 z2 = make_double2(0, 0);
         long long i = gtid;
@@ -482,14 +520,24 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
 // 512 g + 2 t, 2 t + 1 of its CTA's tiles, so the summation order differs from lb_pass_kernel's (results agree
 // to rounding); every histogram copy and every reduction still has a fixed order: reproducible run to run.
 // ---------------------------------------------------------------------------------------------
-constexpr int kLbTile = 2 * kBlock;
-constexpr int kLbRingThreads = kBlock + 32;
+//
+// NW = 512 ("fat" variant, opt-in with VPM_TUNE_LBFAT=1; measured slower than the default, see launch_lb_pass_k): ONE CTA
+// of 16 worker warps per SM instead of two of 8.  The stage passes are bound by shared-memory bandwidth (per warp-row of particles:
+// histogram read-modify-writes 16 cycles, ring 8, table look-ups 8 + bank conflicts), and the conflicts of the table
+// look-ups -- 32 lanes in ~30 different cells -- cost another ~10 cycles.  One CTA per SM shares one table and one ring, which
+// frees the ~8 KB that the REPLICATED, conflict-free table layout (TabCfg) needs in stages 1, 2 and 4 (stage 3 is HBM-bound
+// and keeps the compact table for a deeper ring).  It also halves the partial rows the field kernel has to sum.
 constexpr int kLbMaxStages = 8;
+constexpr int kLbFat = 2 * kBlock;
 
-template <int K, int MODE>
-__global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT || MODE == LB_ENTROPY) ? 3 : 2) lb_pass_ring_kernel(const LbDev P)
+constexpr bool lb_ring_rep(int mode, int nw) { return lb_mode_gather(mode) || (nw == kLbFat && (mode == LB_STAGE1 || mode == LB_STAGE2 || mode == LB_STAGE4)); }
+
+template <int K, int MODE, int NW>
+__global__ void __launch_bounds__(NW + 32, NW == kLbFat ? 1 : ((MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT || MODE == LB_ENTROPY) ? 3 : 2)) lb_pass_ring_kernel(const LbDev P)
 {
     static_assert(MODE >= 0, "the ring variant is specialised per mode");
+    constexpr int kLbTile = 2 * NW, kLbRingThreads = NW + 32;
+    constexpr bool REP = lb_ring_rep(MODE, NW);
     extern __shared__ __align__(16) double smem[];
     using Io = LbIo<MODE>;
     constexpr bool stage = Io::stage;
@@ -505,29 +553,29 @@ __global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE ==
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* s_red = smem;                        // 5 * warps
-    double* s_tab = smem + 5 * (kBlock / 32);    // (ncell + 1) * TSP, or the replicated layout for the gather-only modes
-    double* s_hbase = s_tab + TabCfg<K>::doubles(P.ncell, lb_mode_gather(MODE));
+    double* s_tab = smem + 5 * (kLbFat / 32);    // (ncell + 1) * TSP, or the replicated layout (REP)
+    double* s_hbase = s_tab + TabCfg<K>::doubles(P.ncell, REP);
     double* s_hist = s_hbase + tid;
-    double* s_stage = s_hbase + (dep ? (size_t)P.nbfull * kBlock : 0);      // stages x ns x kLbTile
+    double* s_stage = s_hbase + (dep ? (size_t)P.nbfull * NW : 0);      // stages x ns x kLbTile
     uint64_t* s_full = reinterpret_cast<uint64_t*>(s_stage + (size_t)P.stages * ns * kLbTile);
     uint64_t* s_empty = s_full + kLbMaxStages;
 
     pdl_trigger();
     if (dep)
-        for (int i = tid; i < P.nbfull * kBlock; i += kLbRingThreads) s_hbase[i] = 0.0;
+        for (int i = tid; i < P.nbfull * NW; i += kLbRingThreads) s_hbase[i] = 0.0;
     if (tid == 0) {
         for (int s = 0; s < P.stages; s++) {
             mbar_init(&s_full[s], 1);
-            mbar_init(&s_empty[s], kBlock / 32);
+            mbar_init(&s_empty[s], NW / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     pdl_wait();   // everything below reads what the previous kernels of the stream wrote (f table, A, stage vectors)
-    if (ev) lb_stage_table<K, lb_mode_gather(MODE)>(P, s_tab, tid, kLbRingThreads);
+    if (ev) lb_stage_table<K, REP>(P, s_tab, tid, kLbRingThreads);
     __syncthreads();
 
     const long long ntiles = P.n / kLbTile;
-    if (warp == kBlock / 32) {   // ---- producer warp
+    if (warp == NW / 32) {   // ---- producer warp
         if (lane == 0) {
             const uint32_t tile_bytes = kLbTile * sizeof(double);
             int s = 0;
@@ -577,7 +625,7 @@ __global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE ==
         __syncwarp();
         if (lane == 0 && !P.late_release) mbar_arrive(&s_empty[s]);   // this warp's operands are in registers: the stage may be refilled
         double o1[2] = {0.0, 0.0}, o2[2] = {0.0, 0.0};
-        lb_group<K, MODE, 0, 2>(P, MODE, s_tab, s_hist, it, o1, o2, sums, nA1, nA2, nuh);
+        lb_group<K, MODE, 0, 2, NW, REP>(P, MODE, s_tab, s_hist, it, o1, o2, sums, nA1, nA2, nuh);
         const long long i = g * kLbTile + 2 * tid;
         if (wr_q) st_stream2(P.qout + i, make_double2(it[0].q, it[1].q));
         if (Io::wr_a) st_stream2(P.ka + i, make_double2(it[0].a, it[1].a));
@@ -591,17 +639,17 @@ __global__ void __launch_bounds__(kLbRingThreads, (MODE == LB_MOMENTS || MODE ==
         }
     }
     // remainder (< one tile): plain loads, spread over the grid
-    for (long long i = ntiles * kLbTile + (long long)blockIdx.x * kBlock + tid; i < P.n; i += (long long)gridDim.x * kBlock) {
+    for (long long i = ntiles * kLbTile + (long long)blockIdx.x * NW + tid; i < P.n; i += (long long)gridDim.x * NW) {
         LbItem it[1] = {{rd_q ? P.q[i] : 0.0, (rd_w || ld_w) ? P.w[i] : P.w_uniform, rd_v0 ? P.v0[i] : 0.0, rd_a ? P.ka[i] : 0.0, rd_b ? P.kb[i] : 0.0}};
         double o1[1] = {0.0}, o2[1] = {0.0};
-        lb_group<K, MODE, 0, 1>(P, MODE, s_tab, s_hist, it, o1, o2, sums, nA1, nA2, nuh);
+        lb_group<K, MODE, 0, 1, NW, REP>(P, MODE, s_tab, s_hist, it, o1, o2, sums, nA1, nA2, nuh);
         if (wr_q) P.qout[i] = it[0].q;
         if (Io::wr_a) P.ka[i] = it[0].a;
         if (Io::wr_b) P.kb[i] = it[0].b;
         if (wr_o1) P.out[i] = o1[0];
         if (wr_o2) P.out2[i] = o2[0];
     }
-    lb_epilogue<kBlock, true>(P, MODE, dep, s_hbase, s_red, sums);
+    lb_epilogue<NW, true, NW>(P, MODE, dep, s_hbase, s_red, sums);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -924,7 +972,8 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
     // the gather-only modes run mode-specialised kernels (whenever the arrays are 16-byte aligned) with the replicated table
     // (as long as that copy stays small: large v-grids keep the compact table and the runtime-mode kernel)
     const bool rep = lb_mode_gather(p.mode) && vec && sizeof(double) * (size_t)TabCfg<K>::doubles(vs->ncell, true) <= 40 * 1024;
-    const size_t base = sizeof(double) * (5 * (kBlock / 32) + (size_t)TabCfg<K>::doubles(vs->ncell, rep));
+    // (+ the cp.async prefetch slots of those kernels: kLbPf pairs per thread for q and for w)
+    const size_t base = sizeof(double) * (5 * (kBlock / 32) + (size_t)TabCfg<K>::doubles(vs->ncell, rep)) + (rep ? 2 * kLbPf * kBlock * sizeof(double2) : 0);
     int hm = 0;
     if (dep) {
         if (base + sizeof(double) * (size_t)vs->nbfull * kBlock > ctx->smem_optin) hm = 1;  // shared-memory CAS atomics are ~5x slower
@@ -942,42 +991,61 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
     void (*kern)(const LbDev) = nullptr;
     if (p.mode < LB_DEPOSIT_ONLY || p.mode > LB_ENTROPY) return fail(VPM_ERR_INVALID, "bad LB pass mode");
 
-    // Ring variant: size the ring to the shared memory left at the kernel's target occupancy (2 CTAs/SM beside
-    // the histograms, 3 CTAs/SM for the gather-only modes).
+    // Ring variant: size the ring to the shared memory left at the kernel's target occupancy: 2 CTAs/SM of 256 workers
+    // beside the histograms (3 CTAs/SM for the gather-only modes), or one 512-worker CTA per SM ("fat", opt-in).
     // VPM_TUNE_LBTMA (test / tuning hook): 0 = register-prefetch kernel everywhere; bit m+1 set = ring for mode m.
-    // Default: the deposit passes whose streams fit (stages 1, 2, 4, deposit-only; stage 3 with uniform weights).
+    // VPM_TUNE_LBFAT=1: the 512-worker variant where it fits (2: also for small inputs, tests).  Default 0: measured
+    // SLOWER than two 256-worker CTAs (LB 2.46 vs 2.37 ms per step, profiles/r2_lb_variants.json) -- fewer bytes in flight
+    // (32 instead of 48 KB of ring per SM) and a longer prologue / epilogue per SM outweigh the conflict-free table.
     int tune_tma = -1;
     if (const char* e = getenv("VPM_TUNE_LBTMA")) tune_tma = atoi(e);
+    int tune_fat = 0;
+    if (const char* e = getenv("VPM_TUNE_LBFAT")) tune_fat = atoi(e);
     size_t smem = smem_reg;
     bool tma = false;
+    int nw = kBlock;
     const bool want_ring = tune_tma < 0 ? dep : ((tune_tma >> (p.mode + 1)) & 1) != 0;
-    if (hm == 0 && vec && p.n >= kLbTile && want_ring && (rep || !lb_mode_gather(p.mode))) {
+    if (hm == 0 && vec && p.n >= 2 * kBlock && want_ring && (rep || !lb_mode_gather(p.mode))) {
         int ns = 0;
         if (!(p.mode == LB_STAGE2 || p.mode == LB_STAGE3)) ns++;                 // q
         if (p.mode == LB_STAGE2 || p.mode == LB_STAGE3) ns++;                    // v0
         if (p.mode >= LB_STAGE2 && p.mode <= LB_STAGE4) ns++;                    // ka
         if (p.mode == LB_STAGE3) ns++;                                           // kb
         if ((dep || p.mode == LB_ENTROPY) && !p.use_uw) ns++;                    // w
-        const int target = dep ? 2 : 3;
-        const size_t per_cta = ctx->smem_sm / target - ctx->smem_reserved;
-        const size_t fixed = smem_reg + 2 * kLbMaxStages * sizeof(uint64_t);
-        size_t stage_bytes = (size_t)ns * kLbTile * sizeof(double);
-        int stages = per_cta > fixed ? (int)((per_cta - fixed) / stage_bytes) : 0;
-        if (stages < 2 && dep && !p.use_uw && ns > 1) {
-            // a second stage fits when the weight stream bypasses the ring (prefetched in registers instead)
-            const size_t sb = (size_t)(ns - 1) * kLbTile * sizeof(double);
-            const int st2 = per_cta > fixed ? (int)((per_cta - fixed) / sb) : 0;
-            if (st2 >= 2) {
-                P.w_direct = 1;
-                stage_bytes = sb;
-                stages = st2;
+        // ring plan for a CTA of `workers` worker threads that may use `per_cta` bytes of shared memory
+        auto plan = [&](int workers, size_t per_cta, int* stages_out, int* wdirect_out, size_t* smem_out) {
+            const size_t tile = (size_t)2 * workers * sizeof(double);
+            const size_t fixed = sizeof(double) * (5 * (kLbFat / 32) + (size_t)TabCfg<K>::doubles(vs->ncell, lb_ring_rep(p.mode, workers)) +
+                                                   (dep ? (size_t)vs->nbfull * workers : 0)) + 2 * kLbMaxStages * sizeof(uint64_t);
+            size_t stage_bytes = (size_t)ns * tile;
+            int stages = per_cta > fixed ? (int)((per_cta - fixed) / stage_bytes) : 0, wdirect = 0;
+            if (stages < 2 && dep && !p.use_uw && ns > 1) {
+                // a second stage fits when the weight stream bypasses the ring (prefetched in registers instead)
+                const size_t sb = (size_t)(ns - 1) * tile;
+                const int st2 = per_cta > fixed ? (int)((per_cta - fixed) / sb) : 0;
+                if (st2 >= 2) {
+                    wdirect = 1;
+                    stage_bytes = sb;
+                    stages = st2;
+                }
             }
+            if (stages > 6) stages = 6;
+            *stages_out = stages;
+            *wdirect_out = wdirect;
+            *smem_out = fixed + (size_t)stages * stage_bytes;
+        };
+        int stages = 0, wdirect = 0;
+        size_t sm = 0;
+        if (dep && tune_fat && (tune_fat == 2 || p.n >= (int64_t)ctx->sm_count * 2 * kLbFat)) {   // 2: also for small inputs (tests)
+            plan(kLbFat, ctx->smem_optin, &stages, &wdirect, &sm);
+            if (stages >= 2) nw = kLbFat;
         }
-        if (stages > 6) stages = 6;
+        if (nw == kBlock) plan(kBlock, ctx->smem_sm / (dep ? 2 : 3) - ctx->smem_reserved, &stages, &wdirect, &sm);
         if (stages >= 1) {   // one stage is enough to stream: workers release a stage as soon as their operands are in registers
             tma = true;
             P.stages = stages;
-            smem = fixed + (size_t)stages * stage_bytes;
+            P.w_direct = wdirect;
+            smem = sm;
         }
     }
     if (const char* e = getenv("VPM_TUNE_LBREL")) P.late_release = atoi(e);
@@ -994,17 +1062,25 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
         tma = false;
         smem = smem_tiled;
     }
-    const int block = tma ? kLbRingThreads : kBlock;
-    if (tma) switch (p.mode) {
-        case LB_DEPOSIT_ONLY: kern = lb_pass_ring_kernel<K, LB_DEPOSIT_ONLY>; break;
-        case LB_STAGE1: kern = lb_pass_ring_kernel<K, LB_STAGE1>; break;
-        case LB_STAGE2: kern = lb_pass_ring_kernel<K, LB_STAGE2>; break;
-        case LB_STAGE3: kern = lb_pass_ring_kernel<K, LB_STAGE3>; break;
-        case LB_STAGE4: kern = lb_pass_ring_kernel<K, LB_STAGE4>; break;
-        case LB_RHS_OUT: kern = lb_pass_ring_kernel<K, LB_RHS_OUT>; break;
-        case LB_MOMENTS: kern = lb_pass_ring_kernel<K, LB_MOMENTS>; break;
-        case LB_EVAL: kern = lb_pass_ring_kernel<K, LB_EVAL>; break;
-        case LB_ENTROPY: kern = lb_pass_ring_kernel<K, LB_ENTROPY>; break;
+    if (!tma) nw = kBlock;
+    const int block = tma ? nw + 32 : kBlock;
+    if (tma && nw == kLbFat) switch (p.mode) {
+        case LB_DEPOSIT_ONLY: kern = lb_pass_ring_kernel<K, LB_DEPOSIT_ONLY, kLbFat>; break;
+        case LB_STAGE1: kern = lb_pass_ring_kernel<K, LB_STAGE1, kLbFat>; break;
+        case LB_STAGE2: kern = lb_pass_ring_kernel<K, LB_STAGE2, kLbFat>; break;
+        case LB_STAGE3: kern = lb_pass_ring_kernel<K, LB_STAGE3, kLbFat>; break;
+        case LB_STAGE4: kern = lb_pass_ring_kernel<K, LB_STAGE4, kLbFat>; break;
+    }
+    else if (tma) switch (p.mode) {
+        case LB_DEPOSIT_ONLY: kern = lb_pass_ring_kernel<K, LB_DEPOSIT_ONLY, kBlock>; break;
+        case LB_STAGE1: kern = lb_pass_ring_kernel<K, LB_STAGE1, kBlock>; break;
+        case LB_STAGE2: kern = lb_pass_ring_kernel<K, LB_STAGE2, kBlock>; break;
+        case LB_STAGE3: kern = lb_pass_ring_kernel<K, LB_STAGE3, kBlock>; break;
+        case LB_STAGE4: kern = lb_pass_ring_kernel<K, LB_STAGE4, kBlock>; break;
+        case LB_RHS_OUT: kern = lb_pass_ring_kernel<K, LB_RHS_OUT, kBlock>; break;
+        case LB_MOMENTS: kern = lb_pass_ring_kernel<K, LB_MOMENTS, kBlock>; break;
+        case LB_EVAL: kern = lb_pass_ring_kernel<K, LB_EVAL, kBlock>; break;
+        case LB_ENTROPY: kern = lb_pass_ring_kernel<K, LB_ENTROPY, kBlock>; break;
     }
     else if (tiled) kern = lb_pass_tiled_kernel<K, kTilePPT>;
     else if (hm == 1) kern = vec ? lb_pass_kernel<K, -1, 2, 1> : lb_pass_kernel<K, -1, 1, 1>;
@@ -1028,7 +1104,7 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
         if (rc_occ) return rc_occ;
     }
     if (occ < 1) return fail(VPM_ERR_UNSUPPORTED, "lb pass kernel does not fit on an SM");
-    long long want = tiled ? (p.n + kBlock * kTilePPT - 1) / (kBlock * kTilePPT) : tma ? (p.n + kLbTile - 1) / kLbTile : (p.n / (vec ? 2 : 1) + kBlock - 1) / kBlock;
+    long long want = tiled ? (p.n + kBlock * kTilePPT - 1) / (kBlock * kTilePPT) : tma ? (p.n + 2 * nw - 1) / (2 * nw) : (p.n / (vec ? 2 : 1) + kBlock - 1) / kBlock;
     if (want < 1) want = 1;
     long long grid = (long long)ctx->sm_count * occ;
     if (grid > want) grid = want;

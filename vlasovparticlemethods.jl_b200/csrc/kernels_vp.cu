@@ -792,7 +792,7 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
         return (v >= 2 && v <= 4) ? v : 3;
     }();
     void (*kern)(const VpDev) = nullptr;
-    static const int tune_tma = [] {
+    const int tune_tma = [] {   // (read per launch: the tests switch variants inside one process)
         // 0: register-prefetch kernel; 1: two-stage bulk-async ring with a CTA barrier per tile (round 1);
         // 5 (default): warp-specialised ring (producer warp, per-warp stage release)
         const char* e = getenv("VPM_TUNE_TMA");
@@ -800,7 +800,7 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     }();
     const bool tma = tune_tma && !tiled && hm == 0 && vec && (p.flags == kMainFlags || p.flags == kFrozenFlags);
     const bool ring = tma && tune_tma >= 5;
-    static const int tune_rel = [] {
+    const int tune_rel = [] {
         // 1 (default): a worker warp hands a stage back after the tile's compute and stores; 0: right after its operand
         // loads.  Early release keeps both stages of every CTA in flight all the time and measured SLOWER (0.631 vs 0.612
         // ms per pass at 1e8 particles, profiles/r2_vp_pass_ab.json): the memory system is past its sweet spot there, as

@@ -1,15 +1,19 @@
 // One-shot all-reduce of a small fp64 vector over NVLink peer memory, executed INSIDE the single-CTA field
 // kernels (fused compute + collective): every rank pushes its partial vector into a slot of every peer's
-// mailbox with plain stores over NVLink, publishes a sequence flag with release semantics, spins on the
-// flags that its peers wrote into its own (local) mailbox, and sums the slots in rank order — so all ranks
-// obtain bitwise-identical sums, with no NCCL launch and no extra kernel between deposit and solve.
+// mailbox with plain stores over NVLink, spins on the slots that its peers wrote into its own (local) mailbox,
+// and sums the slots in rank order -- so all ranks obtain bitwise-identical sums, with no NCCL launch and no
+// extra kernel between deposit and solve.
 //
-// The payload is 18 doubles (VP) to ~50 doubles (LB/CLB): pure latency, which is why it is a handful of
-// stores and a flag instead of a ring.  Mailboxes are double-buffered by the parity of the sequence number:
-// a rank can only run one collective ahead of the slowest rank (it needs that rank's flag to finish), so two
-// buffers are enough.  A bounded spin (about 20 s of SM clocks; VPM_P2P_TIMEOUT_MS) turns a dead peer into an
-// error instead of a hung GPU: the mailbox's error word is set (the synchronous steppers check it and return
-// VPM_ERR_COMM) and the reduced vector is poisoned with NaN so that nothing downstream can pass for a result.
+// The payload is 18 doubles (VP) to ~50 doubles (LB/CLB): pure latency.  Round 1 sent data, a system-scope
+// fence and then a separate sequence flag (two NVLink round trips and the fence's wait for every remote write).
+// This version is flag-in-data ("LL" protocol): every double travels as two 64-bit words, each carrying 32 bits
+// of the value and a 32-bit tag of the collective's sequence number.  A 64-bit store is single-copy atomic, so
+// a receiver that sees the tag in both words has the value -- no fence, no flag, one one-way trip.
+// Mailboxes are double-buffered by the parity of the sequence number: a rank can only run one collective ahead
+// of the slowest rank (it needs that rank's words to finish), so two buffers are enough.  A bounded spin (about
+// 20 s of SM clocks; VPM_P2P_TIMEOUT_MS) turns a dead peer into an error instead of a hung GPU: the mailbox's
+// error word is set (the synchronous steppers check it and return VPM_ERR_COMM) and the reduced vector is
+// poisoned with NaN so that nothing downstream can pass for a result.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -19,8 +23,7 @@ constexpr int kP2PMaxRanks = 8;
 constexpr int kP2PCap = 2048;  // doubles per slot
 
 struct P2PMailbox {
-    double data[2][kP2PMaxRanks][kP2PCap];
-    unsigned long long flag[2][kP2PMaxRanks];
+    unsigned long long ll[2][kP2PMaxRanks][2 * kP2PCap];   // low 32 bits: half of a double; high 32 bits: tag
     unsigned long long error;
 };
 
@@ -32,14 +35,14 @@ struct P2PDev {
 };
 
 #ifdef __CUDACC__
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v)
 {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p)
 {
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -49,33 +52,44 @@ __device__ __forceinline__ void p2p_allreduce(const P2PDev& c, double* buf, int 
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int par = (int)(c.seq & 1ull);
+    const unsigned long long tag = ((c.seq % 0xFFFFFFFFull) + 1ull) << 32;   // never 0: a zeroed mailbox matches nothing
     __shared__ int s_dead;
     if (tid == 0) s_dead = 0;
-    for (int r = 0; r < c.nranks; r++) {
-        double* dst = c.mbox[r]->data[par][c.rank];
-        for (int i = tid; i < count; i += nt) dst[i] = buf[i];
-    }
-    __threadfence_system();
     __syncthreads();
-    if (tid < c.nranks) st_release_sys(&c.mbox[tid]->flag[par][c.rank], c.seq);
-    if (tid < c.nranks) {
-        const unsigned long long* f = &c.mbox[c.rank]->flag[par][tid];
-        const long long t0 = clock64();
-        while (ld_acquire_sys(f) < c.seq) {
-            if (clock64() - t0 > c.timeout_cycles) {  // a peer died: flag it, poison the sum below
-                c.mbox[c.rank]->error = c.seq;
-                s_dead = 1;
-                break;
-            }
+    for (int i = tid; i < count; i += nt) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(buf[i]);
+        const unsigned long long w0 = (bits & 0xFFFFFFFFull) | tag, w1 = (bits >> 32) | tag;
+        for (int r = 0; r < c.nranks; r++) {
+            unsigned long long* dst = &c.mbox[r]->ll[par][c.rank][2 * i];
+            st_relaxed_sys(dst, w0);
+            st_relaxed_sys(dst + 1, w1);
         }
     }
-    __syncthreads();
     const P2PMailbox* mine = c.mbox[c.rank];
     for (int i = tid; i < count; i += nt) {
         double s = 0.0;
-        for (int r = 0; r < c.nranks; r++) s += __ldcv(&mine->data[par][r][i]);  // fixed rank order
-        buf[i] = s_dead ? __longlong_as_double(0x7ff8000000000000ll) : s;
+        for (int r = 0; r < c.nranks; r++) {   // fixed rank order: identical bits on every rank
+            const unsigned long long* src = &mine->ll[par][r][2 * i];
+            unsigned long long w0 = ld_relaxed_sys(src), w1 = ld_relaxed_sys(src + 1);
+            if ((w0 & 0xFFFFFFFF00000000ull) != tag || (w1 & 0xFFFFFFFF00000000ull) != tag) {
+                const long long t0 = clock64();
+                do {
+                    w0 = ld_relaxed_sys(src);
+                    w1 = ld_relaxed_sys(src + 1);
+                    if (clock64() - t0 > c.timeout_cycles) {  // a peer died: flag it, poison the sum below
+                        c.mbox[c.rank]->error = c.seq;
+                        s_dead = 1;
+                        break;
+                    }
+                } while ((w0 & 0xFFFFFFFF00000000ull) != tag || (w1 & 0xFFFFFFFF00000000ull) != tag);
+            }
+            s += __longlong_as_double((long long)((w1 << 32) | (w0 & 0xFFFFFFFFull)));
+        }
+        buf[i] = s;
     }
+    __syncthreads();
+    if (s_dead)
+        for (int i = tid; i < count; i += nt) buf[i] = __longlong_as_double(0x7ff8000000000000ll);
     __syncthreads();
 }
 #endif

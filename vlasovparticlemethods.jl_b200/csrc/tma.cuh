@@ -42,6 +42,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "memory");
 }
 
+// Per-thread asynchronous copies (cp.async, SASS LDGSTS): 16 bytes global -> shared without passing through registers,
+// completion tracked per thread in commit groups.  Used by the gather-only LB passes to keep several loads per thread
+// in flight (they are bound by memory-level parallelism: ncu shows them stalled on the long scoreboard).
+__device__ __forceinline__ void cp_async16(void* dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-serialization
 // attribute may become resident while its predecessor in the stream is still draining.  pdl_trigger() lets the
 // NEXT kernel of the stream start its prologue early; pdl_wait() blocks until the PREVIOUS kernel has completed
