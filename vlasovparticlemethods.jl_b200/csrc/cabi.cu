@@ -775,7 +775,8 @@ static int vp_steps(vpm_xspace* xs, double* x, double* v, const double* w, int64
             VPM_CHECK(launch_vp_pass(ctx, xs, pk, &grid));
             VPM_CHECK(launch_vp_field(ctx, xs, FIELD_REDUCE, grid, 0, 1, escale, wscale, -1, 0));
         }
-        ps.flags = VP_PRE | VP_KICK1 | VP_KICK2 | VP_POST1 | VP_DIAG | VP_WRITE_X | VP_WRITE_V;
+        // (K, M are accumulated only when diagnostics were asked for)
+        ps.flags = VP_PRE | VP_KICK1 | VP_KICK2 | VP_POST1 | (diag_mode ? VP_DIAG : 0) | VP_WRITE_X | VP_WRITE_V;
         ps.tau_pre = 0.5 * Dt; ps.tau_kick = 0.5 * Dt; ps.tau_post1 = 0.5 * Dt;
         for (int it = 1; it <= nsteps; it++) {
             VPM_CHECK(launch_vp_pass(ctx, xs, ps, &grid));
@@ -814,11 +815,11 @@ static int vp_steps(vpm_xspace* xs, double* x, double* v, const double* w, int64
                 VPM_CHECK(launch_vp_field(ctx, xs, ALL, grid, 1, 0, escale, wscale, -1, -1));
             }
         } else if (!last) {
-            ps.flags = VP_KICK1 | VP_POST1 | VP_DIAG | VP_POST2 | VP_DEPOSIT | VP_WRITE_X | VP_WRITE_V;
+            ps.flags = VP_KICK1 | VP_POST1 | (diag_mode ? VP_DIAG : 0) | VP_POST2 | VP_DEPOSIT | VP_WRITE_X | VP_WRITE_V;
             VPM_CHECK(launch_vp_pass(ctx, xs, ps, &grid));
-            VPM_CHECK(launch_vp_field(ctx, xs, ALL, grid, 1, 1, escale, wscale, diag_mode ? it + 1 : -1, diag_mode ? it : -1));
+            VPM_CHECK(launch_vp_field(ctx, xs, ALL, grid, 1, diag_mode ? 1 : 0, escale, wscale, diag_mode ? it + 1 : -1, diag_mode ? it : -1));
         } else {
-            ps.flags = VP_KICK1 | VP_POST1 | VP_DIAG | VP_WRITE_X | VP_WRITE_V;
+            ps.flags = VP_KICK1 | VP_POST1 | (diag_mode ? VP_DIAG : 0) | VP_WRITE_X | VP_WRITE_V;
             VPM_CHECK(launch_vp_pass(ctx, xs, ps, &grid));
             if (diag_mode) VPM_CHECK(launch_vp_field(ctx, xs, FIELD_REDUCE, grid, 0, 1, escale, wscale, -1, it));
         }

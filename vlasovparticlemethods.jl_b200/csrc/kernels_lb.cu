@@ -53,6 +53,7 @@ struct LbDev {
     int stages;   // ring depth of lb_pass_ring_kernel
     int w_direct; // ring kernel: the weight stream bypasses the ring (register prefetch) so that a second stage fits
     int late_release;  // ring kernel tuning (VPM_TUNE_LBREL=1): hand a stage back after the tile's compute and stores
+    int np4;           // gather-only passes: four particles per loop trip (default) instead of two
 };
 
 constexpr int kRedW = 8;  // doubles per CTA row of scalar partial sums
@@ -432,8 +433,42 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
             }
             cp_async_commit();
         }
+        // two trips (four particles) per iteration: the passes are short dependent fp64 chains at 8 warps per scheduler,
+        // and twice the independent chains per warp is what fills the issue slots (VPM_TUNE_LBNP=2 restores one trip)
         int slot = 0;
-        for (long long i = gtid; i < nvec; i += stride) {
+        long long i = gtid;
+        if (P.np4) {
+            for (; i + stride < nvec; i += 2 * stride) {
+                cp_async_wait<kLbPf - 2>();   // the two oldest groups -- these trips' operands -- have landed
+                const int slot1 = slot + 1 == kLbPf ? 0 : slot + 1;
+                const double2 qa = s_pq[slot * kBlock], qb = s_pq[slot1 * kBlock];
+                const double2 wa = rd_w ? s_pw[slot * kBlock] : wdef, wb = rd_w ? s_pw[slot1 * kBlock] : wdef;
+                const long long j0 = i + kLbPf * stride, j1 = j0 + stride;
+                if (j0 < nvec) {
+                    cp_async16(s_pq + slot * kBlock, P.q + 2 * j0);
+                    if (rd_w) cp_async16(s_pw + slot * kBlock, P.w + 2 * j0);
+                }
+                cp_async_commit();
+                if (j1 < nvec) {
+                    cp_async16(s_pq + slot1 * kBlock, P.q + 2 * j1);
+                    if (rd_w) cp_async16(s_pw + slot1 * kBlock, P.w + 2 * j1);
+                }
+                cp_async_commit();
+                LbItem it[4] = {{qa.x, wa.x, 0.0, 0.0, 0.0}, {qa.y, wa.y, 0.0, 0.0, 0.0}, {qb.x, wb.x, 0.0, 0.0, 0.0}, {qb.y, wb.y, 0.0, 0.0, 0.0}};
+                double o1[4] = {0.0, 0.0, 0.0, 0.0}, o2[4] = {0.0, 0.0, 0.0, 0.0};
+                lb_group<K, MODE, HM, 4>(P, mode, s_tab, s_hist, it, o1, o2, sums, nA1, nA2, nuh);
+                if (wr_o1) {
+                    st_stream2(P.out + 2 * i, make_double2(o1[0], o1[1]));
+                    st_stream2(P.out + 2 * (i + stride), make_double2(o1[2], o1[3]));
+                }
+                if (wr_o2) {
+                    st_stream2(P.out2 + 2 * i, make_double2(o2[0], o2[1]));
+                    st_stream2(P.out2 + 2 * (i + stride), make_double2(o2[2], o2[3]));
+                }
+                slot = slot1 + 1 == kLbPf ? 0 : slot1 + 1;
+            }
+        }
+        for (; i < nvec; i += stride) {
             cp_async_wait<kLbPf - 1>();   // the oldest group -- this trip's operands -- has landed
             const double2 qa = s_pq[slot * kBlock];
             const double2 wa = rd_w ? s_pw[slot * kBlock] : wdef;
@@ -1049,6 +1084,8 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
         }
     }
     if (const char* e = getenv("VPM_TUNE_LBREL")) P.late_release = atoi(e);
+    P.np4 = 1;
+    if (const char* e = getenv("VPM_TUNE_LBNP")) P.np4 = atoi(e) != 2;
     // grids beyond the per-thread copies: tile-sorted segmented reduction (no fp64 atomics).  VPM_TUNE_HM=3 forces it
     // on a small grid (tests), 1 / 2 select the per-warp / per-CTA CAS fallbacks instead
     constexpr int kTilePPT = 4;

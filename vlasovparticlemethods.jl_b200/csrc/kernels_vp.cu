@@ -50,6 +50,8 @@ struct VpCfg {
 
 constexpr int kMainFlags = VP_KICK1 | VP_POST1 | VP_DIAG | VP_POST2 | VP_DEPOSIT | VP_WRITE_X | VP_WRITE_V;
 constexpr int kFrozenFlags = VP_PRE | VP_KICK1 | VP_KICK2 | VP_POST1 | VP_DIAG | VP_WRITE_X | VP_WRITE_V;
+// the same passes for runs that asked for no diagnostics (diag_mode 0): K, M are not accumulated
+constexpr int kMainFlagsND = kMainFlags & ~VP_DIAG, kFrozenFlagsND = kFrozenFlags & ~VP_DIAG;
 
 // HM: histogram privatisation. 0 = one copy per thread (no atomics), 1 = one copy per warp, 2 = one copy per
 // CTA (shared-memory atomicAdd; for grids whose per-thread copies would not fit in shared memory)
@@ -428,6 +430,7 @@ __global__ void __launch_bounds__(kVpRingThreads, MINB) vp_pass_ring_kernel(cons
         sum = warp_sum(sum);
         if (lane == 0) P.partials[(size_t)blockIdx.x * P.nbp + b] = sum;
     }
+    if (!(FLAGS & VP_DIAG)) return;
     ksum = warp_sum(ksum);
     msum = warp_sum(msum);
     if (lane == 0) {
@@ -798,7 +801,9 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
         const char* e = getenv("VPM_TUNE_TMA");
         return e ? atoi(e) : 5;
     }();
-    const bool tma = tune_tma && !tiled && hm == 0 && vec && (p.flags == kMainFlags || p.flags == kFrozenFlags);
+    const bool nodiag = p.flags == kMainFlagsND || p.flags == kFrozenFlagsND;   // ring kernel only
+    const bool main_f = p.flags == kMainFlags || p.flags == kMainFlagsND, frozen_f = p.flags == kFrozenFlags || p.flags == kFrozenFlagsND;
+    const bool tma = tune_tma && !tiled && hm == 0 && vec && (main_f || frozen_f) && (tune_tma >= 5 || !nodiag);
     const bool ring = tma && tune_tma >= 5;
     const int tune_rel = [] {
         // 1 (default): a worker warp hands a stage back after the tile's compute and stores; 0: right after its operand
@@ -811,17 +816,21 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     P.late_release = tune_rel;
     const bool p2 = (xs->nh & (xs->nh - 1)) == 0;
     const size_t tile_b = sizeof(double) * kTmaTile;
-    if (ring && p.flags == kFrozenFlags) {  // no histograms: a deeper ring fits
+    if (ring && frozen_f) {  // no histograms: a deeper ring fits
         smem += 4 * (p.use_uw ? 2 : 3) * tile_b + sizeof(uint64_t) * 2 * 4;
-        kern = p.use_uw ? (p2 ? vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, true, true> : vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, false, true>)
-                        : (p2 ? vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, true, false> : vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, false, false>);
+        if (nodiag) kern = p.use_uw ? (p2 ? vp_pass_ring_kernel<K, kFrozenFlagsND, 3, 4, true, true> : vp_pass_ring_kernel<K, kFrozenFlagsND, 3, 4, false, true>)
+                                    : (p2 ? vp_pass_ring_kernel<K, kFrozenFlagsND, 3, 4, true, false> : vp_pass_ring_kernel<K, kFrozenFlagsND, 3, 4, false, false>);
+        else kern = p.use_uw ? (p2 ? vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, true, true> : vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, false, true>)
+                             : (p2 ? vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, true, false> : vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, false, false>);
     } else if (ring && p.use_uw) {
         // uniform weights: two tiles per stage, so a third stage fits in the shared memory of the 3-CTA/SM configuration
         smem += 3 * 2 * tile_b + sizeof(uint64_t) * 2 * 3;
-        kern = p2 ? vp_pass_ring_kernel<K, kMainFlags, 3, 3, true, true> : vp_pass_ring_kernel<K, kMainFlags, 3, 3, false, true>;
+        if (nodiag) kern = p2 ? vp_pass_ring_kernel<K, kMainFlagsND, 3, 3, true, true> : vp_pass_ring_kernel<K, kMainFlagsND, 3, 3, false, true>;
+        else kern = p2 ? vp_pass_ring_kernel<K, kMainFlags, 3, 3, true, true> : vp_pass_ring_kernel<K, kMainFlags, 3, 3, false, true>;
     } else if (ring) {
         smem += 2 * 3 * tile_b + sizeof(uint64_t) * 2 * 2;
-        kern = p2 ? vp_pass_ring_kernel<K, kMainFlags, 3, 2, true, false> : vp_pass_ring_kernel<K, kMainFlags, 3, 2, false, false>;
+        if (nodiag) kern = p2 ? vp_pass_ring_kernel<K, kMainFlagsND, 3, 2, true, false> : vp_pass_ring_kernel<K, kMainFlagsND, 3, 2, false, false>;
+        else kern = p2 ? vp_pass_ring_kernel<K, kMainFlags, 3, 2, true, false> : vp_pass_ring_kernel<K, kMainFlags, 3, 2, false, false>;
     } else if (tma && p.flags == kFrozenFlags) {
         smem += 4 * (p.use_uw ? 2 : 3) * tile_b + sizeof(uint64_t) * 4;
         kern = vp_pass_tma_kernel<K, kFrozenFlags, 3, 4>;
