@@ -53,7 +53,7 @@ struct LbDev {
     int stages;   // ring depth of lb_pass_ring_kernel
     int w_direct; // ring kernel: the weight stream bypasses the ring (register prefetch) so that a second stage fits
     int late_release;  // ring kernel tuning (VPM_TUNE_LBREL=1): hand a stage back after the tile's compute and stores
-    int np4;           // gather-only passes: four particles per loop trip (default) instead of two
+    int np4;           // gather-only passes: four particles per loop trip instead of two (tuning knob, measured neutral)
 };
 
 constexpr int kRedW = 8;  // doubles per CTA row of scalar partial sums
@@ -433,8 +433,9 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
             }
             cp_async_commit();
         }
-        // two trips (four particles) per iteration: the passes are short dependent fp64 chains at 8 warps per scheduler,
-        // and twice the independent chains per warp is what fills the issue slots (VPM_TUNE_LBNP=2 restores one trip)
+        // optional (VPM_TUNE_LBNP=4): two trips (four particles) per iteration.  Measured neutral (moments 170.6 vs 171.1 us):
+        // with the loads off the critical path the pass is issue-bound (ncu: 63 % issue slots, the rest lost to the fp64
+        // pipe's two-cycle occupancy and dispatch stalls; 2.7 ready-but-not-selected warps per issue), not ILP-bound
         int slot = 0;
         long long i = gtid;
         if (P.np4) {
@@ -1084,8 +1085,8 @@ int launch_lb_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* g
         }
     }
     if (const char* e = getenv("VPM_TUNE_LBREL")) P.late_release = atoi(e);
-    P.np4 = 1;
-    if (const char* e = getenv("VPM_TUNE_LBNP")) P.np4 = atoi(e) != 2;
+    P.np4 = 0;
+    if (const char* e = getenv("VPM_TUNE_LBNP")) P.np4 = atoi(e) == 4;
     // grids beyond the per-thread copies: tile-sorted segmented reduction (no fp64 atomics).  VPM_TUNE_HM=3 forces it
     // on a small grid (tests), 1 / 2 select the per-warp / per-CTA CAS fallbacks instead
     constexpr int kTilePPT = 4;
