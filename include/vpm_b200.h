@@ -84,8 +84,11 @@ int vpm_memcpy_d2h(vpm_ctx* ctx, double* dst_host, const double* src_dev, int64_
 int vpm_particles_create(vpm_ctx* ctx, int64_t n, vpm_particles** out);
 int vpm_particles_destroy(vpm_particles* p);
 int64_t vpm_particles_size(const vpm_particles* p);
-/* raw device pointers of the SoA arrays (valid until destroy) */
+/* raw device pointers of the SoA arrays (valid until destroy).  Asking for the WRITABLE w pointer ends a uniform-weight
+ * declaration (vpm_particles_set_uniform_weight): the caller may rewrite the weights through it.  Read-only users
+ * (operator-level calls that take v_dev / w_dev) use vpm_particles_ptrs_const, which leaves the declaration alone. */
 int vpm_particles_ptrs(vpm_particles* p, double** x, double** v, double** w);
+int vpm_particles_ptrs_const(const vpm_particles* p, const double** x, const double** v, const double** w);
 /* z: host, column-major ld x N with rows x,v[,w]; ld = 3 moves x,v,w; ld = 2 moves x,v only */
 int vpm_particles_upload_aos(vpm_particles* p, const double* z, int ld);
 int vpm_particles_download_aos(vpm_particles* p, double* z, int ld);

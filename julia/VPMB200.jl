@@ -157,9 +157,10 @@ function attach_peers!(ctx::Context, nranks::Integer, rank::Integer, allgather::
 end
 
 # ---------------------------------------------------------------------------------- seam functions
+# read-only device pointers (the writable form, vpm_particles_ptrs, ends a uniform-weight declaration)
 function ptrs(d::DeviceParticleDistribution)
     x = Ref{Ptr{Float64}}(); v = Ref{Ptr{Float64}}(); w = Ref{Ptr{Float64}}()
-    check(ccall((:vpm_particles_ptrs, libvpm), Cint, (Ptr{Cvoid}, Ref{Ptr{Float64}}, Ref{Ptr{Float64}}, Ref{Ptr{Float64}}), d.h, x, v, w))
+    check(ccall((:vpm_particles_ptrs_const, libvpm), Cint, (Ptr{Cvoid}, Ref{Ptr{Float64}}, Ref{Ptr{Float64}}, Ref{Ptr{Float64}}), d.h, x, v, w))
     x[], v[], w[]
 end
 

@@ -66,3 +66,26 @@ def test_lb_uniform_weight(vpm, oracle):
     np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-12)
     vo, do = oracle.VSpace(-10.0, 10.0, 41, 4).rk438(v, w, 1.0, 0.01, 3, conservative=True)
     assert nrm(res[1][0], vo) < 1e-11
+
+
+def test_writable_weight_pointer_ends_the_declaration(vpm, oracle):
+    """Handing out the WRITABLE w pointer (vpm_particles_ptrs) ends a uniform-weight declaration -- a caller who rewrites
+    the weights through it must not keep getting the old uniform weight from the steppers; the read-only accessor that the
+    operators use (vpm_particles_ptrs_const) leaves it alone."""
+    n = 20001
+    bot = vpm.BumpOnTail()
+    x, v, w = oracle.sample_bump_on_tail(n)
+    d = vpm.ParticleDistribution(1, 1, n).set(x, v, w)
+    d.set_uniform_weight(w[0])
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, bot.L), 4, 16))
+    vpm.projection_(pot, d)                                   # read-only pointers: declaration still active
+    xp, vp, wp = d.ptrs(writable=True)                        # the caller may now rewrite w ...
+    wnew = np.linspace(0.5, 1.5, n) * w[0]
+    lib = vpm._cabi.lib()
+    vpm.check(lib.vpm_memcpy_h2d(d.ctx._h, wp, wnew.ctypes.data, n))   # ... and does, behind the library's back
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(2, 0.1), 0.1, field="selfconsistent")
+    vpm.run_(m, diag_mode=2)
+    xs = oracle.XSpace(0.0, bot.L, 4, 16)
+    xo, vo, do, _ = xs.strang_selfconsistent(x, v, wnew, 0.1, 2)
+    xg, vg, _ = d.get()
+    assert nrm(xg, xo) < 1e-12 and nrm(vg, vo) < 1e-12

@@ -40,6 +40,7 @@ SIGNATURES = {
     "vpm_particles_destroy": (_i32, [_vp]),
     "vpm_particles_size": (_i64, [_vp]),
     "vpm_particles_ptrs": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "vpm_particles_ptrs_const": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "vpm_particles_upload_aos": (_i32, [_vp, _vp, _i32]),
     "vpm_particles_download_aos": (_i32, [_vp, _vp, _i32]),
     "vpm_particles_upload_soa": (_i32, [_vp, _vp, _vp, _vp]),

@@ -235,9 +235,12 @@ class ParticleDistribution(DistributionFunction):
     def __len__(self):
         return self.npart
 
-    def ptrs(self):
+    def ptrs(self, writable=False):
+        """raw device pointers (x, v, w).  writable=True hands out the mutable pointers and thereby ends a uniform-weight
+        declaration (the caller may rewrite w); the read-only form, used by every operator of this module, does not."""
         x, v, w = _vp(), _vp(), _vp()
-        check(_lib().vpm_particles_ptrs(self._h, C.byref(x), C.byref(v), C.byref(w)))
+        fn = _lib().vpm_particles_ptrs if writable else _lib().vpm_particles_ptrs_const
+        check(fn(self._h, C.byref(x), C.byref(v), C.byref(w)))
         return x, v, w
 
     def set(self, x=None, v=None, w=None):

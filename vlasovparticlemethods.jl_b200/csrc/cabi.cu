@@ -449,6 +449,15 @@ int vpm_particles_ptrs(vpm_particles* p, double** x, double** v, double** w)
     return VPM_OK;
 }
 
+int vpm_particles_ptrs_const(const vpm_particles* p, const double** x, const double** v, const double** w)
+{
+    VPM_REQUIRE(p, "vpm_particles_ptrs_const: p is NULL");
+    if (x) *x = p->x;
+    if (v) *v = p->v;
+    if (w) *w = p->w;
+    return VPM_OK;
+}
+
 int vpm_particles_upload_aos(vpm_particles* p, const double* z, int ld)
 {
     VPM_REQUIRE(p && z && (ld == 2 || ld == 3), "vpm_particles_upload_aos: bad arguments (ld must be 2 or 3)");

@@ -566,7 +566,14 @@ __global__ void __launch_bounds__(kBlock, (MODE == LB_MOMENTS || MODE == LB_EVAL
 constexpr int kLbMaxStages = 8;
 constexpr int kLbFat = 2 * kBlock;
 
-constexpr bool lb_ring_rep(int mode, int nw) { return lb_mode_gather(mode) || (nw == kLbFat && (mode == LB_STAGE1 || mode == LB_STAGE2 || mode == LB_STAGE4)); }
+#ifndef VPM_LB_STAGE1_REP
+#define VPM_LB_STAGE1_REP 0   // experiment: replicated table in stage 1 of the 256-worker ring (ring: q only, 3 stages; w beside it)
+#endif
+constexpr bool lb_ring_rep(int mode, int nw)
+{
+    return lb_mode_gather(mode) || (nw == kLbFat && (mode == LB_STAGE1 || mode == LB_STAGE2 || mode == LB_STAGE4)) ||
+           (VPM_LB_STAGE1_REP && nw == kBlock && mode == LB_STAGE1);
+}
 
 template <int K, int MODE, int NW>
 __global__ void __launch_bounds__(NW + 32, NW == kLbFat ? 1 : ((MODE == LB_MOMENTS || MODE == LB_EVAL || MODE == LB_RHS_OUT || MODE == LB_ENTROPY) ? 3 : 2)) lb_pass_ring_kernel(const LbDev P)
