@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvpm_b200.so")
+# VPM_B200_LIB: load another build of the same library (kernel experiments compiled with different macros)
+LIB_PATH = os.environ.get("VPM_B200_LIB") or os.path.join(_HERE, "lib", "libvpm_b200.so")
 
 VPM_OK = 0
 VP_SELFCONSISTENT = 0
