@@ -136,3 +136,41 @@ def test_julia_shim_binds_the_declared_abi():
                     assert jt == "Float64", f"{name}: '{ca}' bound as {jt}"
                 else:
                     assert jt == "Cint", f"{name}: '{ca}' bound as {jt}"
+
+
+def test_julia_shim_blocks_and_brackets_balance():
+    """No Julia parser is available; catch gross syntax slips statically: with comments and strings removed, every
+    (), [], {} closes in order, and at bracket depth 0 every block opener (function, struct, if, for, while, let, begin, try,
+    do, module, quote, macro) has its `end`."""
+    for name in ("VPMB200.jl", "parity_check.jl"):
+        src = open(os.path.join(ROOT, "julia", name)).read()
+        src = re.sub(r'"""(?:.|\n)*?"""', '""', src)
+        src = re.sub(r'"(?:\\.|[^"\\\n])*"', '""', src)
+        src = re.sub(r"#=.*?=#", "", src, flags=re.S)
+        src = re.sub(r"#[^\n]*", "", src)
+        src = re.sub(r"'(?:\\.|[^'\\\n])'", "' '", src)
+        stack, blocks = [], []
+        pairs = {")": "(", "]": "[", "}": "{"}
+        openers = {"function", "struct", "if", "for", "while", "let", "begin", "try", "do", "module", "quote", "macro"}
+        for m in re.finditer(r"[^\W\d]\w*!?|[()\[\]{}]", src):
+            tok = m.group(0)
+            if tok in "([{":
+                stack.append(tok)
+            elif tok in pairs:
+                assert stack and stack[-1] == pairs[tok], f"{name}: unbalanced '{tok}' at offset {m.start()}"
+                stack.pop()
+            elif not stack:
+                prev = src[max(0, m.start() - 1):m.start()]
+                if prev == ":" or prev == ".":          # :end / :function symbols, field access
+                    continue
+                if tok in openers:
+                    if tok == "struct" and blocks and blocks[-1][0] == "mutable":
+                        blocks.pop()
+                    blocks.append((tok, m.start()))
+                elif tok == "mutable":
+                    blocks.append((tok, m.start()))
+                elif tok == "end":
+                    assert blocks, f"{name}: 'end' without an open block at offset {m.start()}"
+                    blocks.pop()
+        assert not stack, f"{name}: unclosed bracket {stack[-1]}"
+        assert not blocks, f"{name}: unclosed block {blocks[-1]}"
