@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, nper, out_dir, comm):
+def _worker(rank, world, port, nper, out_dir, comm, sort):
     import sys
     sys.path.insert(0, ROOT)
     import torch
@@ -35,6 +35,7 @@ def _worker(rank, world, port, nper, out_dir, comm):
     dev = rank % torch.cuda.device_count()
     torch.cuda.set_device(dev)
     os.environ["VPM_P2P_TIMEOUT_MS"] = "15000"    # a stuck peer fails the test instead of spinning for long
+    os.environ["VPM_TUNE_LBSORT"] = sort          # 2: velocity-sorted collision passes (all-reduce of the per-cell power sums), 0: histogram passes
     ctx = vpm.Context(dev)
     if comm == "nccl":
         obj = [vpm.Context.comm_unique_id() if rank == 0 else None]
@@ -70,15 +71,15 @@ def _worker(rank, world, port, nper, out_dir, comm):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("comm", ["p2p", "nccl"])
-def test_two_rank_slabs_match_single_gpu(tmp_path, perr, comm):
+@pytest.mark.parametrize("comm,sort", [("p2p", "2"), ("p2p", "0"), ("nccl", "2")])
+def test_two_rank_slabs_match_single_gpu(tmp_path, perr, comm, sort):
     import torch
     if torch.cuda.device_count() < 2 and comm == "nccl":
         pytest.skip("NCCL needs one GPU per rank (run with gpurun --gpus 2); the p2p variant runs on one GPU")
     import torch.multiprocessing as mp
     import vpm_b200 as vpm
     world, nper = 2, 150001
-    mp.spawn(_worker, args=(world, _free_port(), nper, str(tmp_path), comm), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), nper, str(tmp_path), comm, sort), nprocs=world, join=True)
     r = [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
     np.testing.assert_array_equal(r[0]["phi"], r[1]["phi"])      # replicated solve on identical input
     np.testing.assert_array_equal(r[0]["diag"], r[1]["diag"])
@@ -90,7 +91,7 @@ def test_two_rank_slabs_match_single_gpu(tmp_path, perr, comm):
     m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(5, 0.1), 0.1, field="selfconsistent")
     vpm.run_(m, diag_mode=2)
     x, v, _ = d.get()
-    tag = "@" + comm
+    tag = "@" + comm + "_sort" + sort
     perr("two_rank_x" + tag, nrm(np.concatenate([r[0]["x"], r[1]["x"]]), x), 1e-12)
     perr("two_rank_v" + tag, nrm(np.concatenate([r[0]["v"], r[1]["v"]]), v), 1e-12)
     perr("two_rank_solved_field" + tag, nrm(r[0]["phi"], pot.coefficients), 1e-12)

@@ -431,6 +431,7 @@ int vpm_particles_destroy(vpm_particles* p)
     cudaStreamSynchronize(p->ctx->stream);
     cudaFree(p->x); cudaFree(p->v); cudaFree(p->w);
     cudaFree(p->q); cudaFree(p->ka); cudaFree(p->kb);
+    cudaFree(p->sv); cudaFree(p->sw); cudaFree(p->sinv); cudaFree(p->sort_counts);
     delete p;
     return VPM_OK;
 }
@@ -445,6 +446,11 @@ int vpm_particles_ptrs(vpm_particles* p, double** x, double** v, double** w)
     if (w) {
         *w = p->w;
         p->uw = false;   // the caller may rewrite the weights through this pointer: the uniform-weight declaration ends here
+    }
+    // ... or the velocities, at any later time: the velocity-sorted mirror of the collision steppers is rebuilt at every call from now on
+    if (v || w) {
+        p->exposed = true;
+        p->mirror_valid = false;
     }
     return VPM_OK;
 }
@@ -471,6 +477,7 @@ int vpm_particles_upload_aos(vpm_particles* p, const double* z, int ld)
         VPM_CHECK(launch_aos_to_soa(ctx, ctx->staging, ld, m, p->x + o, p->v + o, ld == 3 ? p->w + o : nullptr));
     }
     if (ld == 3) p->uw = false;
+    p->mirror_valid = false;
     VPM_CUDA(cudaStreamSynchronize(ctx->stream));
     return VPM_OK;
 }
@@ -503,6 +510,7 @@ int vpm_particles_upload_soa(vpm_particles* p, const double* x, const double* v,
         VPM_CUDA(cudaMemcpyAsync(p->w, w, bytes, cudaMemcpyHostToDevice, ctx->stream));
         p->uw = false;
     }
+    if (v || w) p->mirror_valid = false;
     VPM_CUDA(cudaStreamSynchronize(ctx->stream));
     return VPM_OK;
 }
@@ -525,6 +533,7 @@ int vpm_particles_set_uniform_weight(vpm_particles* p, double w)
     VPM_REQUIRE(p && std::isfinite(w), "vpm_particles_set_uniform_weight: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
     VPM_CHECK(launch_fill(p->ctx, p->w, p->n, w));
+    p->mirror_valid = false;
     p->uw = true;
     p->wu = w;
     return VPM_OK;
@@ -536,6 +545,7 @@ int vpm_sample_bump_on_tail(vpm_particles* p, int64_t offset, int64_t ntotal, ui
     VPM_REQUIRE(p && ntotal > 0 && kappa > 0, "vpm_sample_bump_on_tail: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
     p->uw = false;
+    p->mirror_valid = false;
     return launch_sample_bump_on_tail(p->ctx, p, offset, ntotal, seed, eps, kappa, alpha, sigma, v0);
 }
 
@@ -545,6 +555,7 @@ int vpm_sample_normal(vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t
     VPM_REQUIRE(p && ntotal > 0 && xhi > xlo, "vpm_sample_normal: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
     p->uw = false;
+    p->mirror_valid = false;
     return launch_sample_normal(p->ctx, p, offset, ntotal, seed, xlo, xhi, xmax, xmax_used);
 }
 
@@ -554,6 +565,7 @@ int vpm_sample_maxwellian(vpm_particles* p, int64_t offset, int64_t ntotal, uint
     VPM_REQUIRE(p && ntotal > 0, "vpm_sample_maxwellian: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
     p->uw = false;
+    p->mirror_valid = false;
     return launch_sample_maxwellian(p->ctx, p, offset, ntotal, seed, xlo, xhi, shift, doubled, wnum);
 }
 
@@ -563,6 +575,7 @@ int vpm_sample_uniform(vpm_particles* p, int64_t offset, int64_t ntotal, uint64_
     VPM_REQUIRE(p && ntotal > 0, "vpm_sample_uniform: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
     p->uw = false;
+    p->mirror_valid = false;
     return launch_sample_uniform(p->ctx, p, offset, ntotal, seed, xlo, xhi, vlo, vhi, shift, wnum);
 }
 
@@ -724,6 +737,7 @@ int vpm_push_kick(vpm_xspace* xs, vpm_particles* p, const double* phi_host, doub
     VPM_CHECK(launch_vp_field(ctx, xs, FIELD_TABLE, 0, 0, 0, -scale, 1.0, -1, -1));
     VpPass ps{};
     ps.x_in = p->x; ps.v_in = p->v; ps.w = p->w; ps.v_out = p->v; ps.n = p->n;
+    p->mirror_valid = false;
     ps.flags = VP_KICK1 | VP_WRITE_V;
     ps.tau_kick = tau;
     return launch_vp_pass(ctx, xs, ps, nullptr);
@@ -847,6 +861,7 @@ int vpm_vp_strang_steps_async(vpm_xspace* xs, vpm_particles* p, double dt, doubl
         // the deposit positions are the particles' positions at call time; the pass that computes the field
         // runs before any push on the same stream, so no copy is needed
     }
+    p->mirror_valid = false;   // the kick changes v
     return vp_steps(xs, p->x, p->v, p->w, p->n, xdep, p->w, p->n, dt, chi, nsteps, mode, diag_mode, p->uw, p->wu);
 }
 
@@ -946,8 +961,9 @@ int vpm_vspace_create(vpm_ctx* ctx, double lo, double hi, int nknots, int order,
     }
     const int TS = 2 * order - 1;
     std::vector<double> z1((size_t)vs->nv + 8, 0.0), z2((size_t)vs->nv, 0.0), z3((size_t)vs->ncell * TS, 0.0), z4(8, 0.0);
+    std::vector<double> z5((size_t)vs->ncell * (2 * order + 2) + 8, 0.0);
     int rc = VPM_OK;
-    if ((rc = upload(ctx, &vs->pieces, pieces)) || (rc = upload(ctx, &vs->chol, vs->chol_host)) || (rc = upload(ctx, &vs->rhs, z1)) ||
+    if ((rc = upload(ctx, &vs->psum, z5)) || (rc = upload(ctx, &vs->pieces, pieces)) || (rc = upload(ctx, &vs->chol, vs->chol_host)) || (rc = upload(ctx, &vs->rhs, z1)) ||
         (rc = upload(ctx, &vs->coef, z2)) || (rc = upload(ctx, &vs->ftab, z3)) || (rc = upload(ctx, &vs->scal, z4))) {
         vpm_vspace_destroy(vs);
         return rc;
@@ -962,7 +978,7 @@ int vpm_vspace_destroy(vpm_vspace* vs)
     cudaSetDevice(vs->ctx->device);
     cudaStreamSynchronize(vs->ctx->stream);
     cudaFree(vs->pieces); cudaFree(vs->chol); cudaFree(vs->rhs); cudaFree(vs->coef); cudaFree(vs->ftab);
-    cudaFree(vs->scal); cudaFree(vs->diag); cudaFree(vs->ent);
+    cudaFree(vs->scal); cudaFree(vs->diag); cudaFree(vs->ent); cudaFree(vs->psum);
     delete vs;
     return VPM_OK;
 }
@@ -1036,6 +1052,7 @@ int vpm_resample_v(vpm_vspace* vs, const double* coef_host, vpm_particles* p, in
     VPM_CUDA(cudaSetDevice(ctx->device));
     VPM_CHECK(set_coef(vs, coef_host));
     p->uw = false;
+    p->mirror_valid = false;
     return launch_resample_v(ctx, vs, p, offset, ntotal, seed, jitter, mass_out);
 }
 
@@ -1161,6 +1178,57 @@ static int alloc_scratch(vpm_particles* p)
     return VPM_OK;
 }
 
+// Velocity-sorted mirror of (v, w) for the collision steppers (kernels_lbs.cu).  The flow of the collision models cannot
+// reorder particles in v, so the mirror is sorted ONCE and stays sorted while only those steppers advance it; it is rebuilt
+// when anything else wrote v or w (mirror_valid), when the spline domain that defined the sort keys changed, or -- once
+// the caller holds writable device pointers -- at every call.
+static constexpr int kSortGridPerSm = 4;
+
+static int lb_sort_mode(const vpm_vspace* vs, const vpm_particles* p)
+{
+    // VPM_TUNE_LBSORT: 0 = never (private-histogram passes), 1 = default (large ensembles), 2 = always (tests),
+    // 3 = always, but the mirror keeps the caller's order (tests: every trip of the sorted passes takes the mixed-cell path)
+    int mode = 1;
+    if (const char* e = getenv("VPM_TUNE_LBSORT")) mode = atoi(e);
+    if (mode <= 0 || p->n < 1 || p->n >= ((int64_t)1 << 32) || !lbs_supported(vs->ctx, vs)) return 0;
+    if (mode == 1 && p->n < ((int64_t)1 << 18)) return 0;   // launch-latency-bound sizes: the sort buys nothing
+    return mode;
+}
+
+static int ensure_mirror(vpm_vspace* vs, vpm_particles* p, int sort_mode)
+{
+    vpm_ctx* ctx = vs->ctx;
+    const bool need_w = !p->uw;
+    if (p->mirror_valid && !p->exposed && p->mirror_lo == vs->lo && p->mirror_hi == vs->hi && (p->mirror_has_w || !need_w)) return VPM_OK;
+    const size_t bytes = sizeof(double) * (size_t)(p->n + (p->n & 1));
+    const int sort_grid = ctx->sm_count * kSortGridPerSm;
+    if (!p->sv) {
+        cudaError_t e1 = cudaMalloc((void**)&p->sv, bytes), e2 = cudaMalloc((void**)&p->sinv, sizeof(unsigned) * (size_t)(p->n + 1));
+        cudaError_t e3 = cudaMalloc((void**)&p->sort_counts, sizeof(unsigned) * (256 * (size_t)sort_grid + 1));
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+            cudaFree(p->sv); cudaFree(p->sinv); cudaFree(p->sort_counts);
+            p->sv = nullptr; p->sinv = nullptr; p->sort_counts = nullptr;
+            cudaGetLastError();
+            return fail(VPM_ERR_NOMEM, "cudaMalloc of the velocity-sorted mirror failed");
+        }
+    }
+    if (need_w && !p->sw) {
+        if (cudaMalloc((void**)&p->sw, bytes) != cudaSuccess) {
+            p->sw = nullptr;
+            cudaGetLastError();
+            return fail(VPM_ERR_NOMEM, "cudaMalloc of the velocity-sorted mirror failed");
+        }
+    }
+    // the RK438 stage arrays ka, kb serve as the two key buffers of the sort
+    VPM_CHECK(launch_lbs_sort(ctx, p->v, need_w ? p->w : nullptr, p->n, vs->lo, vs->hi, p->ka, p->kb, p->sort_counts, sort_grid, p->sv,
+                              need_w ? p->sw : nullptr, p->sinv, sort_mode != 3));
+    p->mirror_valid = true;
+    p->mirror_has_w = need_w;
+    p->mirror_lo = vs->lo;
+    p->mirror_hi = vs->hi;
+    return VPM_OK;
+}
+
 int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double dt, int nsteps, int conservative)
 {
     VPM_REQUIRE(vs && p && vs->ctx == p->ctx && nsteps >= 0, "vpm_lb_rk438_steps: bad arguments");
@@ -1183,6 +1251,37 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
         else VPM_REQUIRE(vs->ent_cap >= 2 * ((size_t)erow0 + nsteps + 1), "entropy history buffer too small for this leg");
         vs->ent_rows = erow0 + nsteps + 1;
     }
+    if (const int sort_mode = lb_sort_mode(vs, p)) {
+        // ---- velocity-sorted path (kernels_lbs.cu): four passes per step for both models, no histograms, no moments passes.
+        // The stage passes deposit per-cell power sums; the field kernel turns them into the right-hand side and, for the
+        // conservative model, into the five moments of the freshly solved spline (A1, A2 ready for the next pass).
+        VPM_CHECK(ensure_mirror(vs, p, sort_mode));
+        const int PS = LBF_PS_REDUCE | LBF_PS_CONVERT | LBF_SOLVE | LBF_TABLE | (conservative ? (LBF_PS_COEFF | LBF_COEFF) : 0);
+        ps.w = p->sw;
+        {   // projection of the initial state + step-0 diagnostics
+            LbPass p0 = ps;
+            p0.mode = LB_DEPOSIT_ONLY; p0.q = p->sv; p0.diag = 1;
+            VPM_CHECK(launch_lbs_pass(ctx, vs, p0, &grid));
+            VPM_CHECK(launch_lb_field(ctx, vs, PS, grid, 2, 0, p->uw, p->wu));
+            if (ent && erow0 == 0) VPM_CHECK(lb_entropy_row(ctx, vs, p->sv, p->sw, p->n, p->uw, p->wu, 0));
+        }
+        for (int it = 1; it <= nsteps; it++) {
+            for (int s = 1; s <= 4; s++) {
+                LbPass st = ps;
+                st.mode = LB_STAGE1 + (s - 1);
+                st.q = s == 1 ? p->sv : p->q;   // stage input in memory: v (s = 1), q4 (s = 4); stages 2, 3 recompute theirs
+                st.v0 = p->sv;
+                st.qout = s == 4 ? p->sv : p->q;
+                st.diag = s == 4;
+                VPM_CHECK(launch_lbs_pass(ctx, vs, st, &grid));
+                VPM_CHECK(launch_lb_field(ctx, vs, PS, grid, s == 4 ? 2 : 0, s == 4 ? it : -1, p->uw, p->wu));
+            }
+            if (ent) VPM_CHECK(lb_entropy_row(ctx, vs, p->sv, p->sw, p->n, p->uw, p->wu, erow0 + it));
+        }
+        // the caller's array gets the new velocities back in its own order
+        if (nsteps > 0) VPM_CHECK(launch_lbs_writeback(ctx, p->sv, p->sinv, p->v, p->n));
+        return VPM_OK;
+    }
     {   // projection of the initial state + step-0 diagnostics
         LbPass p0 = ps;
         p0.mode = LB_DEPOSIT_ONLY; p0.q = p->v; p0.diag = 1;
@@ -1190,6 +1289,7 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
         VPM_CHECK(launch_lb_field(ctx, vs, PROJ | LBF_SCALRED | LBF_DIAG, grid, 2, 0));
         if (ent && erow0 == 0) VPM_CHECK(lb_entropy_row(ctx, vs, p->v, p->w, p->n, p->uw, p->wu, 0));
     }
+    p->mirror_valid = false;   // this path advances v itself
     for (int it = 1; it <= nsteps; it++) {
         for (int s = 1; s <= 4; s++) {
             // stage input in memory: v (s = 1), q4 (s = 4); q2, q3 only for the conservative model's moments
@@ -1359,6 +1459,7 @@ int vpm_vp_run(vpm_xspace* xs, vpm_particles* p, double dt, double chi, int nste
     VPM_CHECK(fw.mark_ready(0));
     int done = 0;
     if (nsteps == 0 && diag_mode) {
+        p->mirror_valid = false;
         VPM_CHECK(vp_steps(xs, p->x, p->v, p->w, p->n, p->x, p->w, p->n, dt, chi, 0, mode, diag_mode, p->uw, p->wu, false));
         VPM_CUDA(cudaMemcpyAsync(hist.p, xs->diag, sizeof(double) * 3, cudaMemcpyDeviceToDevice, ctx->stream));
     }

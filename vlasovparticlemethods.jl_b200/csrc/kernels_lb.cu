@@ -25,88 +25,11 @@
 // lb_field_kernel (one CTA: reduce, all-reduce, banded Cholesky solve, per-cell table, CLB coefficients).
 #include <cstdlib>
 
-#include "splines.cuh"
-#include "tma.cuh"
-#include "vpm_internal.h"
+#include "lb_common.cuh"
 
 namespace vpm {
 
 namespace {
-
-struct LbDev {
-    int mode;
-    const double *q, *w, *v0;
-    double *ka, *kb, *qout, *out, *out2;
-    long long n;
-    double nu, dt;
-    int conservative, diag;
-    double lo, hi, invh;
-    int ncell, nbfull;
-    const double* ftab;
-    const double* scal;
-    const double* pieces;
-    double* partials;
-    double* red_partials;
-    double w_uniform;
-    int use_uw;
-    double f_floor;
-    int stages;   // ring depth of lb_pass_ring_kernel
-    int w_direct; // ring kernel: the weight stream bypasses the ring (register prefetch) so that a second stage fits
-    int late_release;  // ring kernel tuning (VPM_TUNE_LBREL=1): hand a stage back after the tile's compute and stores
-    int np4;           // gather-only passes: four particles per loop trip instead of two (tuning knob, measured neutral)
-};
-
-constexpr int kRedW = 8;  // doubles per CTA row of scalar partial sums
-constexpr int kLbPf = 4;  // cp.async prefetch depth of the gather-only passes (16-byte loads per thread and stream in flight)
-
-// Shared-memory copy of the per-cell table: only the K monomial coefficients of f (the coefficients of f' are
-// m f_m / h and are formed in registers: the passes are co-limited by shared-memory wavefronts, and 4 loaded
-// doubles instead of 7 per evaluation is worth the three extra fp64 multiplies).  Row stride: even, so that a
-// row is read with 16-byte loads, with an odd number of 16-byte units so that the rows of 8 consecutive cells
-// tile all 32 banks (K = 4: 6 doubles).
-template <int K>
-struct TabCfg {
-    static constexpr int TS = 2 * K - 1;                                   // row stride of the global table (f then f')
-    static constexpr int even = (K + 1) & ~1;
-    static constexpr int TSP = ((even / 2) & 1) ? even : even + 2;         // padded shared-memory row stride
-    static constexpr int NV2 = (K + 1) / 2;                                // double2 loads per row
-    // Gather-only passes (moments, rhs, eval, entropy) have no histograms beside the table and are bound by the
-    // bank conflicts of its look-ups (32 lanes, ~30 different cells): there the table is REPLICATED eight times,
-    // interleaved in 16-byte units by lane & 7, so that the eight lanes of every quarter-warp phase of a 16-byte
-    // load own four banks each -- conflict-free for any combination of cells (10.5 KB instead of 2 KB at 41 knots).
-    static constexpr int REP = 8;
-    static __host__ __device__ constexpr int doubles(int ncell, bool rep) { return rep ? (ncell + 1) * NV2 * REP * 2 : (ncell + 1) * TSP; }
-};
-
-constexpr bool lb_mode_gather(int mode) { return mode == LB_RHS_OUT || mode == LB_MOMENTS || mode == LB_EVAL || mode == LB_ENTROPY; }
-
-// Cell index and local coordinate of q on the clamped grid.  Fast path (0 <= t < ncell, t = (q - lo) / h): one
-// round-toward-zero fma against 2^52 leaves floor(t) in the low mantissa word, so ci and u = t - ci cost four
-// fp64 instructions and no conversions or selects.  Everything else -- q == hi (last cell, u = 1), particles
-// outside the domain, NaN -- is detected from the bit pattern of the sum (return value true) and fixed by
-// v_locate_fix on a rare, shared slow path; outside particles are sent to the GHOST cell ncell, whose f / f'
-// table row is zero (Spline evaluation is zero outside the knots) and which deposits nothing.
-__device__ __forceinline__ bool v_locate_fast(const LbDev& P, double q, int& ci, double& u)
-{
-    const double M = 4503599627370496.0;  // 2^52
-    const double t0 = q - P.lo;
-    const double tm = __fma_rz(t0, P.invh, M);
-    ci = __double2loint(tm);
-    u = fma(t0, P.invh, -(tm - M));
-    return __double2hiint(tm) != 0x43300000 || (unsigned)ci >= (unsigned)P.ncell;
-}
-
-// returns whether q lies inside [lo, hi]; leaves (ci, u) of a particle that did not need fixing untouched
-__device__ __forceinline__ bool v_locate_fix(const LbDev& P, double q, int& ci, double& u)
-{
-    int c;
-    double uu;
-    if (!v_locate_fast(P, q, c, uu)) return true;
-    const bool inside = (q >= P.lo) && (q <= P.hi);  // NaN -> outside
-    ci = inside ? P.ncell - 1 : P.ncell;
-    u = inside ? fma(q - P.lo, P.invh, -(double)(P.ncell - 1)) : 0.0;
-    return inside;
-}
 
 template <int HM>
 struct HistCfg {
@@ -116,12 +39,6 @@ struct HistCfg {
 struct LbItem {
     double q, w, v0, a, b;   // a, b: the stored stage vectors (k1 | v0 + dt (k1+3k2+3k3)/8, k2)
 };
-
-// RK438 stage inputs (GeometricIntegrators tableau: a21 = 1/3; a31 = -1/3, a32 = 1; a41 = 1, a42 = -1, a43 = 1).
-// Explicit fma sequences: the pass that deposits q_s and the pass that evaluates k_s at q_s must agree bitwise.
-__device__ __forceinline__ double rk_q2(double v0, double k1, double dt) { return fma(dt, k1 * (1.0 / 3.0), v0); }
-__device__ __forceinline__ double rk_q3(double v0, double k1, double k2, double dt) { return fma(dt, fma(-k1, 1.0 / 3.0, k2), v0); }
-__device__ __forceinline__ double rk_q4(double v0, double k1, double k2, double k3, double dt) { return fma(dt, (k1 - k2) + k3, v0); }
 
 // One group of NP particles of one thread through a pass.  The work is arranged in PHASES over the whole group
 // (locate all, table rows of all, Horner of all, ..., commit in order) and the rare cases (domain ends,
@@ -312,31 +229,6 @@ struct LbIo {
     static constexpr bool wr_o2 = rt || MODE == LB_EVAL;
 };
 
-template <bool NAMED, int NW = kBlock>
-__device__ __forceinline__ void lb_cta_sync()
-{
-    if (NAMED) asm volatile("bar.sync 1, %0;" ::"n"(NW) : "memory");   // the NW worker threads of a ring CTA
-    else __syncthreads();
-}
-
-// stage the f rows of the table in shared memory with the padded row stride (or replicated, TabCfg); ghost row ncell = 0
-template <int K, bool REP>
-__device__ __forceinline__ void lb_stage_table(const LbDev& P, double* __restrict__ s_tab, int tid, int nthreads)
-{
-    constexpr int TS = TabCfg<K>::TS, TSP = TabCfg<K>::TSP, NV2 = TabCfg<K>::NV2, R = TabCfg<K>::REP;
-    if (REP) {
-        for (int i = tid; i < (P.ncell + 1) * NV2 * R * 2; i += nthreads) {
-            const int d = i & 1, g = i / (2 * R);          // double within the 16-byte unit; unit index = row * NV2 + j
-            const int r = g / NV2, m = 2 * (g - r * NV2) + d;
-            s_tab[i] = (r < P.ncell && m < K) ? P.ftab[r * TS + m] : 0.0;
-        }
-    } else {
-        for (int i = tid; i < (P.ncell + 1) * TSP; i += nthreads) {
-            const int r = i / TSP, m = i - r * TSP;
-            s_tab[i] = (r < P.ncell && m < K) ? P.ftab[r * TS + m] : 0.0;
-        }
-    }
-}
 
 // Fixed-order reduction of the CTA's private histograms into one partial row, and of the scalar sums.
 template <int HS, bool NAMED, int NW = kBlock>
@@ -866,6 +758,11 @@ struct LbFieldDev {
     int nv, nbfull, ncell, K, off;
     double invh;
     P2PDev p2p;
+    // power-sum input of the sorted passes (kernels_lbs.cu): per-CTA rows [ncell][2K+2] with the cell range each CTA touched
+    const int* ranges;
+    double* psum;       // [ncell * (2K+2) + nred]: reduced (all-reduced) power sums | scalar sums
+    int ps_uw;          // declared uniform weights: W_m = wu S_m
+    double wu, lo, h;
 };
 
 // The kernel is a chain of latencies (L2 round trips of the partial rows, the sequential band solve), not of
@@ -882,6 +779,12 @@ __global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbField
     double* s_full = sm;                    // nbfull
     double* s_y = s_full + F.nbfull;        // nv
     double* s_chol = s_y + F.nv;            // (nv + kCholW - 1) * kCholW: padded rows, trailing zero rows
+    // sorted passes only (phases & LBF_PS_*): power sums, monomial table of the new spline, per-cell moment terms, CTA ranges
+    const int NA = 2 * F.K + 2, ncol = F.ncell * NA;
+    double* s_P = s_chol + (F.nv + kCholW - 1) * kCholW;   // ncol + 8
+    double* s_ft = s_P + ncol + 8;                          // ncell * K
+    double* s_mom = s_ft + F.ncell * F.K;                   // 5 * ncell
+    int* s_rng = reinterpret_cast<int*>(s_mom + 5 * F.ncell);   // 2 * nparts
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nwarps = nt / 32;
     const int K = F.K, nv = F.nv;
 
@@ -915,7 +818,60 @@ __global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbField
         }
         __syncthreads();
     }
-    const bool reduced_here = (F.phases & LBF_REDUCE) && !F.p2p.seq;   // rhs of this rank is still in s_full
+    if (F.phases & LBF_PS_REDUCE) {
+        // per-CTA power-sum rows -> psum, in CTA order; a CTA of the sorted pass touched one or two cells, so most rows are
+        // skipped by their range (loads predicated, eight in flight)
+        for (int i = tid; i < 2 * F.nparts; i += nt) s_rng[i] = F.ranges[i];
+        __syncthreads();
+        for (int col = tid; col < ncol; col += nt) {
+            const int c = col / NA;
+            double sum = 0.0;
+            for (int b0 = 0; b0 < F.nparts; b0 += 8) {
+                double t[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int b = b0 + k;
+                    const bool ok = b < F.nparts && s_rng[2 * b] <= c && c <= s_rng[2 * b + 1];
+                    t[k] = ok ? F.partials[(size_t)b * ncol + col] : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) sum += t[k];
+            }
+            F.psum[col] = sum;
+        }
+        if (warp < F.nred) {
+            const double sc = warp_sum(strided_sum(F.red_partials + warp, (size_t)kRedW, F.nparts, lane));
+            if (lane == 0) F.psum[ncol + warp] = sc;
+        }
+        __syncthreads();
+        if (F.p2p.seq) p2p_allreduce(F.p2p, F.psum, ncol + F.nred);   // power sums | scalars: one fused peer-memory all-reduce
+    }
+    if (F.phases & LBF_PS_CONVERT) {
+        for (int i = tid; i < ncol + F.nred; i += nt) s_P[i] = F.psum[i];
+        __syncthreads();
+        if (tid < F.nred) {
+            F.rhs[nv + tid] = s_P[ncol + tid];
+            if (F.nred == 2 && F.diag && F.diag_slot >= 0) F.diag[2 * F.diag_slot + tid] = s_P[ncol + tid];   // sum v, sum v^2
+        }
+        // right-hand side of the projection: bin b = c + j collects function j of cell c, B_{c,j}(u) = sum_m pieces[c][j][m] u^m
+        for (int b = tid; b < F.nbfull; b += nt) {
+            double sum = 0.0;
+            for (int j = 0; j < K; j++) {
+                const int c = b - j;
+                if (c < 0 || c >= F.ncell) continue;
+                const double* pc = F.pieces + ((size_t)c * K + j) * K;
+                const double* Pc = s_P + c * NA + (F.ps_uw ? K : 0);
+                double r = 0.0;
+                for (int m = 0; m < K; m++) r = fma(pc[m], Pc[m], r);
+                sum += F.ps_uw ? F.wu * r : r;
+            }
+            s_full[b] = sum;
+        }
+        __syncthreads();
+        for (int i = tid; i < nv; i += nt) F.rhs[i] = s_full[i + F.off];
+        __syncthreads();
+    }
+    const bool reduced_here = ((F.phases & LBF_REDUCE) && !F.p2p.seq) || (F.phases & LBF_PS_CONVERT);   // rhs is still in s_full
     if (F.p2p.seq && (F.phases & (LBF_REDUCE | LBF_SCALRED))) {
         // multi-GPU: rhs | scalar sums are contiguous; one fused peer-memory all-reduce
         const int start = (F.phases & LBF_REDUCE) ? 0 : nv;
@@ -974,7 +930,41 @@ __global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbField
             for (int j = 0; j < K; j++) s = fma(s_full[c + j], F.pieces[((size_t)c * K + j) * K + m], s);
             F.ftab[c * TS + m] = s;
             if (m >= 1) F.ftab[c * TS + K + m - 1] = (double)m * s * F.invh;
+            if (F.phases & LBF_PS_COEFF) s_ft[idx] = s;
         }
+    }
+    if (F.phases & LBF_PS_COEFF) {
+        // The five sums of density.jl:43-52 over the particles whose power sums S were just deposited, for the spline just
+        // solved: on cell c, f = sum_m F_m u^m and v = v_c + h u, so  sum f = F . S,  sum v f = v_c F . S + h F . S(+1), ...
+        __syncthreads();
+        for (int c = tid; c < F.ncell; c += nt) {
+            const double* Fc = s_ft + c * K;
+            const double* S = s_P + c * NA + K;
+            const double vc = fma((double)c, F.h, F.lo);
+            double n0 = 0.0, n1 = 0.0, n2 = 0.0, d0 = 0.0, d1 = 0.0;
+            for (int m = 0; m < K; m++) {
+                n0 = fma(Fc[m], S[m], n0);
+                n1 = fma(Fc[m], S[m + 1], n1);
+                n2 = fma(Fc[m], S[m + 2], n2);
+                if (m >= 1) {
+                    d0 = fma((double)m * Fc[m], S[m - 1], d0);
+                    d1 = fma((double)m * Fc[m], S[m], d1);
+                }
+            }
+            s_mom[0 * F.ncell + c] = n0;
+            s_mom[1 * F.ncell + c] = fma(vc, n0, F.h * n1);
+            s_mom[2 * F.ncell + c] = fma(vc * vc, n0, fma(2.0 * vc * F.h, n1, F.h * F.h * n2));
+            s_mom[3 * F.ncell + c] = d0 * F.invh;
+            s_mom[4 * F.ncell + c] = fma(vc * F.invh, d0, d1);
+        }
+        __syncthreads();
+        if (warp < 5) {
+            double sum = 0.0;
+            for (int c = lane; c < F.ncell; c += 32) sum += s_mom[warp * F.ncell + c];
+            sum = warp_sum(sum);
+            if (lane == 0) F.rhs[nv + warp] = sum;
+        }
+        __syncthreads();
     }
     if ((F.phases & LBF_COEFF) && tid == 0) {
         // compute_coefficients: src/models/lenard_bernstein_conservative.jl:11-21
@@ -1181,37 +1171,51 @@ int launch_lb_pass(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* gri
     return fail(VPM_ERR_UNSUPPORTED, "spline order must be 2..6");
 }
 
-int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nred, int diag_slot)
+int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nred, int diag_slot, int ps_uw, double ps_wu)
 {
+    const bool ps = (phases & (LBF_PS_REDUCE | LBF_PS_CONVERT)) != 0;   // input: power-sum rows of the sorted passes
+    const int NA = 2 * vs->K + 2, ncol = vs->ncell * NA;
     LbFieldDev F{};
     F.partials = ctx->partials;
-    F.red_partials = ctx->partials + (size_t)nparts * vs->nbfull;
+    F.red_partials = ctx->partials + (size_t)nparts * (ps ? ncol : vs->nbfull);
+    F.ranges = reinterpret_cast<const int*>(ctx->partials + (size_t)nparts * (ncol + kRedW));
+    F.psum = vs->psum;
+    F.ps_uw = ps_uw; F.wu = ps_wu; F.lo = vs->lo; F.h = vs->h;
     F.nparts = nparts; F.diag_slot = diag_slot; F.nred = nred;
     F.rhs = vs->rhs; F.coef = vs->coef; F.ftab = vs->ftab; F.scal = vs->scal; F.diag = vs->diag; F.ent = vs->ent;
     F.chol = vs->chol; F.pieces = vs->pieces;
     F.nv = vs->nv; F.nbfull = vs->nbfull; F.ncell = vs->ncell; F.K = vs->K; F.off = vs->dirichlet ? 1 : 0;
     F.invh = vs->invh;
-    const size_t smem = sizeof(double) * ((size_t)vs->nbfull + vs->nv + ((size_t)vs->nv + kCholW - 1) * kCholW);
+    size_t smem = sizeof(double) * ((size_t)vs->nbfull + vs->nv + ((size_t)vs->nv + kCholW - 1) * kCholW);
+    if (phases & (LBF_PS_REDUCE | LBF_PS_CONVERT | LBF_PS_COEFF))
+        smem += sizeof(double) * ((size_t)ncol + 8 + (size_t)vs->ncell * vs->K + 5 * (size_t)vs->ncell) + sizeof(int) * 2 * (size_t)nparts;
     if (smem > ctx->smem_optin) return fail(VPM_ERR_UNSUPPORTED, "v-space too large for the single-CTA field kernel");
     if (smem > 48 * 1024) VPM_CUDA(cudaFuncSetAttribute(lb_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
-    const int red = phases & (LBF_REDUCE | LBF_SCALRED);
+    const int red = phases & (LBF_REDUCE | LBF_SCALRED | LBF_PS_REDUCE);
     F.p2p = P2PDev{};
     if (ctx->p2p.nranks > 1 && red) {
-        if ((size_t)vs->nv + 8 > (size_t)kP2PCap) return fail(VPM_ERR_UNSUPPORTED, "coefficient vector exceeds the peer mailbox slot");
+        if ((size_t)vs->nv + 8 > (size_t)kP2PCap || (ps && (size_t)ncol + 8 > (size_t)kP2PCap))
+            return fail(VPM_ERR_UNSUPPORTED, "coefficient vector exceeds the peer mailbox slot");
         F.p2p = ctx->p2p;
         F.p2p.seq = ++ctx->p2p_seq;
     } else if (ctx->comm.comm && red) {
         F.phases = red;
         prof_begin(ctx, PROF_LB_FIELD);
-    VPM_CUDA(launch_pdl(lb_field_kernel, 1u, (unsigned)kLbFieldThreads, smem, ctx->stream, F));
-    prof_end(ctx);
+        VPM_CUDA(launch_pdl(lb_field_kernel, 1u, (unsigned)kLbFieldThreads, smem, ctx->stream, F));
+        prof_end(ctx);
         ctx->launches++;
         VPM_CUDA(cudaGetLastError());
-        // rhs | scalars are contiguous: one all-reduce
-        double* buf = (phases & LBF_REDUCE) ? vs->rhs : vs->rhs + vs->nv;
-        size_t cnt = ((phases & LBF_REDUCE) ? (size_t)vs->nv : 0) + ((phases & LBF_SCALRED) ? (size_t)nred : 0);
-        if ((phases & LBF_REDUCE) && !(phases & LBF_SCALRED)) cnt = vs->nv;
+        double* buf;
+        size_t cnt;
+        if (ps) {   // power sums | scalars are contiguous in psum
+            buf = vs->psum;
+            cnt = (size_t)ncol + (size_t)nred;
+        } else {    // rhs | scalars are contiguous: one all-reduce
+            buf = (phases & LBF_REDUCE) ? vs->rhs : vs->rhs + vs->nv;
+            cnt = ((phases & LBF_REDUCE) ? (size_t)vs->nv : 0) + ((phases & LBF_SCALRED) ? (size_t)nred : 0);
+            if ((phases & LBF_REDUCE) && !(phases & LBF_SCALRED)) cnt = vs->nv;
+        }
         int rc = comm_allreduce(ctx, buf, cnt);
         if (rc) return rc;
         phases &= ~red;

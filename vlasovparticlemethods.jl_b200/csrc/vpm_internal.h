@@ -85,6 +85,14 @@ struct vpm_particles {
     // uniform-weight fast path (vpm_particles_set_uniform_weight): the steppers skip the w[] stream
     bool uw = false;
     double wu = 0.0;
+    // velocity-sorted mirror of (v, w) for the collision steppers (kernels_lbs.cu): sv[i] = v[perm[i]], inv = perm^-1.
+    // Valid as long as nothing but those steppers changed v or w (every writer calls mirror_invalidate); once a writable
+    // device pointer has been handed out (vpm_particles_ptrs) the mirror is rebuilt at every stepper call.
+    double *sv = nullptr, *sw = nullptr;
+    unsigned* sinv = nullptr;
+    unsigned* sort_counts = nullptr;
+    bool mirror_valid = false, exposed = false, mirror_has_w = false;
+    double mirror_lo = 0.0, mirror_hi = 0.0;
 };
 
 struct vpm_xspace {
@@ -118,6 +126,7 @@ struct vpm_vspace {
     double* coef = nullptr;    // [nv]
     double* ftab = nullptr;    // [ncell][TS] F (K) then G (K-1) monomial coefficients
     double* scal = nullptr;    // [8] A1, A2, moments...
+    double* psum = nullptr;    // [ncell * (2K+2) + 8] power sums of the sorted passes | scalar sums
     double* diag = nullptr;
     size_t diag_cap = 0;
     // entropy history (vpm_vspace_entropy_history): rows (S, floored count) of the last stepper call
@@ -227,8 +236,19 @@ int launch_lb_pass(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* gri
 // (both all-reduced across ranks when a communicator is attached); SOLVE: banded Cholesky rhs -> coef;
 // TABLE: coef -> per-cell f / f' polynomials; COEFF: CLB A1, A2 from the five moments; DIAG: sums -> diag row;
 // ENT: the two sums of an LB_ENTROPY pass -> entropy history row diag_slot
-enum LbFieldPhase : int { LBF_REDUCE = 1, LBF_SOLVE = 2, LBF_TABLE = 4, LBF_COEFF = 8, LBF_DIAG = 16, LBF_SCALRED = 32, LBF_ENT = 64 };
-int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nred, int diag_slot);
+// PS_REDUCE: power-sum rows of the sorted passes (kernels_lbs.cu) | nred scalar sums -> vs->psum, all-reduced; PS_CONVERT:
+// psum -> right-hand side (and, nred == 2, sum v / sum v^2 -> diag row diag_slot); PS_COEFF: the five CLB moments of the
+// freshly solved spline from the power sums (replaces the moments pass; follow with COEFF)
+enum LbFieldPhase : int { LBF_REDUCE = 1, LBF_SOLVE = 2, LBF_TABLE = 4, LBF_COEFF = 8, LBF_DIAG = 16, LBF_SCALRED = 32, LBF_ENT = 64,
+                          LBF_PS_REDUCE = 128, LBF_PS_CONVERT = 256, LBF_PS_COEFF = 512 };
+int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nred, int diag_slot, int ps_uw = 0, double ps_wu = 0.0);
+
+// ---------------- velocity-sorted Lenard-Bernstein passes (kernels_lbs.cu) ----------------
+int lbs_supported(const vpm_ctx* ctx, const vpm_vspace* vs);
+int launch_lbs_pass(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* grid_out);
+int launch_lbs_sort(vpm_ctx* ctx, const double* v, const double* w, int64_t n, double lo, double hi, double* tmp_a, double* tmp_b,
+                    unsigned* counts, int sort_grid, double* sv, double* sw, unsigned* inv, int do_sort);
+int launch_lbs_writeback(vpm_ctx* ctx, const double* sv, const unsigned* inv, double* v, int64_t n);
 
 // ---------------- misc kernels (kernels_misc.cu) ----------------
 int launch_fill(vpm_ctx* ctx, double* a, int64_t n, double value);
