@@ -402,6 +402,26 @@ int vpm_memcpy_d2h(vpm_ctx* ctx, double* dst_host, const double* src_dev, int64_
 
 /* ---------------------------------------------------------------- particles */
 
+// The collision steppers advance a velocity-sorted MIRROR of (v, w) (kernels_lbs.cu) and leave p->v behind (v_stale) until
+// somebody needs it in the caller's order: every reader of p->v calls particles_sync_v first, every writer of v or w
+// outside those steppers calls mirror_invalidate (which syncs, then drops the mirror).
+static int particles_sync_v(vpm_particles* p)
+{
+    if (!p->v_stale) return VPM_OK;
+    VPM_CHECK(launch_lbs_writeback(p->ctx, p->sv, p->sinv, p->v, p->n));
+    p->v_stale = false;
+    return VPM_OK;
+}
+
+static int mirror_invalidate(vpm_particles* p)
+{
+    VPM_CHECK(particles_sync_v(p));
+    p->mirror_valid = false;
+    return VPM_OK;
+}
+
+
+
 int vpm_particles_create(vpm_ctx* ctx, int64_t n, vpm_particles** out)
 {
     VPM_REQUIRE(ctx && out && n >= 0, "vpm_particles_create: bad arguments");
@@ -441,16 +461,17 @@ int64_t vpm_particles_size(const vpm_particles* p) { return p ? p->n : 0; }
 int vpm_particles_ptrs(vpm_particles* p, double** x, double** v, double** w)
 {
     VPM_REQUIRE(p, "vpm_particles_ptrs: p is NULL");
+    VPM_CUDA(cudaSetDevice(p->ctx->device));
+    // ... or the velocities, at any later time: the velocity-sorted mirror of the collision steppers is rebuilt at every call from now on
+    if (v || w) {
+        VPM_CHECK(mirror_invalidate(p));
+        p->exposed = true;
+    }
     if (x) *x = p->x;
     if (v) *v = p->v;
     if (w) {
         *w = p->w;
         p->uw = false;   // the caller may rewrite the weights through this pointer: the uniform-weight declaration ends here
-    }
-    // ... or the velocities, at any later time: the velocity-sorted mirror of the collision steppers is rebuilt at every call from now on
-    if (v || w) {
-        p->exposed = true;
-        p->mirror_valid = false;
     }
     return VPM_OK;
 }
@@ -458,6 +479,10 @@ int vpm_particles_ptrs(vpm_particles* p, double** x, double** v, double** w)
 int vpm_particles_ptrs_const(const vpm_particles* p, const double** x, const double** v, const double** w)
 {
     VPM_REQUIRE(p, "vpm_particles_ptrs_const: p is NULL");
+    if (v) {   // the array behind the pointer must hold the current velocities (logically const: a cached layout is refreshed)
+        VPM_CUDA(cudaSetDevice(p->ctx->device));
+        VPM_CHECK(particles_sync_v(const_cast<vpm_particles*>(p)));
+    }
     if (x) *x = p->x;
     if (v) *v = p->v;
     if (w) *w = p->w;
@@ -471,13 +496,14 @@ int vpm_particles_upload_aos(vpm_particles* p, const double* z, int ld)
     VPM_CUDA(cudaSetDevice(ctx->device));
     const int64_t chunk = 1 << 24;
     VPM_CHECK(ensure_staging(ctx, (size_t)std::min<int64_t>(chunk, std::max<int64_t>(p->n, 1)) * ld));
+    p->v_stale = false;   // v is overwritten as a whole
+    p->mirror_valid = false;
     for (int64_t o = 0; o < p->n; o += chunk) {
         const int64_t m = std::min(chunk, p->n - o);
         VPM_CUDA(cudaMemcpyAsync(ctx->staging, z + o * ld, sizeof(double) * m * ld, cudaMemcpyHostToDevice, ctx->stream));
         VPM_CHECK(launch_aos_to_soa(ctx, ctx->staging, ld, m, p->x + o, p->v + o, ld == 3 ? p->w + o : nullptr));
     }
     if (ld == 3) p->uw = false;
-    p->mirror_valid = false;
     VPM_CUDA(cudaStreamSynchronize(ctx->stream));
     return VPM_OK;
 }
@@ -489,6 +515,7 @@ int vpm_particles_download_aos(vpm_particles* p, double* z, int ld)
     VPM_CUDA(cudaSetDevice(ctx->device));
     const int64_t chunk = 1 << 24;
     VPM_CHECK(ensure_staging(ctx, (size_t)std::min<int64_t>(chunk, std::max<int64_t>(p->n, 1)) * ld));
+    VPM_CHECK(particles_sync_v(p));
     for (int64_t o = 0; o < p->n; o += chunk) {
         const int64_t m = std::min(chunk, p->n - o);
         VPM_CHECK(launch_soa_to_aos(ctx, p->x + o, p->v + o, ld == 3 ? p->w + o : nullptr, ld, m, ctx->staging));
@@ -504,13 +531,14 @@ int vpm_particles_upload_soa(vpm_particles* p, const double* x, const double* v,
     vpm_ctx* ctx = p->ctx;
     VPM_CUDA(cudaSetDevice(ctx->device));
     const size_t bytes = sizeof(double) * (size_t)p->n;
+    if (v) p->v_stale = false;   // overwritten as a whole
+    if (v || w) VPM_CHECK(mirror_invalidate(p));
     if (x) VPM_CUDA(cudaMemcpyAsync(p->x, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (v) VPM_CUDA(cudaMemcpyAsync(p->v, v, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (w) {
         VPM_CUDA(cudaMemcpyAsync(p->w, w, bytes, cudaMemcpyHostToDevice, ctx->stream));
         p->uw = false;
     }
-    if (v || w) p->mirror_valid = false;
     VPM_CUDA(cudaStreamSynchronize(ctx->stream));
     return VPM_OK;
 }
@@ -521,6 +549,7 @@ int vpm_particles_download_soa(vpm_particles* p, double* x, double* v, double* w
     vpm_ctx* ctx = p->ctx;
     VPM_CUDA(cudaSetDevice(ctx->device));
     const size_t bytes = sizeof(double) * (size_t)p->n;
+    if (v) VPM_CHECK(particles_sync_v(p));
     if (x) VPM_CUDA(cudaMemcpyAsync(x, p->x, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (v) VPM_CUDA(cudaMemcpyAsync(v, p->v, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (w) VPM_CUDA(cudaMemcpyAsync(w, p->w, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -532,8 +561,8 @@ int vpm_particles_set_uniform_weight(vpm_particles* p, double w)
 {
     VPM_REQUIRE(p && std::isfinite(w), "vpm_particles_set_uniform_weight: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
+    VPM_CHECK(mirror_invalidate(p));
     VPM_CHECK(launch_fill(p->ctx, p->w, p->n, w));
-    p->mirror_valid = false;
     p->uw = true;
     p->wu = w;
     return VPM_OK;
@@ -545,6 +574,7 @@ int vpm_sample_bump_on_tail(vpm_particles* p, int64_t offset, int64_t ntotal, ui
     VPM_REQUIRE(p && ntotal > 0 && kappa > 0, "vpm_sample_bump_on_tail: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
     p->uw = false;
+    p->v_stale = false;   // v and w are overwritten as a whole
     p->mirror_valid = false;
     return launch_sample_bump_on_tail(p->ctx, p, offset, ntotal, seed, eps, kappa, alpha, sigma, v0);
 }
@@ -555,6 +585,7 @@ int vpm_sample_normal(vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t
     VPM_REQUIRE(p && ntotal > 0 && xhi > xlo, "vpm_sample_normal: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
     p->uw = false;
+    p->v_stale = false;   // v and w are overwritten as a whole
     p->mirror_valid = false;
     return launch_sample_normal(p->ctx, p, offset, ntotal, seed, xlo, xhi, xmax, xmax_used);
 }
@@ -565,6 +596,7 @@ int vpm_sample_maxwellian(vpm_particles* p, int64_t offset, int64_t ntotal, uint
     VPM_REQUIRE(p && ntotal > 0, "vpm_sample_maxwellian: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
     p->uw = false;
+    p->v_stale = false;   // v and w are overwritten as a whole
     p->mirror_valid = false;
     return launch_sample_maxwellian(p->ctx, p, offset, ntotal, seed, xlo, xhi, shift, doubled, wnum);
 }
@@ -575,6 +607,7 @@ int vpm_sample_uniform(vpm_particles* p, int64_t offset, int64_t ntotal, uint64_
     VPM_REQUIRE(p && ntotal > 0, "vpm_sample_uniform: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
     p->uw = false;
+    p->v_stale = false;   // v and w are overwritten as a whole
     p->mirror_valid = false;
     return launch_sample_uniform(p->ctx, p, offset, ntotal, seed, xlo, xhi, vlo, vhi, shift, wnum);
 }
@@ -737,7 +770,7 @@ int vpm_push_kick(vpm_xspace* xs, vpm_particles* p, const double* phi_host, doub
     VPM_CHECK(launch_vp_field(ctx, xs, FIELD_TABLE, 0, 0, 0, -scale, 1.0, -1, -1));
     VpPass ps{};
     ps.x_in = p->x; ps.v_in = p->v; ps.w = p->w; ps.v_out = p->v; ps.n = p->n;
-    p->mirror_valid = false;
+    VPM_CHECK(mirror_invalidate(p));
     ps.flags = VP_KICK1 | VP_WRITE_V;
     ps.tau_kick = tau;
     return launch_vp_pass(ctx, xs, ps, nullptr);
@@ -861,7 +894,7 @@ int vpm_vp_strang_steps_async(vpm_xspace* xs, vpm_particles* p, double dt, doubl
         // the deposit positions are the particles' positions at call time; the pass that computes the field
         // runs before any push on the same stream, so no copy is needed
     }
-    p->mirror_valid = false;   // the kick changes v
+    VPM_CHECK(mirror_invalidate(p));   // the kick changes v
     return vp_steps(xs, p->x, p->v, p->w, p->n, xdep, p->w, p->n, dt, chi, nsteps, mode, diag_mode, p->uw, p->wu);
 }
 
@@ -1052,6 +1085,7 @@ int vpm_resample_v(vpm_vspace* vs, const double* coef_host, vpm_particles* p, in
     VPM_CUDA(cudaSetDevice(ctx->device));
     VPM_CHECK(set_coef(vs, coef_host));
     p->uw = false;
+    p->v_stale = false;   // v and w are overwritten as a whole
     p->mirror_valid = false;
     return launch_resample_v(ctx, vs, p, offset, ntotal, seed, jitter, mass_out);
 }
@@ -1278,10 +1312,12 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
             }
             if (ent) VPM_CHECK(lb_entropy_row(ctx, vs, p->sv, p->sw, p->n, p->uw, p->wu, erow0 + it));
         }
-        // the caller's array gets the new velocities back in its own order
-        if (nsteps > 0) VPM_CHECK(launch_lbs_writeback(ctx, p->sv, p->sinv, p->v, p->n));
+        // p->v gets the new velocities back in the caller's order when somebody asks for them (particles_sync_v): a random
+        // gather of 1e8 doubles costs as much as a whole RK438 step
+        if (nsteps > 0) p->v_stale = true;
         return VPM_OK;
     }
+    VPM_CHECK(mirror_invalidate(p));   // this path advances v itself
     {   // projection of the initial state + step-0 diagnostics
         LbPass p0 = ps;
         p0.mode = LB_DEPOSIT_ONLY; p0.q = p->v; p0.diag = 1;
@@ -1289,7 +1325,6 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
         VPM_CHECK(launch_lb_field(ctx, vs, PROJ | LBF_SCALRED | LBF_DIAG, grid, 2, 0));
         if (ent && erow0 == 0) VPM_CHECK(lb_entropy_row(ctx, vs, p->v, p->w, p->n, p->uw, p->wu, 0));
     }
-    p->mirror_valid = false;   // this path advances v itself
     for (int it = 1; it <= nsteps; it++) {
         for (int s = 1; s <= 4; s++) {
             // stage input in memory: v (s = 1), q4 (s = 4); q2, q3 only for the conservative model's moments
@@ -1455,11 +1490,11 @@ int vpm_vp_run(vpm_xspace* xs, vpm_particles* p, double dt, double chi, int nste
             return fail(VPM_ERR_NOMEM, "cudaMalloc of the diagnostics history failed");
         }
     }
+    VPM_CHECK(mirror_invalidate(p));   // the kicks change v
     VPM_CHECK(launch_soa_to_aos(ctx, p->x, p->v, nullptr, 2, p->n, fw.snap[0]));
     VPM_CHECK(fw.mark_ready(0));
     int done = 0;
     if (nsteps == 0 && diag_mode) {
-        p->mirror_valid = false;
         VPM_CHECK(vp_steps(xs, p->x, p->v, p->w, p->n, p->x, p->w, p->n, dt, chi, 0, mode, diag_mode, p->uw, p->wu, false));
         VPM_CUDA(cudaMemcpyAsync(hist.p, xs->diag, sizeof(double) * 3, cudaMemcpyDeviceToDevice, ctx->stream));
     }
@@ -1510,6 +1545,7 @@ int vpm_lb_run(vpm_vspace* vs, vpm_particles* p, double nu, double dt, double t0
         }
     }
     const size_t vbytes = sizeof(double) * (size_t)p->n;
+    VPM_CHECK(particles_sync_v(p));
     VPM_CUDA(cudaMemcpyAsync(fw.snap[0], p->v, vbytes, cudaMemcpyDeviceToDevice, ctx->stream));
     VPM_CHECK(fw.mark_ready(0));
     int done = 0;
@@ -1536,7 +1572,9 @@ int vpm_lb_run(vpm_vspace* vs, vpm_particles* p, double nu, double dt, double t0
                                          sizeof(double) * 2 * (size_t)(leg + 1 - skip), cudaMemcpyDeviceToDevice, ctx->stream));
             }
             done += leg;
-            VPM_CUDA(cudaMemcpyAsync(fw.snap[(f + 1) & 1], p->v, vbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+            // frames are in the caller's particle order: straight from the sorted mirror when that is where the state lives
+            if (p->v_stale) VPM_CHECK(launch_lbs_writeback(ctx, p->sv, p->sinv, fw.snap[(f + 1) & 1], p->n));
+            else VPM_CUDA(cudaMemcpyAsync(fw.snap[(f + 1) & 1], p->v, vbytes, cudaMemcpyDeviceToDevice, ctx->stream));
             VPM_CHECK(fw.mark_ready(f + 1));
         }
         const int64_t step = std::min<int64_t>(f * save_stride, nsteps);

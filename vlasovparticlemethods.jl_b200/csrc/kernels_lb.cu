@@ -23,6 +23,7 @@
 // Kernels: lb_pass_ring_kernel (warp-specialised TMA ring, default for the deposit passes), lb_pass_kernel
 // (register prefetch: gather-only modes, unaligned / tiny inputs, per-warp and per-CTA histogram fallbacks),
 // lb_field_kernel (one CTA: reduce, all-reduce, banded Cholesky solve, per-cell table, CLB coefficients).
+#include <climits>
 #include <cstdlib>
 
 #include "lb_common.cuh"
@@ -762,6 +763,7 @@ struct LbFieldDev {
     const int* ranges;
     double* psum;       // [ncell * (2K+2) + nred]: reduced (all-reduced) power sums | scalar sums
     int ps_uw;          // declared uniform weights: W_m = wu S_m
+    int pc_smem;        // the piece table is staged in shared memory (small grids) instead of read from global memory
     double wu, lo, h;
 };
 
@@ -781,10 +783,13 @@ __global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbField
     double* s_chol = s_y + F.nv;            // (nv + kCholW - 1) * kCholW: padded rows, trailing zero rows
     // sorted passes only (phases & LBF_PS_*): power sums, monomial table of the new spline, per-cell moment terms, CTA ranges
     const int NA = 2 * F.K + 2, ncol = F.ncell * NA;
-    double* s_P = s_chol + (F.nv + kCholW - 1) * kCholW;   // ncol + 8
+    double* s_pc = s_chol + (F.nv + kCholW - 1) * kCholW;  // ncell * K * K (pc_smem): the piece table, a constant operator
+    double* s_P = s_pc + (F.pc_smem ? F.ncell * F.K * F.K : 0);   // ncol + 8
     double* s_ft = s_P + ncol + 8;                          // ncell * K
     double* s_mom = s_ft + F.ncell * F.K;                   // 5 * ncell
     int* s_rng = reinterpret_cast<int*>(s_mom + 5 * F.ncell);   // 2 * nparts
+    int* s_cfirst = s_rng + 2 * F.nparts;                       // ncell: first / last CTA that touched each cell
+    int* s_clast = s_cfirst + F.ncell;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nwarps = nt / 32;
     const int K = F.K, nv = F.nv;
 
@@ -799,6 +804,9 @@ __global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbField
             s_chol[i] = (k == 0 && r < nv) ? 1.0 / c : c;
         }
     }
+    if (F.pc_smem && (F.phases & (LBF_TABLE | LBF_PS_CONVERT)))
+        for (int i = tid; i < F.ncell * K * K; i += nt) s_pc[i] = F.pieces[i];
+    const double* pieces = F.pc_smem ? s_pc : F.pieces;
     pdl_wait();
     if (F.phases & LBF_REDUCE) {
         for (int b = warp; b < F.nbfull; b += nwarps) {
@@ -819,19 +827,33 @@ __global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbField
         __syncthreads();
     }
     if (F.phases & LBF_PS_REDUCE) {
-        // per-CTA power-sum rows -> psum, in CTA order; a CTA of the sorted pass touched one or two cells, so most rows are
-        // skipped by their range (loads predicated, eight in flight)
+        // per-CTA power-sum rows -> psum, in CTA order.  A CTA of the sorted pass touched one or two cells, so a cell's rows come
+        // from a short run of CTAs: first / last CTA per cell from the ranges (integer atomics: order-independent), then every
+        // column walks only its run (range re-checked: the run may have holes), loads predicated, eight in flight
         for (int i = tid; i < 2 * F.nparts; i += nt) s_rng[i] = F.ranges[i];
+        for (int c = tid; c < F.ncell; c += nt) {
+            s_cfirst[c] = INT_MAX;
+            s_clast[c] = -1;
+        }
+        __syncthreads();
+        for (int b = tid; b < F.nparts; b += nt) {
+            const int hi = min(s_rng[2 * b + 1], F.ncell - 1);
+            for (int c = max(s_rng[2 * b], 0); c <= hi; c++) {
+                atomicMin(&s_cfirst[c], b);
+                atomicMax(&s_clast[c], b);
+            }
+        }
         __syncthreads();
         for (int col = tid; col < ncol; col += nt) {
             const int c = col / NA;
+            const int bl = s_clast[c];
             double sum = 0.0;
-            for (int b0 = 0; b0 < F.nparts; b0 += 8) {
+            for (int b0 = s_cfirst[c]; b0 <= bl; b0 += 8) {
                 double t[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const int b = b0 + k;
-                    const bool ok = b < F.nparts && s_rng[2 * b] <= c && c <= s_rng[2 * b + 1];
+                    const int b = min(b0 + k, bl);
+                    const bool ok = b0 + k <= bl && s_rng[2 * b] <= c && c <= s_rng[2 * b + 1];
                     t[k] = ok ? F.partials[(size_t)b * ncol + col] : 0.0;
                 }
 #pragma unroll
@@ -859,7 +881,7 @@ __global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbField
             for (int j = 0; j < K; j++) {
                 const int c = b - j;
                 if (c < 0 || c >= F.ncell) continue;
-                const double* pc = F.pieces + ((size_t)c * K + j) * K;
+                const double* pc = pieces + ((size_t)c * K + j) * K;
                 const double* Pc = s_P + c * NA + (F.ps_uw ? K : 0);
                 double r = 0.0;
                 for (int m = 0; m < K; m++) r = fma(pc[m], Pc[m], r);
@@ -927,7 +949,7 @@ __global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbField
         for (int idx = tid; idx < F.ncell * K; idx += nt) {
             const int c = idx / K, m = idx - c * K;
             double s = 0.0;
-            for (int j = 0; j < K; j++) s = fma(s_full[c + j], F.pieces[((size_t)c * K + j) * K + m], s);
+            for (int j = 0; j < K; j++) s = fma(s_full[c + j], pieces[((size_t)c * K + j) * K + m], s);
             F.ftab[c * TS + m] = s;
             if (m >= 1) F.ftab[c * TS + K + m - 1] = (double)m * s * F.invh;
             if (F.phases & LBF_PS_COEFF) s_ft[idx] = s;
@@ -1187,8 +1209,12 @@ int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nr
     F.nv = vs->nv; F.nbfull = vs->nbfull; F.ncell = vs->ncell; F.K = vs->K; F.off = vs->dirichlet ? 1 : 0;
     F.invh = vs->invh;
     size_t smem = sizeof(double) * ((size_t)vs->nbfull + vs->nv + ((size_t)vs->nv + kCholW - 1) * kCholW);
+    const size_t pc_bytes = sizeof(double) * (size_t)vs->ncell * vs->K * vs->K;
+    F.pc_smem = pc_bytes <= 32 * 1024;
+    if (F.pc_smem) smem += pc_bytes;
     if (phases & (LBF_PS_REDUCE | LBF_PS_CONVERT | LBF_PS_COEFF))
-        smem += sizeof(double) * ((size_t)ncol + 8 + (size_t)vs->ncell * vs->K + 5 * (size_t)vs->ncell) + sizeof(int) * 2 * (size_t)nparts;
+        smem += sizeof(double) * ((size_t)ncol + 8 + (size_t)vs->ncell * vs->K + 5 * (size_t)vs->ncell) +
+                sizeof(int) * (2 * (size_t)nparts + 2 * (size_t)vs->ncell);
     if (smem > ctx->smem_optin) return fail(VPM_ERR_UNSUPPORTED, "v-space too large for the single-CTA field kernel");
     if (smem > 48 * 1024) VPM_CUDA(cudaFuncSetAttribute(lb_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 

@@ -92,6 +92,7 @@ struct vpm_particles {
     unsigned* sinv = nullptr;
     unsigned* sort_counts = nullptr;
     bool mirror_valid = false, exposed = false, mirror_has_w = false;
+    bool v_stale = false;   // the mirror is ahead of v: particles_sync_v (cabi.cu) brings v up to date on demand
     double mirror_lo = 0.0, mirror_hi = 0.0;
 };
 
