@@ -92,9 +92,10 @@ def main():
     sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
     # (default ring, 512-worker "fat" ring forced at this small size, register passes, ring for every mode, per-warp /
     # per-CTA CAS fallbacks, tile-sorted deposit)
+    # and the velocity-sorted passes (kernels_lbs.cu): sorted mirror (2) and unsorted mirror (3: every trip on the mixed-cell path)
     for env in ({"VPM_TUNE_LBTMA": "-1"}, {"VPM_TUNE_LBFAT": "2"}, {"VPM_TUNE_LBTMA": "0"}, {"VPM_TUNE_LBTMA": "1022", "VPM_TUNE_LBFAT": "0"},
-                {"VPM_TUNE_HM": "1"}, {"VPM_TUNE_HM": "2"}, {"VPM_TUNE_HM": "3"}):
-        for k in ("VPM_TUNE_LBTMA", "VPM_TUNE_HM", "VPM_TUNE_LBFAT"):
+                {"VPM_TUNE_HM": "1"}, {"VPM_TUNE_HM": "2"}, {"VPM_TUNE_HM": "3"}, {"VPM_TUNE_LBSORT": "2"}, {"VPM_TUNE_LBSORT": "3"}):
+        for k in ("VPM_TUNE_LBTMA", "VPM_TUNE_HM", "VPM_TUNE_LBFAT", "VPM_TUNE_LBSORT"):
             os.environ.pop(k, None)
         os.environ.update(env)
         for cons in (False, True):
@@ -107,7 +108,7 @@ def main():
                 vpm.run_(gi)
                 vo, _ = vs.rk438(vv, ww, 0.8, 0.02, 2, conservative=cons)
                 assert np.abs(d.get("v") - vo).max() < 1e-10, (env, cons, uw)
-    for k in ("VPM_TUNE_LBTMA", "VPM_TUNE_HM", "VPM_TUNE_LBFAT"):
+    for k in ("VPM_TUNE_LBTMA", "VPM_TUNE_HM", "VPM_TUNE_LBFAT", "VPM_TUNE_LBSORT"):
         os.environ.pop(k, None)
     # entropy history (gather pass with the replicated table + the ENT phase of the field kernel)
     d = vpm.ParticleDistribution(1, 1, n).set(np.zeros(n), vv, ww)

@@ -47,10 +47,13 @@ def run(vpm, n, nsteps, conservative, chunk, entropy=False):
     diags, ents = [], []
     t0 = time.perf_counter()
     done = 0
+    step_s = 0.0      # time inside the stepper calls (synchronous: they return with the diagnostics history on the host)
     while done < nsteps:
         k = min(chunk, nsteps - done)
         gi = vpm.GeometricIntegrator(model, vpm.tspan_for(k, dt), dt)
+        t1 = time.perf_counter()
         vpm.run_(gi, entropy=entropy)
+        step_s += time.perf_counter() - t1
         diags.append(gi.diagnostics if not diags else gi.diagnostics[1:])
         if entropy:
             ents.append(gi.entropy if not ents else gi.entropy[1:])
@@ -58,7 +61,7 @@ def run(vpm, n, nsteps, conservative, chunk, entropy=False):
         snaps.append(dict(t=done * dt, **moments(d.get("v"))))
     wall = time.perf_counter() - t0
     dg = np.concatenate(diags)
-    return dg, snaps, wall, (np.concatenate(ents) if entropy else None)
+    return dg, snaps, wall, (np.concatenate(ents) if entropy else None), step_s
 
 
 def main(n=int(1e7), nsteps=50000, models=("clb", "lb"), entropy=False):
@@ -66,7 +69,7 @@ def main(n=int(1e7), nsteps=50000, models=("clb", "lb"), entropy=False):
     out = {"particles": n, "steps": nsteps, "dt": 1e-2, "nu": 1.0}
     chunk = max(nsteps // 10, 1)
     for cons in [m == "clb" for m in models]:
-        dg, snaps, wall, S = run(vpm, n, nsteps, cons, chunk, entropy)
+        dg, snaps, wall, S, step_s = run(vpm, n, nsteps, cons, chunk, entropy)
         key = "clb" if cons else "lb"
         out[key] = {
             "sum_v_first_last": [float(dg[0, 0]), float(dg[-1, 0])],
@@ -76,6 +79,8 @@ def main(n=int(1e7), nsteps=50000, models=("clb", "lb"), entropy=False):
             "snapshots": snaps,
             "wall_s": wall,
             "particle_steps_per_s_incl_snapshots": n * nsteps / wall,
+            # the snapshots are host work (download + numpy moments of all velocities); the stepping itself:
+            "stepper_s": step_s, "ms_per_step": 1e3 * step_s / nsteps, "particle_steps_per_s": n * nsteps / step_s,
         }
         if S is not None:
             var = snaps[-1]["var"]

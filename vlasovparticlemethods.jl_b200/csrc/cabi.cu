@@ -996,6 +996,30 @@ int vpm_vspace_create(vpm_ctx* ctx, double lo, double hi, int nknots, int order,
     std::vector<double> z1((size_t)vs->nv + 8, 0.0), z2((size_t)vs->nv, 0.0), z3((size_t)vs->ncell * TS, 0.0), z4(8, 0.0);
     std::vector<double> z5((size_t)vs->ncell * (2 * order + 2) + 8, 0.0);
     int rc = VPM_OK;
+    if (vs->nv <= 64) {
+        // dense inverse from the banded factor, column by column (cond(M) ~ 20 on these grids: nothing is lost): the field
+        // kernel then solves with one row product per thread instead of a serial chain of 2 nv substitution rows
+        const int nv = vs->nv, K = order;
+        std::vector<double> inv((size_t)nv * nv, 0.0), y(nv);
+        const std::vector<double>& L = vs->chol_host;   // L[i*K + k] = L(i, i-k)
+        for (int col = 0; col < nv; col++) {
+            for (int i = 0; i < nv; i++) {
+                double t = i == col ? 1.0 : 0.0;
+                for (int k = 1; k < K && k <= i; k++) t -= L[(size_t)i * K + k] * y[i - k];
+                y[i] = t / L[(size_t)i * K];
+            }
+            for (int i = nv - 1; i >= 0; i--) {
+                double t = y[i];
+                for (int k = 1; k < K && i + k < nv; k++) t -= L[(size_t)(i + k) * K + k] * y[i + k];
+                y[i] = t / L[(size_t)i * K];
+            }
+            for (int i = 0; i < nv; i++) inv[(size_t)i * nv + col] = y[i];
+        }
+        if ((rc = upload(ctx, &vs->minv, inv))) {
+            vpm_vspace_destroy(vs);
+            return rc;
+        }
+    }
     if ((rc = upload(ctx, &vs->psum, z5)) || (rc = upload(ctx, &vs->pieces, pieces)) || (rc = upload(ctx, &vs->chol, vs->chol_host)) || (rc = upload(ctx, &vs->rhs, z1)) ||
         (rc = upload(ctx, &vs->coef, z2)) || (rc = upload(ctx, &vs->ftab, z3)) || (rc = upload(ctx, &vs->scal, z4))) {
         vpm_vspace_destroy(vs);
@@ -1011,7 +1035,7 @@ int vpm_vspace_destroy(vpm_vspace* vs)
     cudaSetDevice(vs->ctx->device);
     cudaStreamSynchronize(vs->ctx->stream);
     cudaFree(vs->pieces); cudaFree(vs->chol); cudaFree(vs->rhs); cudaFree(vs->coef); cudaFree(vs->ftab);
-    cudaFree(vs->scal); cudaFree(vs->diag); cudaFree(vs->ent); cudaFree(vs->psum);
+    cudaFree(vs->scal); cudaFree(vs->diag); cudaFree(vs->ent); cudaFree(vs->psum); cudaFree(vs->minv);
     delete vs;
     return VPM_OK;
 }

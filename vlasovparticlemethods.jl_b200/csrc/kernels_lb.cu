@@ -23,6 +23,7 @@
 // Kernels: lb_pass_ring_kernel (warp-specialised TMA ring, default for the deposit passes), lb_pass_kernel
 // (register prefetch: gather-only modes, unaligned / tiny inputs, per-warp and per-CTA histogram fallbacks),
 // lb_field_kernel (one CTA: reduce, all-reduce, banded Cholesky solve, per-cell table, CLB coefficients).
+#include <algorithm>
 #include <climits>
 #include <cstdlib>
 
@@ -764,6 +765,8 @@ struct LbFieldDev {
     double* psum;       // [ncell * (2K+2) + nred]: reduced (all-reduced) power sums | scalar sums
     int ps_uw;          // declared uniform weights: W_m = wu S_m
     int pc_smem;        // the piece table is staged in shared memory (small grids) instead of read from global memory
+    const double* minv; // dense inverse of the mass matrix (small grids, else null): the solve becomes one row product per thread
+    int psum_out;       // PS_REDUCE must leave its result in psum (another kernel or the all-reduce reads it)
     double wu, lo, h;
 };
 
@@ -778,23 +781,27 @@ constexpr int kCholW = kMaxOrder;
 __global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbFieldDev F)
 {
     extern __shared__ double sm[];
+    __shared__ double s_m5[5];
     double* s_full = sm;                    // nbfull
     double* s_y = s_full + F.nbfull;        // nv
     double* s_chol = s_y + F.nv;            // (nv + kCholW - 1) * kCholW: padded rows, trailing zero rows
     // sorted passes only (phases & LBF_PS_*): power sums, monomial table of the new spline, per-cell moment terms, CTA ranges
     const int NA = 2 * F.K + 2, ncol = F.ncell * NA;
-    double* s_pc = s_chol + (F.nv + kCholW - 1) * kCholW;  // ncell * K * K (pc_smem): the piece table, a constant operator
+    double* s_minv = s_chol + (F.nv + kCholW - 1) * kCholW; // nv * nv (F.minv): dense inverse of the mass matrix
+    double* s_pc = s_minv + (F.minv ? F.nv * F.nv : 0);     // ncell * K * K (pc_smem): the piece table, a constant operator
     double* s_P = s_pc + (F.pc_smem ? F.ncell * F.K * F.K : 0);   // ncol + 8
     double* s_ft = s_P + ncol + 8;                          // ncell * K
-    double* s_mom = s_ft + F.ncell * F.K;                   // 5 * ncell
-    int* s_rng = reinterpret_cast<int*>(s_mom + 5 * F.ncell);   // 2 * nparts
+    double* s_mom = s_ft + F.ncell * F.K;                   // max(5 * ncell, nbfull * K): per-cell moment terms / per-(bin, j) terms
+    int* s_rng = reinterpret_cast<int*>(s_mom + max(5 * F.ncell, F.nbfull * F.K));   // 2 * nparts
     int* s_cfirst = s_rng + 2 * F.nparts;                       // ncell: first / last CTA that touched each cell
     int* s_clast = s_cfirst + F.ncell;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nwarps = nt / 32;
     const int K = F.K, nv = F.nv;
 
     pdl_trigger();
-    if (F.phases & LBF_SOLVE) {
+    if ((F.phases & LBF_SOLVE) && F.minv) {
+        for (int i = tid; i < nv * nv; i += nt) s_minv[i] = F.minv[i];
+    } else if (F.phases & LBF_SOLVE) {
         // s_chol[i][0] = 1 / L(i,i), s_chol[i][k] = L(i, i-k) for 1 <= k < K, k <= i; zero elsewhere
         // (constant operator: staged before the dependency wait, while the particle pass drains)
         for (int i = tid; i < (nv + kCholW - 1) * kCholW; i += nt) {
@@ -848,49 +855,60 @@ __global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbField
             const int c = col / NA;
             const int bl = s_clast[c];
             double sum = 0.0;
-            for (int b0 = s_cfirst[c]; b0 <= bl; b0 += 8) {
-                double t[8];
+            for (int b0 = s_cfirst[c]; b0 <= bl; b0 += 16) {
+                double t[16];
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
+                for (int k = 0; k < 16; k++) {
                     const int b = min(b0 + k, bl);
                     const bool ok = b0 + k <= bl && s_rng[2 * b] <= c && c <= s_rng[2 * b + 1];
                     t[k] = ok ? F.partials[(size_t)b * ncol + col] : 0.0;
                 }
 #pragma unroll
-                for (int k = 0; k < 8; k++) sum += t[k];
+                for (int k = 0; k < 16; k++) sum += t[k];
             }
-            F.psum[col] = sum;
+            s_P[col] = sum;
+            if (F.psum_out) F.psum[col] = sum;
         }
         if (warp < F.nred) {
             const double sc = warp_sum(strided_sum(F.red_partials + warp, (size_t)kRedW, F.nparts, lane));
-            if (lane == 0) F.psum[ncol + warp] = sc;
+            if (lane == 0) {
+                s_P[ncol + warp] = sc;
+                if (F.psum_out) F.psum[ncol + warp] = sc;
+            }
         }
         __syncthreads();
         if (F.p2p.seq) p2p_allreduce(F.p2p, F.psum, ncol + F.nred);   // power sums | scalars: one fused peer-memory all-reduce
     }
     if (F.phases & LBF_PS_CONVERT) {
-        for (int i = tid; i < ncol + F.nred; i += nt) s_P[i] = F.psum[i];
-        __syncthreads();
+        if (F.psum_out) {   // reduced by another launch, or all-reduced just now
+            for (int i = tid; i < ncol + F.nred; i += nt) s_P[i] = F.psum[i];
+            __syncthreads();
+        }
         if (tid < F.nred) {
             F.rhs[nv + tid] = s_P[ncol + tid];
             if (F.nred == 2 && F.diag && F.diag_slot >= 0) F.diag[2 * F.diag_slot + tid] = s_P[ncol + tid];   // sum v, sum v^2
         }
-        // right-hand side of the projection: bin b = c + j collects function j of cell c, B_{c,j}(u) = sum_m pieces[c][j][m] u^m
-        for (int b = tid; b < F.nbfull; b += nt) {
-            double sum = 0.0;
-            for (int j = 0; j < K; j++) {
-                const int c = b - j;
-                if (c < 0 || c >= F.ncell) continue;
+        // right-hand side of the projection: bin b = c + j collects function j of cell c, B_{c,j}(u) = sum_m pieces[c][j][m] u^m;
+        // one thread per (b, j), the K terms of a bin added in order of j
+        for (int i = tid; i < F.nbfull * K; i += nt) {
+            const int b = i / K, j = i - b * K, c = b - j;
+            double r = 0.0;
+            if (c >= 0 && c < F.ncell) {
                 const double* pc = pieces + ((size_t)c * K + j) * K;
                 const double* Pc = s_P + c * NA + (F.ps_uw ? K : 0);
-                double r = 0.0;
                 for (int m = 0; m < K; m++) r = fma(pc[m], Pc[m], r);
-                sum += F.ps_uw ? F.wu * r : r;
+                if (F.ps_uw) r *= F.wu;
             }
-            s_full[b] = sum;
+            s_mom[i] = r;
         }
         __syncthreads();
-        for (int i = tid; i < nv; i += nt) F.rhs[i] = s_full[i + F.off];
+        for (int b = tid; b < F.nbfull; b += nt) {
+            double sum = 0.0;
+            for (int j = 0; j < K; j++) sum += s_mom[b * K + j];
+            s_full[b] = sum;
+            const int i = b - F.off;
+            if (i >= 0 && i < nv) F.rhs[i] = sum;
+        }
         __syncthreads();
     }
     const bool reduced_here = ((F.phases & LBF_REDUCE) && !F.p2p.seq) || (F.phases & LBF_PS_CONVERT);   // rhs is still in s_full
@@ -904,7 +922,15 @@ __global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbField
         // ldiv!(coefficients, cholesky(M), rhs): banded forward / backward substitution
         for (int i = tid; i < nv; i += nt) s_y[i] = reduced_here ? s_full[i + F.off] : F.rhs[i];
         __syncthreads();
-        if (tid == 0) {
+        if (F.minv) {
+            // small grids: coefficients = M^-1 rhs with the dense inverse staged above, one row per thread, fixed order
+            // (the band substitution below is a serial chain of 2 nv rows on one thread: 4.5 us of a 24 us kernel)
+            double y = 0.0;
+            if (tid < nv)
+                for (int j = 0; j < nv; j++) y = fma(s_minv[tid * nv + j], s_y[j], y);
+            __syncthreads();
+            if (tid < nv) s_y[tid] = y;
+        } else if (tid == 0) {
             double y1 = 0.0, y2 = 0.0, y3 = 0.0, y4 = 0.0, y5 = 0.0;
             for (int i = 0; i < nv; i++) {
                 const double* c = s_chol + i * kCholW;
@@ -984,18 +1010,23 @@ __global__ void __launch_bounds__(kLbFieldThreads) lb_field_kernel(const LbField
             double sum = 0.0;
             for (int c = lane; c < F.ncell; c += 32) sum += s_mom[warp * F.ncell + c];
             sum = warp_sum(sum);
-            if (lane == 0) F.rhs[nv + warp] = sum;
+            if (lane == 0) {
+                F.rhs[nv + warp] = sum;
+                s_m5[warp] = sum;
+            }
         }
         __syncthreads();
     }
     if ((F.phases & LBF_COEFF) && tid == 0) {
         // compute_coefficients: src/models/lenard_bernstein_conservative.jl:11-21
-        const double n = F.rhs[nv], nu = F.rhs[nv + 1], ne = F.rhs[nv + 2];
-        const double B1 = -F.rhs[nv + 3], B2 = -F.rhs[nv + 4];
+        double m5[5];
+        for (int k = 0; k < 5; k++) m5[k] = (F.phases & LBF_PS_COEFF) ? s_m5[k] : F.rhs[nv + k];
+        const double n = m5[0], nu = m5[1], ne = m5[2];
+        const double B1 = -m5[3], B2 = -m5[4];
         const double det = n * ne - nu * nu;
         F.scal[0] = (ne * B1 - nu * B2) / det;
         F.scal[1] = -(nu * B1 - n * B2) / det;
-        for (int k = 0; k < 5; k++) F.scal[2 + k] = F.rhs[nv + k];
+        for (int k = 0; k < 5; k++) F.scal[2 + k] = m5[k];
     }
     if ((F.phases & LBF_DIAG) && tid == 0 && F.diag && F.diag_slot >= 0) {
         F.diag[2 * F.diag_slot] = F.rhs[nv];
@@ -1212,14 +1243,18 @@ int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nr
     const size_t pc_bytes = sizeof(double) * (size_t)vs->ncell * vs->K * vs->K;
     F.pc_smem = pc_bytes <= 32 * 1024;
     if (F.pc_smem) smem += pc_bytes;
+    F.minv = vs->minv;
+    if (F.minv) smem += sizeof(double) * (size_t)vs->nv * vs->nv;
     if (phases & (LBF_PS_REDUCE | LBF_PS_CONVERT | LBF_PS_COEFF))
-        smem += sizeof(double) * ((size_t)ncol + 8 + (size_t)vs->ncell * vs->K + 5 * (size_t)vs->ncell) +
+        smem += sizeof(double) * ((size_t)ncol + 8 + (size_t)vs->ncell * vs->K + std::max(5 * (size_t)vs->ncell, (size_t)vs->nbfull * vs->K)) +
                 sizeof(int) * (2 * (size_t)nparts + 2 * (size_t)vs->ncell);
     if (smem > ctx->smem_optin) return fail(VPM_ERR_UNSUPPORTED, "v-space too large for the single-CTA field kernel");
     if (smem > 48 * 1024) VPM_CUDA(cudaFuncSetAttribute(lb_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     const int red = phases & (LBF_REDUCE | LBF_SCALRED | LBF_PS_REDUCE);
     F.p2p = P2PDev{};
+    // the reduced power sums stay in shared memory unless an all-reduce or a second launch has to read them
+    F.psum_out = (ctx->p2p.nranks > 1 || ctx->comm.comm || !(phases & LBF_PS_REDUCE) || !(phases & LBF_PS_CONVERT)) ? 1 : 0;
     if (ctx->p2p.nranks > 1 && red) {
         if ((size_t)vs->nv + 8 > (size_t)kP2PCap || (ps && (size_t)ncol + 8 > (size_t)kP2PCap))
             return fail(VPM_ERR_UNSUPPORTED, "coefficient vector exceeds the peer mailbox slot");

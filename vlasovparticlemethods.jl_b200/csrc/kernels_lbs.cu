@@ -598,7 +598,10 @@ int launch_lbs_pass_k(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* 
     // ring: what two CTAs per SM leave, capped (deeper rings measured slower on the VP pass: DESIGN 4.1)
     int ring_kb = 48;
     if (const char* e = getenv("VPM_TUNE_LBSRING")) ring_kb = atoi(e);
-    const size_t per_cta = ctx->smem_sm / 2 - ctx->smem_reserved;
+    // two CTAs per SM (82-96 registers).  Tried: stage 1 and the deposit-only pass compiled for three (72 registers): slower
+    // (stage 1 0.419 vs 0.390 ms, deposit-only 0.31 vs 0.27 ms) -- the tighter register budget costs more than the extra warps buy
+    size_t per_cta = ctx->smem_sm / 2 - ctx->smem_reserved;
+    if (per_cta < fixed + 2 * stage_bytes) per_cta = ctx->smem_optin;   // large v-grids: one CTA per SM
     if (per_cta < fixed + stage_bytes) return fail(VPM_ERR_UNSUPPORTED, "v-space too large for the sorted LB pass");
     int stages = (int)((per_cta - fixed) / stage_bytes);
     const int cap = (int)std::max<size_t>(2, (size_t)ring_kb * 1024 / stage_bytes);
@@ -642,7 +645,7 @@ int lbs_supported(const vpm_ctx* ctx, const vpm_vspace* vs)
     const int NA = 2 * vs->K + 2;
     if ((size_t)vs->ncell * NA + 8 > (size_t)kP2PCap) return 0;   // one all-reduce slot must hold the power sums
     const size_t fixed = sizeof(double) * (2 * (kBlock / 32) + (size_t)(vs->ncell + 1) * (vs->K + 3) + (size_t)(kBlock / 32) * (vs->ncell + 1) * NA);
-    return fixed + 2 * 4 * kLbsTile * sizeof(double) + 1024 <= ctx->smem_sm / 2 - ctx->smem_reserved;
+    return fixed + 4 * kLbsTile * sizeof(double) + 1024 <= ctx->smem_optin;
 }
 
 int launch_lbs_pass(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* grid_out)

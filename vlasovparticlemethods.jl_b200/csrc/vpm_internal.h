@@ -123,6 +123,7 @@ struct vpm_vspace {
     std::vector<double> chol_host;   // banded lower factor [nv][K] (chol[i][k] = L(i, i-k))
     double* pieces = nullptr;  // [ncell][K][K] monomial coefficients of B_{c+j} on cell c
     double* chol = nullptr;    // [nv][K]
+    double* minv = nullptr;    // [nv][nv] dense inverse of the mass matrix (nv <= 64 only): the field kernel's solve as one row product per thread
     double* rhs = nullptr;     // [nv]
     double* coef = nullptr;    // [nv]
     double* ftab = nullptr;    // [ncell][TS] F (K) then G (K-1) monomial coefficients
