@@ -171,3 +171,53 @@ def test_sorted_trajectory_frames(vpm, oracle, perr, monkeypatch, tmp_path):
     for f, k in ((1, 2), (2, 4)):
         vo, _ = vs.rk438(v, w, nu, dt, k, conservative=True)
         perr(f"clb_sorted_frame{f}", nrm(z[f], vo), TOL)
+
+
+def test_sorted_mirror_follows_other_writers(vpm, oracle, perr, monkeypatch):
+    """collisions, Vlasov-Poisson steps (the kick rewrites v: the mirror must be dropped and v synced first), collisions
+    again -- against the same sequence on the oracle; then a caller holding WRITABLE device pointers (mirror rebuilt at every
+    call from then on)"""
+    monkeypatch.setenv("VPM_TUNE_LBSORT", "2")
+    n, nu, dt = 30_001, 0.9, 0.02
+    L = 2 * np.pi / 0.3
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0.0, L, n)
+    v, _ = ensemble(n, 31, edge=False)
+    w = np.full(n, L / n)
+    vs, xs = oracle.VSpace(-10.0, 10.0, 41, 4), oracle.XSpace(0.0, L, 4, 16)
+    sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
+    d = vpm.ParticleDistribution(1, 1, n).set(x, v, w)
+    clb = vpm.ConservativeLenardBernstein(d, vpm.CollisionEntropy(sd), nu=nu)
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), 4, 16))
+    vo, xo = v, x
+    for _ in range(2):
+        vpm.run_(vpm.GeometricIntegrator(clb, vpm.tspan_for(2, dt), dt))
+        vo, _ = vs.rk438(vo, w, nu, dt, 2, conservative=True)
+        vpm.run_(vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(2, 0.1), 0.1, field="selfconsistent"))
+        xo, vo, _, _ = xs.strang_selfconsistent(xo, vo, w, 0.1, 2)
+    xg, vg, _ = d.get()
+    perr("sorted_collisions_then_vp_x", nrm(xg, xo), TOL)
+    perr("sorted_collisions_then_vp_v", nrm(vg, vo), TOL)
+    # writable pointers handed out: the library can no longer know when v changes
+    d.ptrs(writable=True)
+    for _ in range(2):
+        vpm.run_(vpm.GeometricIntegrator(clb, vpm.tspan_for(1, dt), dt))
+        vo, _ = vs.rk438(vo, w, nu, dt, 1, conservative=True)
+    perr("sorted_after_writable_pointers_v", nrm(d.get("v"), vo), TOL)
+
+
+@pytest.mark.parametrize("case", ["one_cell", "identical", "all_outside"])
+def test_sorted_degenerate_ensembles(vpm, oracle, perr, monkeypatch, case):
+    """every particle in one cell (all CTAs feed the same columns), identical velocities (ties in the sort), nobody inside
+    the spline domain (only the ghost row is touched: zero right-hand side)"""
+    monkeypatch.setenv("VPM_TUNE_LBSORT", "2")
+    n, nu, dt, ns = 20_000, 0.9, 0.02, 2
+    rng = np.random.default_rng(9)
+    v = {"one_cell": 0.26 + 0.2 * rng.random(n), "identical": np.full(n, 1.2345), "all_outside": 10.5 + rng.random(n)}[case]
+    w = rng.uniform(0.5, 1.5, n) / n
+    vs = oracle.VSpace(-10.0, 10.0, 41, 4)
+    sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
+    d, gi = run_gpu(vpm, sd, v, w, nu, dt, ns, False)
+    vo, do = vs.rk438(v, w, nu, dt, ns, conservative=False)
+    perr("lb_sorted_rk438_v@" + case, np.abs(d.get("v") - vo).max() / np.abs(vo).max(), TOL)
+    perr("lb_sorted_moment_history@" + case, (np.abs(gi.diagnostics[:, :2] - do) / np.array([np.abs(v).sum(), (v * v).sum()])).max(), TOL)

@@ -754,6 +754,7 @@ int vpm_push_drift(vpm_xspace* xs, vpm_particles* p, double tau)
 {
     VPM_REQUIRE(xs && p, "vpm_push_drift: NULL argument");
     VPM_CUDA(cudaSetDevice(xs->ctx->device));
+    VPM_CHECK(particles_sync_v(p));   // reads v
     VpPass ps{};
     ps.x_in = p->x; ps.v_in = p->v; ps.w = p->w; ps.x_out = p->x; ps.n = p->n;
     ps.flags = VP_POST1 | VP_WRITE_X;
@@ -1258,6 +1259,7 @@ static int ensure_mirror(vpm_vspace* vs, vpm_particles* p, int sort_mode)
     vpm_ctx* ctx = vs->ctx;
     const bool need_w = !p->uw;
     if (p->mirror_valid && !p->exposed && p->mirror_lo == vs->lo && p->mirror_hi == vs->hi && (p->mirror_has_w || !need_w)) return VPM_OK;
+    VPM_CHECK(particles_sync_v(p));   // a rebuild starts from v in the caller's order: bring it up to date first
     const size_t bytes = sizeof(double) * (size_t)(p->n + (p->n & 1));
     const int sort_grid = ctx->sm_count * kSortGridPerSm;
     if (!p->sv) {
@@ -1338,7 +1340,11 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
         }
         // p->v gets the new velocities back in the caller's order when somebody asks for them (particles_sync_v): a random
         // gather of 1e8 doubles costs as much as a whole RK438 step
-        if (nsteps > 0) p->v_stale = true;
+        // (a caller holding writable device pointers may look at v at any time: written back at once)
+        if (nsteps > 0) {
+            p->v_stale = true;
+            if (p->exposed) VPM_CHECK(particles_sync_v(p));
+        }
         return VPM_OK;
     }
     VPM_CHECK(mirror_invalidate(p));   // this path advances v itself
