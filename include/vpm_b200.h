@@ -86,7 +86,14 @@ int vpm_particles_destroy(vpm_particles* p);
 int64_t vpm_particles_size(const vpm_particles* p);
 /* raw device pointers of the SoA arrays (valid until destroy).  Asking for the WRITABLE w pointer ends a uniform-weight
  * declaration (vpm_particles_set_uniform_weight): the caller may rewrite the weights through it.  Read-only users
- * (operator-level calls that take v_dev / w_dev) use vpm_particles_ptrs_const, which leaves the declaration alone. */
+ * (operator-level calls that take v_dev / w_dev) use vpm_particles_ptrs_const, which leaves the declaration alone.
+ * Contents and the collision steppers: vpm_lb_rk438_steps / vpm_lb_run advance a velocity-sorted copy of (v, w) held
+ * inside the object (from 2^18 particles) and bring v[] up to date, in the caller's particle order, whenever it is read
+ * through this API -- download, either pointer accessor, a trajectory frame, any other stepper.  So: call
+ * vpm_particles_ptrs_const AGAIN after a collision stepper call before reading v through a raw pointer obtained earlier;
+ * and once the WRITABLE v or w pointer has been handed out, every collision stepper call writes v back at once and
+ * rebuilds its sorted copy at the next call (a few tens of ms at 1e8 particles), because the library can no longer know
+ * when the caller changes the arrays. */
 int vpm_particles_ptrs(vpm_particles* p, double** x, double** v, double** w);
 int vpm_particles_ptrs_const(const vpm_particles* p, const double** x, const double** v, const double** w);
 /* z: host, column-major ld x N with rows x,v[,w]; ld = 3 moves x,v,w; ld = 2 moves x,v only */
@@ -202,7 +209,10 @@ int vpm_lb_rhs(vpm_vspace* vs, const double* v_dev, const double* w_dev, int64_t
 /* GeometricIntegrator(model, tspan, tstep) + run! with RK438: src/models/lenard_bernstein.jl:68-84,
  * lenard_bernstein_conservative.jl:88-104, src/methods/geometric_integrator.jl:12-44.
  * Advances p->v by nsteps steps on the device.  diag_host: (nsteps+1) x 2 rows (sum v, sum v^2)
- * (scripts/lenard_bernstein_conservative.jl:49-50); may be NULL. */
+ * (scripts/lenard_bernstein_conservative.jl:49-50); may be NULL.
+ * From 2^18 particles the steps run on a velocity-sorted mirror of (v, w) that is built once (the collision flow cannot
+ * reorder particles in v): four passes and 136 B per particle-step for both models; see vpm_particles_ptrs for when
+ * v[] itself is refreshed.  Results do not depend on which path runs (parity 1e-12 either way). */
 int vpm_lb_rk438_steps(vpm_vspace* vs, vpm_particles* p, double nu, double dt, int nsteps, int conservative,
                        double* diag_host);
 int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double dt, int nsteps, int conservative);
