@@ -303,6 +303,8 @@ class Bench:
 
     def barrier(self):
         if self.world > 1:
+            if not hasattr(self, "_align"):
+                self._align = self.torch.zeros(1, device="cuda")
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
@@ -322,6 +324,10 @@ class Bench:
         l0 = self.ctx.launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
+        if self.world > 1:
+            # device-side rendezvous on the launching stream: the host-side barrier leaves the ranks' launch times ~100 us apart,
+            # which the first fused all-reduce of the timed region would absorb (a fixed cost per call, visible in short windows)
+            self.dist.all_reduce(self._align)
         e0.record(self.stream)
         run_steps(steps)
         e1.record(self.stream)

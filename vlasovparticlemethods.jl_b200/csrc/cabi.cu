@@ -417,6 +417,7 @@ static int mirror_invalidate(vpm_particles* p)
 {
     VPM_CHECK(particles_sync_v(p));
     p->mirror_valid = false;
+    p->stag_valid = false;   // (and the carried half drift of the Strang stepper, which was taken with the old v)
     return VPM_OK;
 }
 
@@ -451,7 +452,7 @@ int vpm_particles_destroy(vpm_particles* p)
     cudaStreamSynchronize(p->ctx->stream);
     cudaFree(p->x); cudaFree(p->v); cudaFree(p->w);
     cudaFree(p->q); cudaFree(p->ka); cudaFree(p->kb);
-    cudaFree(p->sv); cudaFree(p->sw); cudaFree(p->sinv); cudaFree(p->sort_counts);
+    cudaFree(p->sv); cudaFree(p->sw); cudaFree(p->sinv); cudaFree(p->sort_counts); cudaFree(p->xstag);
     delete p;
     return VPM_OK;
 }
@@ -463,7 +464,7 @@ int vpm_particles_ptrs(vpm_particles* p, double** x, double** v, double** w)
     VPM_REQUIRE(p, "vpm_particles_ptrs: p is NULL");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
     // ... or the velocities, at any later time: the velocity-sorted mirror of the collision steppers is rebuilt at every call from now on
-    if (v || w) {
+    if (x || v || w) {
         VPM_CHECK(mirror_invalidate(p));
         p->exposed = true;
     }
@@ -498,6 +499,7 @@ int vpm_particles_upload_aos(vpm_particles* p, const double* z, int ld)
     VPM_CHECK(ensure_staging(ctx, (size_t)std::min<int64_t>(chunk, std::max<int64_t>(p->n, 1)) * ld));
     p->v_stale = false;   // v is overwritten as a whole
     p->mirror_valid = false;
+    p->stag_valid = false;
     for (int64_t o = 0; o < p->n; o += chunk) {
         const int64_t m = std::min(chunk, p->n - o);
         VPM_CUDA(cudaMemcpyAsync(ctx->staging, z + o * ld, sizeof(double) * m * ld, cudaMemcpyHostToDevice, ctx->stream));
@@ -533,6 +535,7 @@ int vpm_particles_upload_soa(vpm_particles* p, const double* x, const double* v,
     const size_t bytes = sizeof(double) * (size_t)p->n;
     if (v) p->v_stale = false;   // overwritten as a whole
     if (v || w) VPM_CHECK(mirror_invalidate(p));
+    if (x) p->stag_valid = false;
     if (x) VPM_CUDA(cudaMemcpyAsync(p->x, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (v) VPM_CUDA(cudaMemcpyAsync(p->v, v, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (w) {
@@ -574,8 +577,9 @@ int vpm_sample_bump_on_tail(vpm_particles* p, int64_t offset, int64_t ntotal, ui
     VPM_REQUIRE(p && ntotal > 0 && kappa > 0, "vpm_sample_bump_on_tail: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
     p->uw = false;
-    p->v_stale = false;   // v and w are overwritten as a whole
+    p->v_stale = false;   // x, v and w are overwritten as a whole
     p->mirror_valid = false;
+    p->stag_valid = false;
     return launch_sample_bump_on_tail(p->ctx, p, offset, ntotal, seed, eps, kappa, alpha, sigma, v0);
 }
 
@@ -585,8 +589,9 @@ int vpm_sample_normal(vpm_particles* p, int64_t offset, int64_t ntotal, uint64_t
     VPM_REQUIRE(p && ntotal > 0 && xhi > xlo, "vpm_sample_normal: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
     p->uw = false;
-    p->v_stale = false;   // v and w are overwritten as a whole
+    p->v_stale = false;   // x, v and w are overwritten as a whole
     p->mirror_valid = false;
+    p->stag_valid = false;
     return launch_sample_normal(p->ctx, p, offset, ntotal, seed, xlo, xhi, xmax, xmax_used);
 }
 
@@ -596,8 +601,9 @@ int vpm_sample_maxwellian(vpm_particles* p, int64_t offset, int64_t ntotal, uint
     VPM_REQUIRE(p && ntotal > 0, "vpm_sample_maxwellian: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
     p->uw = false;
-    p->v_stale = false;   // v and w are overwritten as a whole
+    p->v_stale = false;   // x, v and w are overwritten as a whole
     p->mirror_valid = false;
+    p->stag_valid = false;
     return launch_sample_maxwellian(p->ctx, p, offset, ntotal, seed, xlo, xhi, shift, doubled, wnum);
 }
 
@@ -607,8 +613,9 @@ int vpm_sample_uniform(vpm_particles* p, int64_t offset, int64_t ntotal, uint64_
     VPM_REQUIRE(p && ntotal > 0, "vpm_sample_uniform: bad arguments");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
     p->uw = false;
-    p->v_stale = false;   // v and w are overwritten as a whole
+    p->v_stale = false;   // x, v and w are overwritten as a whole
     p->mirror_valid = false;
+    p->stag_valid = false;
     return launch_sample_uniform(p->ctx, p, offset, ntotal, seed, xlo, xhi, vlo, vhi, shift, wnum);
 }
 
@@ -755,6 +762,7 @@ int vpm_push_drift(vpm_xspace* xs, vpm_particles* p, double tau)
     VPM_REQUIRE(xs && p, "vpm_push_drift: NULL argument");
     VPM_CUDA(cudaSetDevice(xs->ctx->device));
     VPM_CHECK(particles_sync_v(p));   // reads v
+    p->stag_valid = false;            // writes x
     VpPass ps{};
     ps.x_in = p->x; ps.v_in = p->v; ps.w = p->w; ps.x_out = p->x; ps.n = p->n;
     ps.flags = VP_POST1 | VP_WRITE_X;
@@ -884,6 +892,45 @@ static int vp_steps(vpm_xspace* xs, double* x, double* v, const double* w, int64
     return VPM_OK;
 }
 
+// Self-consistent Strang steps with a CARRIED stagger (no diagnostics).  The fused pass keeps the particles half a drift
+// ahead (kick(n) + drift/2 | drift/2 + deposit(n+1) in one launch), so a call used to cost nsteps + 1 passes: a prologue
+// (drift/2 + deposit) and an epilogue (kick + drift/2).  Here the LAST pass of a call is a full fused pass as well: it
+// stores the caller-visible position (after the trailing half drift) to p->x, keeps the staggered one in p->xstag and
+// leaves the next step's field solved in xs.  The next call with the same (xs, dt, chi, weights) -- and nobody having
+// touched the particles or the field in between -- starts with a fused pass straight away: nsteps passes per call, one
+// pass per step for callers that step one step per call (was two).  p->x, p->v always hold the official state.
+static int vp_steps_carry(vpm_xspace* xs, vpm_particles* p, double dt, double chi, int nsteps, bool carried)
+{
+    vpm_ctx* ctx = xs->ctx;
+    const double Dt = dt * chi, escale = -1.0 / (chi * chi), wscale = 1.0 / (chi * chi);
+    const int ALL = FIELD_REDUCE | FIELD_SOLVE | FIELD_TABLE;
+    const int kFused = VP_KICK1 | VP_POST1 | VP_POST2 | VP_DEPOSIT | VP_WRITE_X | VP_WRITE_V;
+    int grid = 0;
+    VpPass ps{};
+    ps.v_in = p->v; ps.w = p->w; ps.v_out = p->v; ps.n = p->n;
+    ps.use_uw = p->uw; ps.w_uniform = p->wu;
+    ps.tau_kick = Dt; ps.tau_post1 = 0.5 * Dt; ps.tau_post2 = 0.5 * Dt;
+    if (!carried) {
+        VpPass p1 = ps;
+        p1.x_in = p->x; p1.x_out = p->xstag;
+        p1.flags = VP_POST2 | VP_DEPOSIT | VP_WRITE_X;
+        VPM_CHECK(launch_vp_pass(ctx, xs, p1, &grid));
+        VPM_CHECK(launch_vp_field(ctx, xs, ALL, grid, 1, 0, escale, wscale, -1, -1));
+    }
+    ps.x_in = p->xstag; ps.x_out = p->xstag;
+    for (int it = 1; it <= nsteps; it++) {
+        const bool last = it == nsteps;
+        ps.flags = kFused | (last ? VP_WRITE_XU : 0);
+        ps.xu_out = last ? p->x : nullptr;
+        VPM_CHECK(launch_vp_pass(ctx, xs, ps, &grid));
+        VPM_CHECK(launch_vp_field(ctx, xs, ALL, grid, 1, 0, escale, wscale, -1, -1));
+    }
+    p->stag_valid = true;
+    p->stag_xs = xs; p->stag_gen = xs->field_gen;
+    p->stag_Dt = Dt; p->stag_chi = chi; p->stag_uw = p->uw; p->stag_wu = p->wu;
+    return VPM_OK;
+}
+
 int vpm_vp_strang_steps_async(vpm_xspace* xs, vpm_particles* p, double dt, double chi, int nsteps, int mode, int diag_mode)
 {
     VPM_REQUIRE(xs && p && xs->ctx == p->ctx, "vpm_vp_strang_steps: bad handles");
@@ -895,7 +942,22 @@ int vpm_vp_strang_steps_async(vpm_xspace* xs, vpm_particles* p, double dt, doubl
         // the deposit positions are the particles' positions at call time; the pass that computes the field
         // runs before any push on the same stream, so no copy is needed
     }
-    VPM_CHECK(mirror_invalidate(p));   // the kick changes v
+    // VPM_TUNE_VPCARRY=0: every call ends unstaggered (prologue and epilogue passes, as in round 1)
+    bool tune_carry = true;   // (read per call: the tests switch it inside one process)
+    if (const char* e = getenv("VPM_TUNE_VPCARRY")) tune_carry = atoi(e) != 0;
+    const bool carried = p->stag_valid && p->stag_xs == xs && p->stag_gen == xs->field_gen && p->stag_Dt == dt * chi && p->stag_chi == chi &&
+                         p->stag_uw == p->uw && (!p->uw || p->stag_wu == p->wu);
+    VPM_CHECK(mirror_invalidate(p));   // the kick changes v (this also drops the stagger: `carried` was read first)
+    if (tune_carry && mode == VPM_VP_SELFCONSISTENT && diag_mode == 0 && nsteps >= 1 && !p->exposed) {
+        if (!p->xstag) {
+            const size_t bytes = sizeof(double) * (size_t)(p->n > 0 ? p->n + (p->n & 1) : 2);
+            if (cudaMalloc((void**)&p->xstag, bytes) != cudaSuccess) {
+                p->xstag = nullptr;
+                cudaGetLastError();   // no room for the staggered copy: the two-ended scheme below needs none
+            }
+        }
+        if (p->xstag) return vp_steps_carry(xs, p, dt, chi, nsteps, carried);
+    }
     return vp_steps(xs, p->x, p->v, p->w, p->n, xdep, p->w, p->n, dt, chi, nsteps, mode, diag_mode, p->uw, p->wu);
 }
 
@@ -1110,8 +1172,9 @@ int vpm_resample_v(vpm_vspace* vs, const double* coef_host, vpm_particles* p, in
     VPM_CUDA(cudaSetDevice(ctx->device));
     VPM_CHECK(set_coef(vs, coef_host));
     p->uw = false;
-    p->v_stale = false;   // v and w are overwritten as a whole
+    p->v_stale = false;   // x, v and w are overwritten as a whole
     p->mirror_valid = false;
+    p->stag_valid = false;
     return launch_resample_v(ctx, vs, p, offset, ntotal, seed, jitter, mass_out);
 }
 
@@ -1296,6 +1359,7 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
     VPM_CUDA(cudaSetDevice(ctx->device));
     VPM_CHECK(alloc_scratch(p));
     VPM_CHECK(grow_diag(ctx, &vs->diag, &vs->diag_cap, 2 * ((size_t)nsteps + 2)));
+    if (nsteps > 0) p->stag_valid = false;   // v changes: a carried half drift of the Strang stepper is void
     const int PROJ = LBF_REDUCE | LBF_SOLVE | LBF_TABLE;
     int grid = 0;
     LbPass ps{};

@@ -28,6 +28,7 @@ namespace {
 struct VpDev {
     const double *x_in, *v_in, *w;
     double *x_out, *v_out;
+    double* xu_out;   // VP_WRITE_XU: the position after the trailing half drift (the caller-visible x of a carried stagger)
     long long n;
     int flags;
     double tau_pre, tau_kick, tau_post1, tau_post2;
@@ -52,6 +53,8 @@ constexpr int kMainFlags = VP_KICK1 | VP_POST1 | VP_DIAG | VP_POST2 | VP_DEPOSIT
 constexpr int kFrozenFlags = VP_PRE | VP_KICK1 | VP_KICK2 | VP_POST1 | VP_DIAG | VP_WRITE_X | VP_WRITE_V;
 // the same passes for runs that asked for no diagnostics (diag_mode 0): K, M are not accumulated
 constexpr int kMainFlagsND = kMainFlags & ~VP_DIAG, kFrozenFlagsND = kFrozenFlags & ~VP_DIAG;
+// last pass of a stepper call with a carried stagger: also stores the unstaggered position (48 instead of 40 B per particle)
+constexpr int kMainFlagsXU = kMainFlagsND | VP_WRITE_XU;
 
 // HM: histogram privatisation. 0 = one copy per thread (no atomics), 1 = one copy per warp, 2 = one copy per
 // CTA (shared-memory atomicAdd; for grids whose per-thread copies would not fit in shared memory)
@@ -63,7 +66,8 @@ struct HistCfg {
 template <int K, int FLAGS, int HM, bool P2 = false>
 __device__ __forceinline__ void vp_particle(const VpDev& P, const int flags_rt, const double* __restrict__ s_etab,
                                             double* __restrict__ s_hist, double& x, double& v, const double w,
-                                            double& ksum, double& msum, int* dep_c = nullptr, double* dep_u = nullptr)
+                                            double& ksum, double& msum, int* dep_c = nullptr, double* dep_u = nullptr,
+                                            double* xu = nullptr)
 {
     constexpr int ES = VpCfg<K>::ES;
     const int flags = FLAGS >= 0 ? FLAGS : flags_rt;
@@ -80,6 +84,7 @@ __device__ __forceinline__ void vp_particle(const VpDev& P, const int flags_rt, 
         if (flags & VP_KICK2) v = fma(P.tau_kick, E, v);
     }
     if (flags & VP_POST1) x = fma(P.tau_post1, v, x);
+    if (flags & VP_WRITE_XU) *xu = x;
     if (flags & VP_DIAG) {
         const double wv = w * v;
         msum += wv;
@@ -157,27 +162,31 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
                 if (need_v) vn = ld_stream2(P.v_in + 2 * inext);
                 if (need_w) wn = ld_stream2(P.w + 2 * inext);
             }
-            vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, xa.x, va.x, wa.x, ksum, msum);
-            vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, xa.y, va.y, wa.y, ksum, msum);
+            double2 xu = make_double2(0, 0);
+            vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, xa.x, va.x, wa.x, ksum, msum, nullptr, nullptr, &xu.x);
+            vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, xa.y, va.y, wa.y, ksum, msum, nullptr, nullptr, &xu.y);
             if (flags & VP_WRITE_X) st_stream2(P.x_out + 2 * i, xa);
             if (flags & VP_WRITE_V) st_stream2(P.v_out + 2 * i, va);
+            if (flags & VP_WRITE_XU) st_stream2(P.xu_out + 2 * i, xu);
             xa = xn; va = vn; wa = wn;
             i = inext;
             have = hn;
         }
         if ((P.n & 1) && gtid == 0) {  // odd tail
             const long long t = P.n - 1;
-            double x = P.x_in[t], v = need_v ? P.v_in[t] : 0.0, w = need_w ? P.w[t] : P.w_uniform;
-            vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, x, v, w, ksum, msum);
+            double x = P.x_in[t], v = need_v ? P.v_in[t] : 0.0, w = need_w ? P.w[t] : P.w_uniform, xu = 0.0;
+            vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, x, v, w, ksum, msum, nullptr, nullptr, &xu);
             if (flags & VP_WRITE_X) P.x_out[t] = x;
             if (flags & VP_WRITE_V) P.v_out[t] = v;
+            if (flags & VP_WRITE_XU) P.xu_out[t] = xu;
         }
     } else {
         for (long long i = gtid; i < P.n; i += stride) {
-            double x = P.x_in[i], v = need_v ? P.v_in[i] : 0.0, w = need_w ? P.w[i] : P.w_uniform;
-            vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, x, v, w, ksum, msum);
+            double x = P.x_in[i], v = need_v ? P.v_in[i] : 0.0, w = need_w ? P.w[i] : P.w_uniform, xu = 0.0;
+            vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, x, v, w, ksum, msum, nullptr, nullptr, &xu);
             if (flags & VP_WRITE_X) P.x_out[i] = x;
             if (flags & VP_WRITE_V) P.v_out[i] = v;
+            if (flags & VP_WRITE_XU) P.xu_out[i] = xu;
         }
     }
 
@@ -403,10 +412,12 @@ __global__ void __launch_bounds__(kVpRingThreads, MINB) vp_pass_ring_kernel(cons
             const double2 wa = UW ? wdef : *reinterpret_cast<const double2*>(src + 2 * kTmaTile);
             __syncwarp();
             if (lane == 0 && !P.late_release) mbar_arrive(&s_empty[s]);   // this warp's operands are in registers: the stage may be refilled
-            vp_particle<K, FLAGS, 0, P2>(P, FLAGS, s_etab, s_hist, xa.x, va.x, wa.x, ksum, msum);
-            vp_particle<K, FLAGS, 0, P2>(P, FLAGS, s_etab, s_hist, xa.y, va.y, wa.y, ksum, msum);
+            double2 xu = make_double2(0, 0);
+            vp_particle<K, FLAGS, 0, P2>(P, FLAGS, s_etab, s_hist, xa.x, va.x, wa.x, ksum, msum, nullptr, nullptr, &xu.x);
+            vp_particle<K, FLAGS, 0, P2>(P, FLAGS, s_etab, s_hist, xa.y, va.y, wa.y, ksum, msum, nullptr, nullptr, &xu.y);
             st_stream2(xo + g * kTmaTile, xa);
             st_stream2(vo + g * kTmaTile, va);
+            if (FLAGS & VP_WRITE_XU) st_stream2(P.xu_out + 2 * tid + g * kTmaTile, xu);
             if (lane == 0 && P.late_release) mbar_arrive(&s_empty[s]);
             if (++s == STAGES) {
                 s = 0;
@@ -416,10 +427,11 @@ __global__ void __launch_bounds__(kVpRingThreads, MINB) vp_pass_ring_kernel(cons
     }
     // remainder (< one tile): plain loads, spread over the grid
     for (long long i = ntiles * kTmaTile + (long long)blockIdx.x * kBlock + tid; i < P.n; i += (long long)gridDim.x * kBlock) {
-        double x = P.x_in[i], v = P.v_in[i], w = UW ? P.w_uniform : P.w[i];
-        vp_particle<K, FLAGS, 0, P2>(P, FLAGS, s_etab, s_hist, x, v, w, ksum, msum);
+        double x = P.x_in[i], v = P.v_in[i], w = UW ? P.w_uniform : P.w[i], xu = 0.0;
+        vp_particle<K, FLAGS, 0, P2>(P, FLAGS, s_etab, s_hist, x, v, w, ksum, msum, nullptr, nullptr, &xu);
         P.x_out[i] = x;
         P.v_out[i] = v;
+        if (FLAGS & VP_WRITE_XU) P.xu_out[i] = xu;
     }
 
     vp_worker_sync();
@@ -496,11 +508,12 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_tiled_kernel(const VpDev
             const long long i = base + (long long)k * kBlock + tid;
             pc[k] = -1;
             if (i < P.n) {
-                double x = P.x_in[i], v = need_v ? P.v_in[i] : 0.0;
+                double x = P.x_in[i], v = need_v ? P.v_in[i] : 0.0, xu = 0.0;
                 pw[k] = need_w ? P.w[i] : P.w_uniform;
-                vp_particle<K, -1, 3>(P, flags, s_etab, nullptr, x, v, pw[k], ksum, msum, &pc[k], &pu[k]);
+                vp_particle<K, -1, 3>(P, flags, s_etab, nullptr, x, v, pw[k], ksum, msum, &pc[k], &pu[k], &xu);
                 if (flags & VP_WRITE_X) P.x_out[i] = x;
                 if (flags & VP_WRITE_V) P.v_out[i] = v;
+                if (flags & VP_WRITE_XU) P.xu_out[i] = xu;
                 if (dep) pr[k] = atomicAdd(&s_cnt[pc[k]], 1);
                 else pc[k] = -1;
             }
@@ -743,7 +756,7 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
 {
     constexpr int ES = VpCfg<K>::ES;
     VpDev P{};
-    P.x_in = p.x_in; P.v_in = p.v_in; P.w = p.w; P.x_out = p.x_out; P.v_out = p.v_out;
+    P.x_in = p.x_in; P.v_in = p.v_in; P.w = p.w; P.x_out = p.x_out; P.v_out = p.v_out; P.xu_out = p.xu_out;
     P.n = p.n; P.flags = p.flags;
     P.tau_pre = p.tau_pre; P.tau_kick = p.tau_kick; P.tau_post1 = p.tau_post1; P.tau_post2 = p.tau_post2;
     P.lo = xs->lo; P.invh = xs->invh; P.nh = xs->nh; P.fm = xs->fm;
@@ -785,7 +798,7 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
         return fail(VPM_ERR_UNSUPPORTED, "x-space too large: the field table and one histogram copy must fit in shared memory");
 
     auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    const bool vec = aligned16(p.x_in) && aligned16(p.v_in) && aligned16(p.w) && aligned16(p.x_out) && aligned16(p.v_out);
+    const bool vec = aligned16(p.x_in) && aligned16(p.v_in) && aligned16(p.w) && aligned16(p.x_out) && aligned16(p.v_out) && aligned16(p.xu_out);
 
     // VPM_TUNE_MINB = 2|3|4 selects the register/occupancy trade-off of the fused step kernel
     // (91 / 85 / 64 registers per thread); default chosen from ncu runs, see DESIGN.md
@@ -801,8 +814,9 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
         const char* e = getenv("VPM_TUNE_TMA");
         return e ? atoi(e) : 5;
     }();
-    const bool nodiag = p.flags == kMainFlagsND || p.flags == kFrozenFlagsND;   // ring kernel only
-    const bool main_f = p.flags == kMainFlags || p.flags == kMainFlagsND, frozen_f = p.flags == kFrozenFlags || p.flags == kFrozenFlagsND;
+    const bool carry_f = p.flags == kMainFlagsXU;   // ring kernel only (everything else takes the run-time-flag kernels)
+    const bool nodiag = p.flags == kMainFlagsND || p.flags == kFrozenFlagsND || carry_f;   // ring kernel only
+    const bool main_f = p.flags == kMainFlags || p.flags == kMainFlagsND || carry_f, frozen_f = p.flags == kFrozenFlags || p.flags == kFrozenFlagsND;
     const bool tma = tune_tma && !tiled && hm == 0 && vec && (main_f || frozen_f) && (tune_tma >= 5 || !nodiag);
     const bool ring = tma && tune_tma >= 5;
     const int tune_rel = [] {
@@ -825,11 +839,13 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     } else if (ring && p.use_uw) {
         // uniform weights: two tiles per stage, so a third stage fits in the shared memory of the 3-CTA/SM configuration
         smem += 3 * 2 * tile_b + sizeof(uint64_t) * 2 * 3;
-        if (nodiag) kern = p2 ? vp_pass_ring_kernel<K, kMainFlagsND, 3, 3, true, true> : vp_pass_ring_kernel<K, kMainFlagsND, 3, 3, false, true>;
+        if (carry_f) kern = p2 ? vp_pass_ring_kernel<K, kMainFlagsXU, 3, 3, true, true> : vp_pass_ring_kernel<K, kMainFlagsXU, 3, 3, false, true>;
+        else if (nodiag) kern = p2 ? vp_pass_ring_kernel<K, kMainFlagsND, 3, 3, true, true> : vp_pass_ring_kernel<K, kMainFlagsND, 3, 3, false, true>;
         else kern = p2 ? vp_pass_ring_kernel<K, kMainFlags, 3, 3, true, true> : vp_pass_ring_kernel<K, kMainFlags, 3, 3, false, true>;
     } else if (ring) {
         smem += 2 * 3 * tile_b + sizeof(uint64_t) * 2 * 2;
-        if (nodiag) kern = p2 ? vp_pass_ring_kernel<K, kMainFlagsND, 3, 2, true, false> : vp_pass_ring_kernel<K, kMainFlagsND, 3, 2, false, false>;
+        if (carry_f) kern = p2 ? vp_pass_ring_kernel<K, kMainFlagsXU, 3, 2, true, false> : vp_pass_ring_kernel<K, kMainFlagsXU, 3, 2, false, false>;
+        else if (nodiag) kern = p2 ? vp_pass_ring_kernel<K, kMainFlagsND, 3, 2, true, false> : vp_pass_ring_kernel<K, kMainFlagsND, 3, 2, false, false>;
         else kern = p2 ? vp_pass_ring_kernel<K, kMainFlags, 3, 2, true, false> : vp_pass_ring_kernel<K, kMainFlags, 3, 2, false, false>;
     } else if (tma && p.flags == kFrozenFlags) {
         smem += 4 * (p.use_uw ? 2 : 3) * tile_b + sizeof(uint64_t) * 4;
@@ -892,6 +908,7 @@ int launch_vp_pass(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* gri
 int launch_vp_field(vpm_ctx* ctx, vpm_xspace* xs, int phases, int nparts, int has_dep, int has_kin, double escale,
                     double wscale, int w_slot, int km_slot)
 {
+    xs->field_gen++;   // whatever this launch leaves in rhs / phi / etab replaces what a carried stagger was relying on
     FieldDev F{};
     const int nb = xs->nh + xs->K - 1;
     F.partials = ctx->partials;

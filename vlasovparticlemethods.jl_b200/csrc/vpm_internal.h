@@ -93,6 +93,14 @@ struct vpm_particles {
     unsigned* sort_counts = nullptr;
     bool mirror_valid = false, exposed = false, mirror_has_w = false;
     bool v_stale = false;   // the mirror is ahead of v: particles_sync_v (cabi.cu) brings v up to date on demand
+    // carried stagger of the self-consistent Strang stepper (cabi.cu, vp_steps_carry): xstag = x + dt/2 v of the state in
+    // (x, v), already deposited and solved in stag_xs -- the next call with the same parameters needs no prologue pass
+    double* xstag = nullptr;
+    bool stag_valid = false;
+    const vpm_xspace* stag_xs = nullptr;
+    uint64_t stag_gen = 0;
+    double stag_Dt = 0.0, stag_chi = 0.0, stag_wu = 0.0;
+    bool stag_uw = false;
     double mirror_lo = 0.0, mirror_hi = 0.0;
 };
 
@@ -113,6 +121,7 @@ struct vpm_xspace {
     double* etab = nullptr;    // [nh][ES] per-cell monomial coefficients of the kick field
     double* diag = nullptr;    // device history buffer
     size_t diag_cap = 0;
+    uint64_t field_gen = 0;    // bumped by every field-kernel launch on this space: a carried stagger (vpm_particles) checks it
 };
 
 struct vpm_vspace {
@@ -182,11 +191,13 @@ enum VpFlags : int {
     VP_DEPOSIT = 64,   // scatter w B(x) into the per-CTA partial
     VP_WRITE_X = 128,
     VP_WRITE_V = 256,
+    VP_WRITE_XU = 512, // also store x as it is after POST1 (before POST2) to xu_out: the unstaggered position of a carried stagger
 };
 
 struct VpPass {
     const double *x_in, *v_in, *w;
     double *x_out, *v_out;
+    double* xu_out;     // VP_WRITE_XU
     int64_t n;
     int flags;
     double tau_pre, tau_kick, tau_post1, tau_post2;
