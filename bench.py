@@ -389,17 +389,23 @@ class Bench:
         per = ms / args.steps
         kms, kcnt, _, _ = self.profile(run_steps, min(args.steps, 20))
         pass_ms, pass_cnt, field_ms = float(kms[0]), int(kcnt[0]), float(kms[1])
-        bytes_per_launch = BYTES_PER_STEP * n           # one fused pass = one particle-step of every particle
+        # one fused pass = one particle-step of every particle (40 B).  With the carried stagger (default, self-consistent mode)
+        # a stepper call is exactly `steps` fused passes, the last of which also stores the caller-visible x (48 B); without it
+        # (VPM_TUNE_VPCARRY=0, frozen mode) the K + 1 passes of a call include a 32 B prologue and a 32 B epilogue
+        carry = os.environ.get("VPM_TUNE_VPCARRY", "1") != "0" and mode == 0
+        kprof = min(args.steps, 20)
+        call_bytes = (BYTES_PER_STEP * kprof + 8) if carry else (BYTES_PER_STEP * (kprof - 1) + 64)
+        bytes_per_launch = call_bytes * n / max(pass_cnt, 1) if mode == 0 else BYTES_PER_STEP * n
         avg = pass_ms / max(pass_cnt, 1)
         achieved = bytes_per_launch / (avg * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("vp")
-        kernel = ("vp_pass_tma_kernel (fused kick+drift+deposit; prologue/epilogue passes use vp_pass_kernel)"
-                  if os.environ.get("VPM_TUNE_TMA", "1") != "0" else "vp_pass_kernel")
+        kernel = ("vp_pass_ring_kernel (fused kick+drift+deposit; one pass per step, the stagger is carried from call to call)"
+                  if os.environ.get("VPM_TUNE_TMA", "5") != "0" else "vp_pass_kernel")
         out = {"value": self.ntotal / (per * 1e-3), "ms_per_step": per, "launches": launches, "clocks": clocks,
-               "passes": args.steps + 1,
+               "passes": args.steps + (0 if carry else 1),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": self.peak, "unit": "GB/s", "frac": achieved / self.peak,
                             "traffic": traffic, "traffic_source": "one ncu --set full capture (profiles/traffic.json), not re-measured per run",
                             "peak_source": self.peak_src, "kernel": kernel, "bytes_per_launch": bytes_per_launch,
