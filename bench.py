@@ -390,11 +390,11 @@ class Bench:
         kms, kcnt, _, _ = self.profile(run_steps, min(args.steps, 20))
         pass_ms, pass_cnt, field_ms = float(kms[0]), int(kcnt[0]), float(kms[1])
         # one fused pass = one particle-step of every particle (40 B).  With the carried stagger (default, self-consistent mode)
-        # a stepper call is exactly `steps` fused passes, the last of which also stores the caller-visible x (48 B); without it
-        # (VPM_TUNE_VPCARRY=0, frozen mode) the K + 1 passes of a call include a 32 B prologue and a 32 B epilogue
+        # a stepper call is exactly `steps` fused passes of 40 B; without it (VPM_TUNE_VPCARRY=0) the K + 1 passes of a call
+        # include a 32 B prologue and a 32 B epilogue
         carry = os.environ.get("VPM_TUNE_VPCARRY", "1") != "0" and mode == 0
         kprof = min(args.steps, 20)
-        call_bytes = (BYTES_PER_STEP * kprof + 8) if carry else (BYTES_PER_STEP * (kprof - 1) + 64)
+        call_bytes = BYTES_PER_STEP * kprof if carry else (BYTES_PER_STEP * (kprof - 1) + 64)
         bytes_per_launch = call_bytes * n / max(pass_cnt, 1) if mode == 0 else BYTES_PER_STEP * n
         avg = pass_ms / max(pass_cnt, 1)
         achieved = bytes_per_launch / (avg * 1e-3) / 1e9
@@ -580,7 +580,7 @@ class Bench:
         a single-rank run of the same global ensemble on rank 0 and the CPU oracle."""
         vpm, torch, dist, ctx = self.vpm, self.torch, self.dist, self.ctx
         world, rank = self.world, self.rank
-        nper, vp_steps, lb_steps = 200_000, 5, 3
+        nper, vp_steps, lb_steps = 300_000, 5, 3   # >= 2^18 per rank: the CLB steps take the velocity-sorted passes, as the timed region does
         ntot = nper * world
 
         def run_pair(c, npart, offset):

@@ -452,7 +452,7 @@ int vpm_particles_destroy(vpm_particles* p)
     cudaStreamSynchronize(p->ctx->stream);
     cudaFree(p->x); cudaFree(p->v); cudaFree(p->w);
     cudaFree(p->q); cudaFree(p->ka); cudaFree(p->kb);
-    cudaFree(p->sv); cudaFree(p->sw); cudaFree(p->sinv); cudaFree(p->sort_counts); cudaFree(p->xstag);
+    cudaFree(p->sv); cudaFree(p->sw); cudaFree(p->sinv); cudaFree(p->sort_counts);
     delete p;
     return VPM_OK;
 }
@@ -895,10 +895,11 @@ static int vp_steps(vpm_xspace* xs, double* x, double* v, const double* w, int64
 // Self-consistent Strang steps with a CARRIED stagger (no diagnostics).  The fused pass keeps the particles half a drift
 // ahead (kick(n) + drift/2 | drift/2 + deposit(n+1) in one launch), so a call used to cost nsteps + 1 passes: a prologue
 // (drift/2 + deposit) and an epilogue (kick + drift/2).  Here the LAST pass of a call is a full fused pass as well: it
-// stores the caller-visible position (after the trailing half drift) to p->x, keeps the staggered one in p->xstag and
-// leaves the next step's field solved in xs.  The next call with the same (xs, dt, chi, weights) -- and nobody having
-// touched the particles or the field in between -- starts with a fused pass straight away: nsteps passes per call, one
-// pass per step for callers that step one step per call (was two).  p->x, p->v always hold the official state.
+// stores the caller-visible position (after the trailing half drift) but still deposits at the staggered one, leaving the
+// next step's field solved in xs; the FIRST pass of the next call -- same (xs, dt, chi, weights), nobody having touched the
+// particles or the field in between -- redoes that half drift in registers (the same fma on the same operands: the same
+// bits) and carries on.  Every pass moves 40 B per particle, a call of nsteps steps is nsteps passes, and callers that
+// step one step per call pay one pass per step instead of two.  p->x, p->v hold the official state at every call boundary.
 static int vp_steps_carry(vpm_xspace* xs, vpm_particles* p, double dt, double chi, int nsteps, bool carried)
 {
     vpm_ctx* ctx = xs->ctx;
@@ -907,21 +908,19 @@ static int vp_steps_carry(vpm_xspace* xs, vpm_particles* p, double dt, double ch
     const int kFused = VP_KICK1 | VP_POST1 | VP_POST2 | VP_DEPOSIT | VP_WRITE_X | VP_WRITE_V;
     int grid = 0;
     VpPass ps{};
-    ps.v_in = p->v; ps.w = p->w; ps.v_out = p->v; ps.n = p->n;
+    ps.x_in = p->x; ps.v_in = p->v; ps.w = p->w; ps.x_out = p->x; ps.v_out = p->v; ps.n = p->n;
     ps.use_uw = p->uw; ps.w_uniform = p->wu;
-    ps.tau_kick = Dt; ps.tau_post1 = 0.5 * Dt; ps.tau_post2 = 0.5 * Dt;
-    if (!carried) {
+    ps.tau_pre = 0.5 * Dt; ps.tau_kick = Dt; ps.tau_post1 = 0.5 * Dt; ps.tau_post2 = 0.5 * Dt;
+    if (!carried) {   // deposit at x + dt/2 v without moving anything (24 B per particle)
         VpPass p1 = ps;
-        p1.x_in = p->x; p1.x_out = p->xstag;
-        p1.flags = VP_POST2 | VP_DEPOSIT | VP_WRITE_X;
+        p1.flags = VP_POST2 | VP_DEPOSIT;
         VPM_CHECK(launch_vp_pass(ctx, xs, p1, &grid));
         VPM_CHECK(launch_vp_field(ctx, xs, ALL, grid, 1, 0, escale, wscale, -1, -1));
     }
-    ps.x_in = p->xstag; ps.x_out = p->xstag;
     for (int it = 1; it <= nsteps; it++) {
-        const bool last = it == nsteps;
-        ps.flags = kFused | (last ? VP_WRITE_XU : 0);
-        ps.xu_out = last ? p->x : nullptr;
+        const bool first = it == 1, last = it == nsteps;
+        ps.flags = (first || last) ? (kFused | VP_PRE | VP_WRITE_XU) : kFused;
+        ps.rt_pre = first; ps.rt_store_mid = last;
         VPM_CHECK(launch_vp_pass(ctx, xs, ps, &grid));
         VPM_CHECK(launch_vp_field(ctx, xs, ALL, grid, 1, 0, escale, wscale, -1, -1));
     }
@@ -948,16 +947,8 @@ int vpm_vp_strang_steps_async(vpm_xspace* xs, vpm_particles* p, double dt, doubl
     const bool carried = p->stag_valid && p->stag_xs == xs && p->stag_gen == xs->field_gen && p->stag_Dt == dt * chi && p->stag_chi == chi &&
                          p->stag_uw == p->uw && (!p->uw || p->stag_wu == p->wu);
     VPM_CHECK(mirror_invalidate(p));   // the kick changes v (this also drops the stagger: `carried` was read first)
-    if (tune_carry && mode == VPM_VP_SELFCONSISTENT && diag_mode == 0 && nsteps >= 1 && !p->exposed) {
-        if (!p->xstag) {
-            const size_t bytes = sizeof(double) * (size_t)(p->n > 0 ? p->n + (p->n & 1) : 2);
-            if (cudaMalloc((void**)&p->xstag, bytes) != cudaSuccess) {
-                p->xstag = nullptr;
-                cudaGetLastError();   // no room for the staggered copy: the two-ended scheme below needs none
-            }
-        }
-        if (p->xstag) return vp_steps_carry(xs, p, dt, chi, nsteps, carried);
-    }
+    if (tune_carry && mode == VPM_VP_SELFCONSISTENT && diag_mode == 0 && nsteps >= 1 && !p->exposed)
+        return vp_steps_carry(xs, p, dt, chi, nsteps, carried);
     return vp_steps(xs, p->x, p->v, p->w, p->n, xdep, p->w, p->n, dt, chi, nsteps, mode, diag_mode, p->uw, p->wu);
 }
 

@@ -28,7 +28,7 @@ namespace {
 struct VpDev {
     const double *x_in, *v_in, *w;
     double *x_out, *v_out;
-    double* xu_out;   // VP_WRITE_XU: the position after the trailing half drift (the caller-visible x of a carried stagger)
+    int rt_pre, rt_store_mid;   // VP_WRITE_XU (edge passes of a carried stagger): apply the leading half drift / store x as it is after POST1
     long long n;
     int flags;
     double tau_pre, tau_kick, tau_post1, tau_post2;
@@ -53,8 +53,10 @@ constexpr int kMainFlags = VP_KICK1 | VP_POST1 | VP_DIAG | VP_POST2 | VP_DEPOSIT
 constexpr int kFrozenFlags = VP_PRE | VP_KICK1 | VP_KICK2 | VP_POST1 | VP_DIAG | VP_WRITE_X | VP_WRITE_V;
 // the same passes for runs that asked for no diagnostics (diag_mode 0): K, M are not accumulated
 constexpr int kMainFlagsND = kMainFlags & ~VP_DIAG, kFrozenFlagsND = kFrozenFlags & ~VP_DIAG;
-// last pass of a stepper call with a carried stagger: also stores the unstaggered position (48 instead of 40 B per particle)
-constexpr int kMainFlagsXU = kMainFlagsND | VP_WRITE_XU;
+// first / last pass of a stepper call with a carried stagger (cabi.cu, vp_steps_carry): the first one starts from the
+// caller-visible x and applies the leading half drift itself (rt_pre), the last one stores x as it is after the trailing
+// half drift (rt_store_mid) while still depositing at the staggered position -- both still 40 B per particle
+constexpr int kMainFlagsXU = kMainFlagsND | VP_WRITE_XU | VP_PRE;
 
 // HM: histogram privatisation. 0 = one copy per thread (no atomics), 1 = one copy per warp, 2 = one copy per
 // CTA (shared-memory atomicAdd; for grids whose per-thread copies would not fit in shared memory)
@@ -71,7 +73,7 @@ __device__ __forceinline__ void vp_particle(const VpDev& P, const int flags_rt, 
 {
     constexpr int ES = VpCfg<K>::ES;
     const int flags = FLAGS >= 0 ? FLAGS : flags_rt;
-    if (flags & VP_PRE) x = fma(P.tau_pre, v, x);
+    if ((flags & VP_PRE) && (!(flags & VP_WRITE_XU) || P.rt_pre)) x = fma(P.tau_pre, v, x);
     if (flags & VP_KICK1) {
         int ci;
         double u;
@@ -165,9 +167,9 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
             double2 xu = make_double2(0, 0);
             vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, xa.x, va.x, wa.x, ksum, msum, nullptr, nullptr, &xu.x);
             vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, xa.y, va.y, wa.y, ksum, msum, nullptr, nullptr, &xu.y);
+            if ((flags & VP_WRITE_XU) && P.rt_store_mid) xa = xu;
             if (flags & VP_WRITE_X) st_stream2(P.x_out + 2 * i, xa);
             if (flags & VP_WRITE_V) st_stream2(P.v_out + 2 * i, va);
-            if (flags & VP_WRITE_XU) st_stream2(P.xu_out + 2 * i, xu);
             xa = xn; va = vn; wa = wn;
             i = inext;
             have = hn;
@@ -176,17 +178,17 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_kernel(const VpDev P)
             const long long t = P.n - 1;
             double x = P.x_in[t], v = need_v ? P.v_in[t] : 0.0, w = need_w ? P.w[t] : P.w_uniform, xu = 0.0;
             vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, x, v, w, ksum, msum, nullptr, nullptr, &xu);
+            if ((flags & VP_WRITE_XU) && P.rt_store_mid) x = xu;
             if (flags & VP_WRITE_X) P.x_out[t] = x;
             if (flags & VP_WRITE_V) P.v_out[t] = v;
-            if (flags & VP_WRITE_XU) P.xu_out[t] = xu;
         }
     } else {
         for (long long i = gtid; i < P.n; i += stride) {
             double x = P.x_in[i], v = need_v ? P.v_in[i] : 0.0, w = need_w ? P.w[i] : P.w_uniform, xu = 0.0;
             vp_particle<K, FLAGS, HM>(P, flags, s_etab, s_hist, x, v, w, ksum, msum, nullptr, nullptr, &xu);
+            if ((flags & VP_WRITE_XU) && P.rt_store_mid) x = xu;
             if (flags & VP_WRITE_X) P.x_out[i] = x;
             if (flags & VP_WRITE_V) P.v_out[i] = v;
-            if (flags & VP_WRITE_XU) P.xu_out[i] = xu;
         }
     }
 
@@ -415,9 +417,9 @@ __global__ void __launch_bounds__(kVpRingThreads, MINB) vp_pass_ring_kernel(cons
             double2 xu = make_double2(0, 0);
             vp_particle<K, FLAGS, 0, P2>(P, FLAGS, s_etab, s_hist, xa.x, va.x, wa.x, ksum, msum, nullptr, nullptr, &xu.x);
             vp_particle<K, FLAGS, 0, P2>(P, FLAGS, s_etab, s_hist, xa.y, va.y, wa.y, ksum, msum, nullptr, nullptr, &xu.y);
+            if ((FLAGS & VP_WRITE_XU) && P.rt_store_mid) xa = xu;
             st_stream2(xo + g * kTmaTile, xa);
             st_stream2(vo + g * kTmaTile, va);
-            if (FLAGS & VP_WRITE_XU) st_stream2(P.xu_out + 2 * tid + g * kTmaTile, xu);
             if (lane == 0 && P.late_release) mbar_arrive(&s_empty[s]);
             if (++s == STAGES) {
                 s = 0;
@@ -429,9 +431,9 @@ __global__ void __launch_bounds__(kVpRingThreads, MINB) vp_pass_ring_kernel(cons
     for (long long i = ntiles * kTmaTile + (long long)blockIdx.x * kBlock + tid; i < P.n; i += (long long)gridDim.x * kBlock) {
         double x = P.x_in[i], v = P.v_in[i], w = UW ? P.w_uniform : P.w[i], xu = 0.0;
         vp_particle<K, FLAGS, 0, P2>(P, FLAGS, s_etab, s_hist, x, v, w, ksum, msum, nullptr, nullptr, &xu);
+        if ((FLAGS & VP_WRITE_XU) && P.rt_store_mid) x = xu;
         P.x_out[i] = x;
         P.v_out[i] = v;
-        if (FLAGS & VP_WRITE_XU) P.xu_out[i] = xu;
     }
 
     vp_worker_sync();
@@ -511,9 +513,9 @@ __global__ void __launch_bounds__(kBlock, MINB) vp_pass_tiled_kernel(const VpDev
                 double x = P.x_in[i], v = need_v ? P.v_in[i] : 0.0, xu = 0.0;
                 pw[k] = need_w ? P.w[i] : P.w_uniform;
                 vp_particle<K, -1, 3>(P, flags, s_etab, nullptr, x, v, pw[k], ksum, msum, &pc[k], &pu[k], &xu);
+                if ((flags & VP_WRITE_XU) && P.rt_store_mid) x = xu;
                 if (flags & VP_WRITE_X) P.x_out[i] = x;
                 if (flags & VP_WRITE_V) P.v_out[i] = v;
-                if (flags & VP_WRITE_XU) P.xu_out[i] = xu;
                 if (dep) pr[k] = atomicAdd(&s_cnt[pc[k]], 1);
                 else pc[k] = -1;
             }
@@ -756,7 +758,7 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
 {
     constexpr int ES = VpCfg<K>::ES;
     VpDev P{};
-    P.x_in = p.x_in; P.v_in = p.v_in; P.w = p.w; P.x_out = p.x_out; P.v_out = p.v_out; P.xu_out = p.xu_out;
+    P.x_in = p.x_in; P.v_in = p.v_in; P.w = p.w; P.x_out = p.x_out; P.v_out = p.v_out; P.rt_pre = p.rt_pre; P.rt_store_mid = p.rt_store_mid;
     P.n = p.n; P.flags = p.flags;
     P.tau_pre = p.tau_pre; P.tau_kick = p.tau_kick; P.tau_post1 = p.tau_post1; P.tau_post2 = p.tau_post2;
     P.lo = xs->lo; P.invh = xs->invh; P.nh = xs->nh; P.fm = xs->fm;
@@ -798,7 +800,7 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
         return fail(VPM_ERR_UNSUPPORTED, "x-space too large: the field table and one histogram copy must fit in shared memory");
 
     auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    const bool vec = aligned16(p.x_in) && aligned16(p.v_in) && aligned16(p.w) && aligned16(p.x_out) && aligned16(p.v_out) && aligned16(p.xu_out);
+    const bool vec = aligned16(p.x_in) && aligned16(p.v_in) && aligned16(p.w) && aligned16(p.x_out) && aligned16(p.v_out);
 
     // VPM_TUNE_MINB = 2|3|4 selects the register/occupancy trade-off of the fused step kernel
     // (91 / 85 / 64 registers per thread); default chosen from ncu runs, see DESIGN.md

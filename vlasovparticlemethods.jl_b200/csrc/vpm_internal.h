@@ -93,9 +93,8 @@ struct vpm_particles {
     unsigned* sort_counts = nullptr;
     bool mirror_valid = false, exposed = false, mirror_has_w = false;
     bool v_stale = false;   // the mirror is ahead of v: particles_sync_v (cabi.cu) brings v up to date on demand
-    // carried stagger of the self-consistent Strang stepper (cabi.cu, vp_steps_carry): xstag = x + dt/2 v of the state in
-    // (x, v), already deposited and solved in stag_xs -- the next call with the same parameters needs no prologue pass
-    double* xstag = nullptr;
+    // carried stagger of the self-consistent Strang stepper (cabi.cu, vp_steps_carry): the deposit of x + dt/2 v of the
+    // state in (x, v) is already solved in stag_xs -- the next call with the same parameters needs no prologue pass
     bool stag_valid = false;
     const vpm_xspace* stag_xs = nullptr;
     uint64_t stag_gen = 0;
@@ -191,13 +190,13 @@ enum VpFlags : int {
     VP_DEPOSIT = 64,   // scatter w B(x) into the per-CTA partial
     VP_WRITE_X = 128,
     VP_WRITE_V = 256,
-    VP_WRITE_XU = 512, // also store x as it is after POST1 (before POST2) to xu_out: the unstaggered position of a carried stagger
+    VP_WRITE_XU = 512, // edge pass of a carried stagger: VP_PRE applies only if rt_pre; rt_store_mid stores x as it is after POST1
 };
 
 struct VpPass {
     const double *x_in, *v_in, *w;
     double *x_out, *v_out;
-    double* xu_out;     // VP_WRITE_XU
+    int rt_pre = 0, rt_store_mid = 0;   // VP_WRITE_XU
     int64_t n;
     int flags;
     double tau_pre, tau_kick, tau_post1, tau_post2;
