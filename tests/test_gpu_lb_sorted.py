@@ -221,3 +221,41 @@ def test_sorted_degenerate_ensembles(vpm, oracle, perr, monkeypatch, case):
     vo, do = vs.rk438(v, w, nu, dt, ns, conservative=False)
     perr("lb_sorted_rk438_v@" + case, np.abs(d.get("v") - vo).max() / np.abs(vo).max(), TOL)
     perr("lb_sorted_moment_history@" + case, (np.abs(gi.diagnostics[:, :2] - do) / np.array([np.abs(v).sum(), (v * v).sum()])).max(), TOL)
+
+
+@pytest.mark.parametrize("cons", [False, True])
+def test_sorted_projection_is_carried_between_calls(vpm, oracle, perr, monkeypatch, cons):
+    """the stage-4 pass of a call leaves the projection of the final state solved: the next call on the same ensemble and
+    space skips the deposit-only pass (4 passes + 4 field kernels per step, nothing else) and its history continues the last
+    row; another ensemble using the same space in between voids that"""
+    monkeypatch.setenv("VPM_TUNE_LBSORT", "2")
+    n, nu, dt = 20_011, 0.9, 0.02
+    v, w = ensemble(n, 77)
+    vs = oracle.VSpace(-10.0, 10.0, 41, 4)
+    sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
+    d = vpm.ParticleDistribution(1, 1, n).set(np.zeros(n), v, w)
+    model = (vpm.ConservativeLenardBernstein if cons else vpm.LenardBernstein)(d, vpm.CollisionEntropy(sd), nu=nu)
+    ctx = vpm.default_context()
+    rows, counts = [], []
+    for k in (1, 1, 2):
+        l0 = ctx.launches
+        gi = vpm.GeometricIntegrator(model, vpm.tspan_for(k, dt), dt)
+        vpm.run_(gi)
+        counts.append(ctx.launches - l0)
+        rows.append(gi.diagnostics[:, :2] if not rows else gi.diagnostics[1:, :2])
+        if len(rows) > 1:
+            np.testing.assert_array_equal(gi.diagnostics[0, :2], last)      # row 0 of a carried call = the previous call's last row
+        last = gi.diagnostics[-1, :2].copy()
+    assert counts[1] == 8 and counts[2] == 16 and counts[0] > 8 + 2            # (first call: sort + deposit-only pass + its field kernel)
+    vo, do = vs.rk438(v, w, nu, dt, 4, conservative=cons)
+    tag = "@clb" if cons else "@lb"
+    perr("sorted_carried_rk438_v" + tag, nrm(d.get("v"), vo), TOL)
+    perr("sorted_carried_moment_history" + tag, (np.abs(np.concatenate(rows) - do) / np.array([np.abs(v).sum(), (v * v).sum()])).max(), TOL)
+    # another ensemble projects into the same SplineDistribution: the carried projection is void
+    other = vpm.ParticleDistribution(1, 1, n).set(np.zeros(n), v[::-1] * 0.5, w)
+    vpm.projection(None, other, sd)
+    l0 = ctx.launches
+    vpm.run_(vpm.GeometricIntegrator(model, vpm.tspan_for(1, dt), dt))
+    assert ctx.launches - l0 == 8 + 2
+    vo, _ = vs.rk438(vo, w, nu, dt, 1, conservative=cons)
+    perr("sorted_carry_voided_rk438_v" + tag, nrm(d.get("v"), vo), TOL)

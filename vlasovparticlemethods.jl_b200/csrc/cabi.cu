@@ -1047,7 +1047,7 @@ int vpm_vspace_create(vpm_ctx* ctx, double lo, double hi, int nknots, int order,
         return fail(VPM_ERR_INVALID, "vpm_vspace_create: mass matrix is not positive definite");
     }
     const int TS = 2 * order - 1;
-    std::vector<double> z1((size_t)vs->nv + 8, 0.0), z2((size_t)vs->nv, 0.0), z3((size_t)vs->ncell * TS, 0.0), z4(8, 0.0);
+    std::vector<double> z1((size_t)vs->nv + 8, 0.0), z2((size_t)vs->nv, 0.0), z3((size_t)vs->ncell * TS, 0.0), z4(12, 0.0);   // scal: A1, A2 | five moments | - | last diagnostics row of a stepper call (8, 9)
     std::vector<double> z5((size_t)vs->ncell * (2 * order + 2) + 8, 0.0);
     int rc = VPM_OK;
     if (vs->nv <= 64) {
@@ -1308,12 +1308,14 @@ static int lb_sort_mode(const vpm_vspace* vs, const vpm_particles* p)
     return mode;
 }
 
-static int ensure_mirror(vpm_vspace* vs, vpm_particles* p, int sort_mode)
+static int ensure_mirror(vpm_vspace* vs, vpm_particles* p, int sort_mode, bool* rebuilt)
 {
+    *rebuilt = false;
     vpm_ctx* ctx = vs->ctx;
     const bool need_w = !p->uw;
     if (p->mirror_valid && !p->exposed && p->mirror_lo == vs->lo && p->mirror_hi == vs->hi && (p->mirror_has_w || !need_w)) return VPM_OK;
     VPM_CHECK(particles_sync_v(p));   // a rebuild starts from v in the caller's order: bring it up to date first
+    *rebuilt = true;
     const size_t bytes = sizeof(double) * (size_t)(p->n + (p->n & 1));
     const int sort_grid = ctx->sm_count * kSortGridPerSm;
     if (!p->sv) {
@@ -1370,16 +1372,24 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
         // ---- velocity-sorted path (kernels_lbs.cu): four passes per step for both models, no histograms, no moments passes.
         // The stage passes deposit per-cell power sums; the field kernel turns them into the right-hand side and, for the
         // conservative model, into the five moments of the freshly solved spline (A1, A2 ready for the next pass).
-        VPM_CHECK(ensure_mirror(vs, p, sort_mode));
+        bool rebuilt = false;
+        VPM_CHECK(ensure_mirror(vs, p, sort_mode, &rebuilt));
         const int PS = LBF_PS_REDUCE | LBF_PS_CONVERT | LBF_SOLVE | LBF_TABLE | (conservative ? (LBF_PS_COEFF | LBF_COEFF) : 0);
         ps.w = p->sw;
-        {   // projection of the initial state + step-0 diagnostics
+        // The previous call on this mirror ended with the projection of its final state solved in vs (spline table, A1, A2):
+        // if nothing touched the particles (the mirror was not rebuilt) or the space (generation counter) since, the
+        // deposit-only pass that re-projects the initial state is skipped and row 0 of the history is that call's last row
+        const bool carried = !rebuilt && p->lb_carry_vs == vs && p->lb_carry_gen == vs->field_gen && p->lb_carry_cons == (conservative != 0) &&
+                             p->lb_carry_uw == p->uw && (!p->uw || p->lb_carry_wu == p->wu);
+        if (carried) {
+            VPM_CUDA(cudaMemcpyAsync(vs->diag, vs->scal + 8, 2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {   // projection of the initial state + step-0 diagnostics
             LbPass p0 = ps;
             p0.mode = LB_DEPOSIT_ONLY; p0.q = p->sv; p0.diag = 1;
             VPM_CHECK(launch_lbs_pass(ctx, vs, p0, &grid));
             VPM_CHECK(launch_lb_field(ctx, vs, PS, grid, 2, 0, p->uw, p->wu));
-            if (ent && erow0 == 0) VPM_CHECK(lb_entropy_row(ctx, vs, p->sv, p->sw, p->n, p->uw, p->wu, 0));
         }
+        if (ent && erow0 == 0) VPM_CHECK(lb_entropy_row(ctx, vs, p->sv, p->sw, p->n, p->uw, p->wu, 0));
         for (int it = 1; it <= nsteps; it++) {
             for (int s = 1; s <= 4; s++) {
                 LbPass st = ps;
@@ -1400,6 +1410,9 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
             p->v_stale = true;
             if (p->exposed) VPM_CHECK(particles_sync_v(p));
         }
+        VPM_CUDA(cudaMemcpyAsync(vs->scal + 8, vs->diag + 2 * (size_t)nsteps, 2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        p->lb_carry_vs = vs; p->lb_carry_gen = vs->field_gen; p->lb_carry_cons = conservative != 0;
+        p->lb_carry_uw = p->uw; p->lb_carry_wu = p->wu;
         return VPM_OK;
     }
     VPM_CHECK(mirror_invalidate(p));   // this path advances v itself

@@ -1226,6 +1226,7 @@ int launch_lb_pass(vpm_ctx* ctx, const vpm_vspace* vs, const LbPass& p, int* gri
 
 int launch_lb_field(vpm_ctx* ctx, vpm_vspace* vs, int phases, int nparts, int nred, int diag_slot, int ps_uw, double ps_wu)
 {
+    vs->field_gen++;   // whatever this launch leaves in rhs / coef / ftab / scal replaces what a carried projection was relying on
     const bool ps = (phases & (LBF_PS_REDUCE | LBF_PS_CONVERT)) != 0;   // input: power-sum rows of the sorted passes
     const int NA = 2 * vs->K + 2, ncol = vs->ncell * NA;
     LbFieldDev F{};

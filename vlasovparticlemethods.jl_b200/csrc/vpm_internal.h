@@ -100,9 +100,15 @@ struct vpm_particles {
     uint64_t stag_gen = 0;
     double stag_Dt = 0.0, stag_chi = 0.0, stag_wu = 0.0;
     bool stag_uw = false;
+    // the collision steppers' analogue: the projection of the mirror's state is still solved in lb_carry_vs
+    const vpm_vspace* lb_carry_vs = nullptr;
+    uint64_t lb_carry_gen = 0;
+    bool lb_carry_cons = false, lb_carry_uw = false;
+    double lb_carry_wu = 0.0;
     double mirror_lo = 0.0, mirror_hi = 0.0;
 };
 
+struct vpm_vspace;
 struct vpm_xspace {
     vpm_ctx* ctx = nullptr;
     double lo = 0, hi = 1, h = 1, invh = 1;
@@ -144,6 +150,7 @@ struct vpm_vspace {
     size_t ent_cap = 0;
     int want_entropy = 0, ent_row0 = 0, ent_rows = 0;
     double f_floor = 1e-14;
+    uint64_t field_gen = 0;   // bumped by every field-kernel launch on this space (a carried projection checks it)
 };
 
 namespace vpm {
