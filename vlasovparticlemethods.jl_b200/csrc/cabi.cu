@@ -1368,12 +1368,17 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
         else VPM_REQUIRE(vs->ent_cap >= 2 * ((size_t)erow0 + nsteps + 1), "entropy history buffer too small for this leg");
         vs->ent_rows = erow0 + nsteps + 1;
     }
-    if (const int sort_mode = lb_sort_mode(vs, p)) {
+    int sort_mode = lb_sort_mode(vs, p);
+    bool rebuilt = false;
+    if (sort_mode) {
+        const int rc = ensure_mirror(vs, p, sort_mode, &rebuilt);
+        if (rc == VPM_ERR_NOMEM) sort_mode = 0;   // no room for the mirror (+20 B per particle): the histogram passes need none
+        else if (rc) return rc;
+    }
+    if (sort_mode) {
         // ---- velocity-sorted path (kernels_lbs.cu): four passes per step for both models, no histograms, no moments passes.
         // The stage passes deposit per-cell power sums; the field kernel turns them into the right-hand side and, for the
         // conservative model, into the five moments of the freshly solved spline (A1, A2 ready for the next pass).
-        bool rebuilt = false;
-        VPM_CHECK(ensure_mirror(vs, p, sort_mode, &rebuilt));
         const int PS = LBF_PS_REDUCE | LBF_PS_CONVERT | LBF_SOLVE | LBF_TABLE | (conservative ? (LBF_PS_COEFF | LBF_COEFF) : 0);
         ps.w = p->sw;
         // The previous call on this mirror ended with the projection of its final state solved in vs (spline table, A1, A2):
