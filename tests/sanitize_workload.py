@@ -78,6 +78,16 @@ def main():
             xo, vo, _ = xs.strang_frozen(x, v, x, w, 0.1, 3)
         xg, vg, _ = d.get()
         assert nrm(xg, xo) < 1e-12 and nrm(vg, vo) < 1e-12, field
+    # the production stepper: no diagnostics, stagger carried across calls (edge passes with run-time pre-drift / mid-x store),
+    # on the ring kernel (nh 16), the general-grid ring kernel (nh 17) and the tiled large-grid kernel (nh 400)
+    for nh in (16, 17, 400):
+        d = vpm.ParticleDistribution(1, 1, n).set(x, v, w)
+        pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, bot.L), 4, nh))
+        for k in (1, 3, 1):
+            vpm.run_(vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(k, 0.1), 0.1, field="selfconsistent"), diag_mode=0)
+        xo, vo, _, _ = orc.XSpace(0.0, bot.L, 4, nh).strang_selfconsistent(x, v, w, 0.1, 5)
+        xg, vg, _ = d.get()
+        assert nrm(xg, xo) < 1e-12 and nrm(vg, vo) < 1e-12, ("carried stagger", nh)
     # large grid: tiled segmented-reduction deposit
     d = vpm.ParticleDistribution(1, 1, n).set(x, v, w)
     pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, bot.L), 4, 400))
