@@ -710,7 +710,9 @@ def main():
     else:
         cons = args.workload == "clb"
         r = B.bench_lb(cons, args.steps, sustained=extras or args.sustained)
-        line["passes_in_timed_region"] = 4 * args.steps * (2 if (cons and "sorted_mirror" not in r) else 1) + 1
+        # velocity-sorted path: four passes per step and nothing else (the projection is carried from the warm-up call);
+        # histogram path: a deposit-only pass per call, and four moments passes per step for CLB
+        line["passes_in_timed_region"] = 4 * args.steps if "sorted_mirror" in r else 4 * args.steps * (2 if cons else 1) + 1
         line.update({"value": r["value"], "ms_per_step": r["ms_per_step"], "config": cfg, "roofline": r["roofline"],
                      "gpu_launches": r["gpu_launches"], "clocks": r["clocks"], "passes": r["passes"],
                      "whole_step_frac": r["whole_step_frac"], "bytes_per_particle_step": r["bytes_per_particle_step"],
