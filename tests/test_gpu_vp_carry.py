@@ -103,3 +103,21 @@ def test_stagger_is_dropped_when_something_else_touches_state(vpm, oracle, perr,
     xg, vg, _ = d.get()
     perr("carry_uniform_weights_x", nrm(xg, xo), TOL)
     perr("carry_uniform_weights_v", nrm(vg, vo), TOL)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 511, 513])
+def test_carry_tiny_ensembles(vpm, oracle, perr, monkeypatch, n):
+    """empty and tiny inputs (no whole ring tile): the edge passes run on the run-time-flag kernels"""
+    monkeypatch.setenv("VPM_TUNE_VPCARRY", "1")
+    rng = np.random.default_rng(n)
+    x, v, w = rng.uniform(0.0, L, n), rng.standard_normal(n), np.full(n, L / max(n, 1))
+    d = vpm.ParticleDistribution(1, 1, n).set(x, v, w)
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), 4, 16))
+    for k in (1, 2, 1):
+        stepper(vpm, d, pot, k)
+    if n == 0:
+        return
+    xo, vo, _, _ = oracle.XSpace(0.0, L, 4, 16).strang_selfconsistent(x, v, w, 0.1, 4)
+    xg, vg, _ = d.get()
+    perr(f"carry_tiny_x@n{n}", np.abs(xg - xo).max() / max(1.0, np.abs(xo).max()), TOL)
+    perr(f"carry_tiny_v@n{n}", np.abs(vg - vo).max() / max(1.0, np.abs(vo).max()), TOL)
