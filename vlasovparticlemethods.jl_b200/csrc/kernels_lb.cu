@@ -20,6 +20,10 @@
 // = 136 B per RK438 particle-step (the accumulate-and-store form needed 184 B).  The conservative model
 // also needs q_2, q_3 in memory for its moments pass (qout != nullptr in stages 1, 2: +8 B each).
 //
+// From 2^18 particles the RK438 steppers run the velocity-sorted passes of kernels_lbs.cu instead (register power sums, no
+// histograms; CLB without moments passes); the passes below serve small ensembles, grids beyond ~200 cells, the operator-level
+// calls (LB_rhs!, moments, gather, entropy) and VPM_TUNE_LBSORT=0.  The field kernel at the end serves both.
+//
 // Kernels: lb_pass_ring_kernel (warp-specialised TMA ring, default for the deposit passes), lb_pass_kernel
 // (register prefetch: gather-only modes, unaligned / tiny inputs, per-warp and per-CTA histogram fallbacks),
 // lb_field_kernel (one CTA: reduce, all-reduce, banded Cholesky solve, per-cell table, CLB coefficients).
