@@ -121,3 +121,28 @@ def test_carry_tiny_ensembles(vpm, oracle, perr, monkeypatch, n):
     xg, vg, _ = d.get()
     perr(f"carry_tiny_x@n{n}", np.abs(xg - xo).max() / max(1.0, np.abs(xo).max()), TOL)
     perr(f"carry_tiny_v@n{n}", np.abs(vg - vo).max() / max(1.0, np.abs(vo).max()), TOL)
+
+
+def test_run_with_trajectory_output_carries_the_stagger(vpm, oracle, perr, monkeypatch, tmp_path):
+    """run!(method, h5file) without diagnostics: the legs between saved frames carry the stagger (one pass per step plus
+    the snapshot pass of each frame); frames in the file are the caller-visible states"""
+    import h5mini
+    monkeypatch.setenv("VPM_TUNE_VPCARRY", "1")
+    n = 30_001
+    x, v, w = oracle.sample_bump_on_tail(n)
+    d = vpm.ParticleDistribution(1, 1, n).set(x, v, w)
+    pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), 4, 16))
+    m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(5, 0.1), 0.1, field="selfconsistent")
+    path = str(tmp_path / "vp.h5")
+    l0 = vpm.default_context().launches
+    vpm.run_(m, path, save_stride=2, diag_mode=0)
+    launches = vpm.default_context().launches - l0
+    z = h5mini.File(path).read("z")
+    assert z.shape == (4, n, 2)
+    xs = oracle.XSpace(0.0, L, 4, 16)
+    for f, k in enumerate((0, 2, 4, 5)):
+        xo, vo, _, _ = xs.strang_selfconsistent(x, v, w, 0.1, k)
+        perr(f"carry_run_frame{f}_x", nrm(z[f, :, 0], xo), TOL)
+        perr(f"carry_run_frame{f}_v", nrm(z[f, :, 1], vo), TOL)
+    # 1 deposit-only pass + 5 fused passes, 6 field kernels, 4 snapshot passes
+    assert launches == 1 + 5 + 6 + 4, launches

@@ -930,6 +930,19 @@ static int vp_steps_carry(vpm_xspace* xs, vpm_particles* p, double dt, double ch
     return VPM_OK;
 }
 
+static bool vp_carry_enabled()
+{
+    // VPM_TUNE_VPCARRY=0: every call ends unstaggered (prologue and epilogue passes, as in round 1); read per call: the tests switch it
+    if (const char* e = getenv("VPM_TUNE_VPCARRY")) return atoi(e) != 0;
+    return true;
+}
+
+static bool vp_stag_matches(const vpm_xspace* xs, const vpm_particles* p, double dt, double chi)
+{
+    return p->stag_valid && p->stag_xs == xs && p->stag_gen == xs->field_gen && p->stag_Dt == dt * chi && p->stag_chi == chi &&
+           p->stag_uw == p->uw && (!p->uw || p->stag_wu == p->wu);
+}
+
 int vpm_vp_strang_steps_async(vpm_xspace* xs, vpm_particles* p, double dt, double chi, int nsteps, int mode, int diag_mode)
 {
     VPM_REQUIRE(xs && p && xs->ctx == p->ctx, "vpm_vp_strang_steps: bad handles");
@@ -941,13 +954,9 @@ int vpm_vp_strang_steps_async(vpm_xspace* xs, vpm_particles* p, double dt, doubl
         // the deposit positions are the particles' positions at call time; the pass that computes the field
         // runs before any push on the same stream, so no copy is needed
     }
-    // VPM_TUNE_VPCARRY=0: every call ends unstaggered (prologue and epilogue passes, as in round 1)
-    bool tune_carry = true;   // (read per call: the tests switch it inside one process)
-    if (const char* e = getenv("VPM_TUNE_VPCARRY")) tune_carry = atoi(e) != 0;
-    const bool carried = p->stag_valid && p->stag_xs == xs && p->stag_gen == xs->field_gen && p->stag_Dt == dt * chi && p->stag_chi == chi &&
-                         p->stag_uw == p->uw && (!p->uw || p->stag_wu == p->wu);
+    const bool carried = vp_stag_matches(xs, p, dt, chi);
     VPM_CHECK(mirror_invalidate(p));   // the kick changes v (this also drops the stagger: `carried` was read first)
-    if (tune_carry && mode == VPM_VP_SELFCONSISTENT && diag_mode == 0 && nsteps >= 1 && !p->exposed)
+    if (vp_carry_enabled() && mode == VPM_VP_SELFCONSISTENT && diag_mode == 0 && nsteps >= 1 && !p->exposed)
         return vp_steps_carry(xs, p, dt, chi, nsteps, carried);
     return vp_steps(xs, p->x, p->v, p->w, p->n, xdep, p->w, p->n, dt, chi, nsteps, mode, diag_mode, p->uw, p->wu);
 }
@@ -1605,6 +1614,12 @@ int vpm_vp_run(vpm_xspace* xs, vpm_particles* p, double dt, double chi, int nste
         if (done < nsteps) {
             // enqueue the next leg and its snapshot before draining frame f, so the GPU computes while the host writes
             const int leg = std::min(save_stride, nsteps - done);
+            if (vp_carry_enabled() && mode == VPM_VP_SELFCONSISTENT && diag_mode == 0 && !p->exposed) {
+                // without diagnostics the legs carry the stagger: a saved frame costs its snapshot pass and nothing else
+                const bool carried = done > 0 && vp_stag_matches(xs, p, dt, chi);
+                p->stag_valid = false;
+                VPM_CHECK(vp_steps_carry(xs, p, dt, chi, leg, carried));
+            } else
             VPM_CHECK(vp_steps(xs, p->x, p->v, p->w, p->n, p->x, p->w, p->n, dt, chi, leg, mode, diag_mode, p->uw, p->wu, done > 0, done > 0));
             if (diag_mode) {
                 const int skip = done > 0 ? 1 : 0;   // row 0 of a later leg repeats the previous leg's last row
