@@ -35,7 +35,17 @@ def _worker(rank, world, port, nper, out_dir, comm, sort):
     dev = rank % torch.cuda.device_count()
     torch.cuda.set_device(dev)
     os.environ["VPM_P2P_TIMEOUT_MS"] = "15000"    # a stuck peer fails the test instead of spinning for long
-    os.environ["VPM_TUNE_LBSORT"] = sort          # 2: velocity-sorted collision passes (all-reduce of the per-cell power sums), 0: histogram passes
+    # 2: velocity-sorted collision passes (all-reduce of the per-cell power sums), 0: histogram passes, "1r": the default
+    # switch with RAGGED slabs -- rank 0 above the single-GPU switch-over of 2^18 particles, rank 1 far below it: the choice of
+    # passes must not depend on the local slab size (both ranks must send the same all-reduce payload)
+    ragged = sort.endswith("r")
+    os.environ["VPM_TUNE_LBSORT"] = sort.rstrip("r")
+    ntot = world * nper
+    if ragged:
+        sizes = [270_000, ntot - 270_000]
+        nper, off = sizes[rank], sum(sizes[:rank])
+    else:
+        off = rank * nper
     ctx = vpm.Context(dev)
     if comm == "nccl":
         obj = [vpm.Context.comm_unique_id() if rank == 0 else None]
@@ -49,14 +59,14 @@ def _worker(rank, world, port, nper, out_dir, comm, sort):
     L = 2 * np.pi / 0.3
     # Vlasov-Poisson, self-consistent, exact diagnostics
     d = vpm.ParticleDistribution(1, 1, nper, ctx)
-    vpm.initialize_(d, vpm.BumpOnTail(), offset=rank * nper, ntotal=world * nper)
+    vpm.initialize_(d, vpm.BumpOnTail(), offset=off, ntotal=ntot)
     pot = vpm.Potential(vpm.PeriodicBasisBSplineKit((0.0, L), 4, 16), ctx)
     m = vpm.SplittingMethod(vpm.VlasovPoisson(d, pot), vpm.tspan_for(5, 0.1), 0.1, field="selfconsistent")
     vpm.run_(m, diag_mode=2)
     x, v, _ = d.get()
     # conservative Lenard-Bernstein RK438
     d2 = vpm.ParticleDistribution(1, 1, nper, ctx)
-    vpm.initialize_(d2, vpm.DoubleMaxwellian((-10.0, 10.0), 2.0), offset=rank * nper, ntotal=world * nper)
+    vpm.initialize_(d2, vpm.DoubleMaxwellian((-10.0, 10.0), 2.0), offset=off, ntotal=ntot)
     sd = vpm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet", ctx)
     gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d2, vpm.CollisionEntropy(sd)), vpm.tspan_for(3, 0.01), 0.01)
     vpm.run_(gi)
@@ -71,7 +81,7 @@ def _worker(rank, world, port, nper, out_dir, comm, sort):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("comm,sort", [("p2p", "2"), ("p2p", "0"), ("nccl", "2")])
+@pytest.mark.parametrize("comm,sort", [("p2p", "2"), ("p2p", "0"), ("p2p", "1r"), ("nccl", "2")])
 def test_two_rank_slabs_match_single_gpu(tmp_path, perr, comm, sort):
     import torch
     if torch.cuda.device_count() < 2 and comm == "nccl":

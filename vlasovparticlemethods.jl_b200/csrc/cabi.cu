@@ -4,6 +4,7 @@
 #include <sched.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -402,6 +403,14 @@ int vpm_memcpy_d2h(vpm_ctx* ctx, double* dst_host, const double* src_dev, int64_
 
 /* ---------------------------------------------------------------- particles */
 
+static uint64_t next_generation_seed()
+{
+    // generation counters of the spaces start at distinct values, so that a space re-created at the address of a destroyed
+    // one can never look like the space a carried stagger / projection was recorded against
+    static std::atomic<uint64_t> seed{1};
+    return seed.fetch_add(1) << 32;
+}
+
 // The collision steppers advance a velocity-sorted MIRROR of (v, w) (kernels_lbs.cu) and leave p->v behind (v_stale) until
 // somebody needs it in the caller's order: every reader of p->v calls particles_sync_v first, every writer of v or w
 // outside those steppers calls mirror_invalidate (which syncs, then drops the mirror).
@@ -631,6 +640,7 @@ int vpm_xspace_create(vpm_ctx* ctx, double lo, double hi, int order, int n_basis
     vpm_xspace* xs = new (std::nothrow) vpm_xspace();
     if (!xs) return fail(VPM_ERR_NOMEM, "out of host memory");
     xs->ctx = ctx;
+    xs->field_gen = next_generation_seed();
     xs->lo = lo; xs->hi = hi; xs->K = order; xs->nh = n_basis;
     xs->h = (hi - lo) / n_basis;
     xs->invh = 1.0 / xs->h;
@@ -1042,6 +1052,7 @@ int vpm_vspace_create(vpm_ctx* ctx, double lo, double hi, int nknots, int order,
     vpm_vspace* vs = new (std::nothrow) vpm_vspace();
     if (!vs) return fail(VPM_ERR_NOMEM, "out of host memory");
     vs->ctx = ctx;
+    vs->field_gen = next_generation_seed();
     vs->lo = lo; vs->hi = hi; vs->K = order; vs->nknots = nknots; vs->ncell = nknots - 1;
     vs->h = (hi - lo) / (nknots - 1);
     vs->invh = 1.0 / vs->h;
@@ -1310,9 +1321,17 @@ static int lb_sort_mode(const vpm_vspace* vs, const vpm_particles* p)
 {
     // VPM_TUNE_LBSORT: 0 = never (private-histogram passes), 1 = default (large ensembles), 2 = always (tests),
     // 3 = always, but the mirror keeps the caller's order (tests: every trip of the sorted passes takes the mixed-cell path)
+    // Returns < 0 when no consistent choice exists.
     int mode = 1;
     if (const char* e = getenv("VPM_TUNE_LBSORT")) mode = atoi(e);
-    if (mode <= 0 || p->n < 1 || p->n >= ((int64_t)1 << 32) || !lbs_supported(vs->ctx, vs)) return 0;
+    if (mode <= 0 || !lbs_supported(vs->ctx, vs)) return 0;
+    // Multi-GPU: every rank must take the same passes (the all-reduce carries power sums on one path, spline right-hand
+    // sides on the other), so the choice may only depend on what all ranks share -- the space and the environment -- and not
+    // on the size of the local slab: sorted passes at any slab size, including an empty one.
+    const bool multi = vs->ctx->p2p.nranks > 1 || vs->ctx->comm.comm != nullptr;
+    if (p->n >= ((int64_t)1 << 32)) return multi ? -1 : 0;   // 32-bit sort indices
+    if (multi) return mode;
+    if (p->n < 1) return 0;
     if (mode == 1 && p->n < ((int64_t)1 << 18)) return 0;   // launch-latency-bound sizes: the sort buys nothing
     return mode;
 }
@@ -1325,7 +1344,7 @@ static int ensure_mirror(vpm_vspace* vs, vpm_particles* p, int sort_mode, bool* 
     if (p->mirror_valid && !p->exposed && p->mirror_lo == vs->lo && p->mirror_hi == vs->hi && (p->mirror_has_w || !need_w)) return VPM_OK;
     VPM_CHECK(particles_sync_v(p));   // a rebuild starts from v in the caller's order: bring it up to date first
     *rebuilt = true;
-    const size_t bytes = sizeof(double) * (size_t)(p->n + (p->n & 1));
+    const size_t bytes = sizeof(double) * (size_t)(p->n > 0 ? p->n + (p->n & 1) : 2);
     const int sort_grid = ctx->sm_count * kSortGridPerSm;
     if (!p->sv) {
         cudaError_t e1 = cudaMalloc((void**)&p->sv, bytes), e2 = cudaMalloc((void**)&p->sinv, sizeof(unsigned) * (size_t)(p->n + 1));
@@ -1378,10 +1397,13 @@ int vpm_lb_rk438_steps_async(vpm_vspace* vs, vpm_particles* p, double nu, double
         vs->ent_rows = erow0 + nsteps + 1;
     }
     int sort_mode = lb_sort_mode(vs, p);
+    if (sort_mode < 0) return fail(VPM_ERR_UNSUPPORTED, "multi-GPU collision steppers need slabs below 2^32 particles per rank");
     bool rebuilt = false;
     if (sort_mode) {
         const int rc = ensure_mirror(vs, p, sort_mode, &rebuilt);
-        if (rc == VPM_ERR_NOMEM) sort_mode = 0;   // no room for the mirror (+20 B per particle): the histogram passes need none
+        // no room for the mirror (+20 B per particle): the histogram passes need none -- but a single rank must not change
+        // passes on its own (see lb_sort_mode), so with a communicator attached the error stands
+        if (rc == VPM_ERR_NOMEM && ctx->p2p.nranks <= 1 && !ctx->comm.comm) sort_mode = 0;
         else if (rc) return rc;
     }
     if (sort_mode) {
