@@ -544,7 +544,8 @@ __global__ void __launch_bounds__(kLbsThreads, 2) lbs_pass_kernel(const LbDev P)
     lb_cta_sync<true>();
     const int c_lo = s_rng[0], c_hi = s_rng[1];
     double* row = P.partials + (size_t)blockIdx.x * ncol;
-    for (int i = c_lo * C::NA + tid; i < (c_hi + 1) * C::NA; i += kBlock) row[i] = s_hist[i];
+    if (c_lo <= c_hi)   // (nothing deposited: c_lo is still INT_MAX -- no arithmetic on it)
+        for (int i = c_lo * C::NA + tid; i < (c_hi + 1) * C::NA; i += kBlock) row[i] = s_hist[i];
     if (tid == 0) {
         P.ranges[2 * blockIdx.x] = c_lo;
         P.ranges[2 * blockIdx.x + 1] = c_hi;   // c_lo > c_hi: nothing deposited
