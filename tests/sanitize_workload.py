@@ -120,6 +120,14 @@ def main():
                 assert np.abs(d.get("v") - vo).max() < 1e-10, (env, cons, uw)
     for k in ("VPM_TUNE_LBTMA", "VPM_TUNE_HM", "VPM_TUNE_LBFAT", "VPM_TUNE_LBSORT"):
         os.environ.pop(k, None)
+    # sorted passes whose CTAs deposit nothing at all (every particle outside the spline domain: only the ghost row is touched)
+    os.environ["VPM_TUNE_LBSORT"] = "2"
+    vout = 10.5 + np.random.default_rng(2).random(n)
+    d = vpm.ParticleDistribution(1, 1, n).set(np.zeros(n), vout, ww)
+    gi = vpm.GeometricIntegrator(vpm.LenardBernstein(d, vpm.CollisionEntropy(sd), nu=0.8), vpm.tspan_for(2, 0.02), 0.02)
+    vpm.run_(gi)
+    assert np.array_equal(d.get("v"), vout) and np.all(sd.coefficients == 0.0)   # f = f' = 0 outside the knots: nothing moves
+    os.environ.pop("VPM_TUNE_LBSORT", None)
     # entropy history (gather pass with the replicated table + the ENT phase of the field kernel)
     d = vpm.ParticleDistribution(1, 1, n).set(np.zeros(n), vv, ww)
     gi = vpm.GeometricIntegrator(vpm.ConservativeLenardBernstein(d, vpm.CollisionEntropy(sd), nu=0.8), vpm.tspan_for(2, 0.02), 0.02)
