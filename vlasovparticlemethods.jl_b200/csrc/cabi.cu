@@ -472,7 +472,8 @@ int vpm_particles_ptrs(vpm_particles* p, double** x, double** v, double** w)
 {
     VPM_REQUIRE(p, "vpm_particles_ptrs: p is NULL");
     VPM_CUDA(cudaSetDevice(p->ctx->device));
-    // ... or the velocities, at any later time: the velocity-sorted mirror of the collision steppers is rebuilt at every call from now on
+    // the caller may write x, v or w through these pointers at any later time: from now on the velocity-sorted mirror of the
+    // collision steppers is rebuilt (and v written back) at every call, and the Strang stepper's stagger is not carried
     if (x || v || w) {
         VPM_CHECK(mirror_invalidate(p));
         p->exposed = true;
