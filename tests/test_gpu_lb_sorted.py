@@ -88,7 +88,7 @@ def test_sorted_uniform_weights_and_entropy(vpm, oracle, perr, monkeypatch, cons
         perr("sorted_moment_history" + u + tag, (np.abs(gi.diagnostics[:, :2] - do) / dscale).max(), TOL)
 
 
-@pytest.mark.parametrize("K,nk", [(3, 33), (5, 12), (6, 25), (4, 101)])
+@pytest.mark.parametrize("K,nk", [(3, 33), (5, 12), (6, 25), (4, 101), (4, 201), (2, 64), (6, 140)])
 def test_sorted_other_grids(vpm, oracle, perr, monkeypatch, K, nk):
     """other spline orders and knot counts (the power sums run up to u^(K+1)); tolerance: the mass matrix's backward-error bound"""
     monkeypatch.setenv("VPM_TUNE_LBSORT", "2")
