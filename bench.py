@@ -395,7 +395,9 @@ class Bench:
         carry = os.environ.get("VPM_TUNE_VPCARRY", "1") != "0" and mode == 0
         kprof = min(args.steps, 20)
         call_bytes = BYTES_PER_STEP * kprof if carry else (BYTES_PER_STEP * (kprof - 1) + 64)
-        bytes_per_launch = call_bytes * n / max(pass_cnt, 1) if mode == 0 else BYTES_PER_STEP * n
+        if mode == 1:   # frozen field (the reference as shipped): one deposit pass per call (x, w: 16 B), then passes that read and
+            call_bytes = 32 * kprof + 16   # write x, v only (32 B: without diagnostics the weights are not needed)
+        bytes_per_launch = call_bytes * n / max(pass_cnt, 1)
         avg = pass_ms / max(pass_cnt, 1)
         achieved = bytes_per_launch / (avg * 1e-3) / 1e9
         traffic = None

@@ -833,9 +833,11 @@ int launch_vp_pass_k(vpm_ctx* ctx, const vpm_xspace* xs, const VpPass& p, int* g
     const bool p2 = (xs->nh & (xs->nh - 1)) == 0;
     const size_t tile_b = sizeof(double) * kTmaTile;
     if (ring && frozen_f) {  // no histograms: a deeper ring fits
-        smem += 4 * (p.use_uw ? 2 : 3) * tile_b + sizeof(uint64_t) * 2 * 4;
-        if (nodiag) kern = p.use_uw ? (p2 ? vp_pass_ring_kernel<K, kFrozenFlagsND, 3, 4, true, true> : vp_pass_ring_kernel<K, kFrozenFlagsND, 3, 4, false, true>)
-                                    : (p2 ? vp_pass_ring_kernel<K, kFrozenFlagsND, 3, 4, true, false> : vp_pass_ring_kernel<K, kFrozenFlagsND, 3, 4, false, false>);
+        // without diagnostics the frozen pass neither deposits nor sums K, M: the weights are not needed at all, so it runs
+        // the two-stream instantiation whatever the weights are (32 instead of 40 B per particle)
+        const bool no_w = p.use_uw || nodiag;
+        smem += 4 * (no_w ? 2 : 3) * tile_b + sizeof(uint64_t) * 2 * 4;
+        if (nodiag) kern = p2 ? vp_pass_ring_kernel<K, kFrozenFlagsND, 3, 4, true, true> : vp_pass_ring_kernel<K, kFrozenFlagsND, 3, 4, false, true>;
         else kern = p.use_uw ? (p2 ? vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, true, true> : vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, false, true>)
                              : (p2 ? vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, true, false> : vp_pass_ring_kernel<K, kFrozenFlags, 3, 4, false, false>);
     } else if (ring && p.use_uw) {
